@@ -1,0 +1,246 @@
+"""LMCacheEngine -- store()/retrieve() with the reference's signatures and semantics
+(lmcache/cache_engine.py:16-436), rebuilt around the CUDA hot path:
+
+  * chunk hashes: one b200kv_sha256_chain launch on the token ids (no per-chunk tokens.cpu() sync,
+    cache_engine.py:58-96); digests are bit-identical to hashlib's.
+  * blob pack + chunking: one b200kv_pack_chunks gather from the caller's 2L tensors straight into per-chunk
+    blobs (replaces 3x torch.stack + permute + split + .contiguous() per chunk, :98-161).
+  * retrieve assembles chunks into one preallocated blob (replaces torch.cat, :362-368).
+Prefix-match / mask semantics are unchanged: chunks are matched front to back through `contains`, the first
+miss ends the match, everything after the first missing chunk is (re)stored (:183-208).
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+from typing import Dict, Iterable, List, Optional, Tuple, Union
+
+import torch
+
+from lmcache_b200 import _native as N
+from lmcache_b200.codec import KvView, PinnedBuffer
+from lmcache_b200.config import LMCacheEngineConfig, LMCacheEngineMetadata
+from lmcache_b200.logging import init_logger
+from lmcache_b200.storage_backend import CreateStorageBackend
+from lmcache_b200.utils import CacheEngineKey, KVCache, _lmcache_nvtx_annotate
+
+logger = init_logger(__name__)
+
+
+def sha256_prefix_chain(tokens: torch.Tensor, chunk_size: int, seq_offsets: Optional[List[int]] = None) -> List[str]:
+    """Hex digests h_i = sha256(hex(h_{i-1}) || bytes(chunk_i)) for every chunk of every sequence
+    (cache_engine.py:58-96), computed on the GPU.  tokens: 1-D integer tensor on any device; the bytes hashed
+    are the tensor's native little-endian dtype, as in the reference.  seq_offsets: token boundaries of
+    independent sequences (default: one sequence)."""
+    N.require_cuda()
+    if tokens.dim() != 1:
+        raise ValueError(f"Invalid shape of tokens: {tokens.shape}")
+    n = tokens.shape[0]
+    offs = [0, n] if seq_offsets is None else list(seq_offsets)
+    n_seq = len(offs) - 1
+    nchunks = sum((offs[i + 1] - offs[i] + chunk_size - 1) // chunk_size for i in range(n_seq))
+    if nchunks == 0:
+        return []
+    dev_tokens = tokens if tokens.is_cuda else tokens.to("cuda", non_blocking=False)
+    dev_tokens = dev_tokens.contiguous()
+    out = PinnedBuffer(32 * nchunks)   # the kernel writes digests straight into mapped host memory
+    try:
+        with torch.cuda.device(dev_tokens.device):
+            sp = torch.cuda.current_stream().cuda_stream
+            N.check(N.lib().b200kv_sha256_chain(ctypes.c_void_p(dev_tokens.data_ptr()), dev_tokens.element_size(),
+                                                N.i64_array(offs), n_seq, chunk_size, ctypes.c_void_p(out.dev_ptr),
+                                                sp), "sha256_chain")
+            N.check(N.lib().b200kv_stream_sync(sp), "stream_sync")
+        raw = bytes(out.view(0, 32 * nchunks))
+    finally:
+        out.close()
+    return [raw[32 * i: 32 * i + 32].hex() for i in range(nchunks)]
+
+
+class LMCacheEngine:
+
+    def __init__(self, config: LMCacheEngineConfig, metadata: LMCacheEngineMetadata):
+        self.config = config
+        self.metadata = metadata
+        self.chunk_size = config.chunk_size
+        self.save_decode_cache = config.save_decode_cache
+        self.engine_ = CreateStorageBackend(config, metadata)
+        logger.debug(f"Current storage backend type {type(self.engine_)}")
+
+    # ------------------------------------------------------------------ keys / hashes
+    def _make_key(self, chunk_hash: str, fmt: str) -> CacheEngineKey:
+        return CacheEngineKey(fmt, self.metadata.model_name, self.metadata.world_size, self.metadata.worker_id,
+                              chunk_hash)
+
+    def _num_tokens_in_kv(self, kv_tensors: Union[KVCache, torch.Tensor], fmt: str) -> int:
+        if fmt == "huggingface":
+            return kv_tensors[0][0].shape[1]
+        elif fmt == "vllm":
+            return kv_tensors[0][0].shape[0]
+        raise ValueError(f"Invalid format: {fmt}")
+
+    def _get_init_hash(self) -> str:
+        return ""
+
+    def _prefix_hash(self, tokens: torch.Tensor, num_skip_chunk: Optional[int] = 0) -> List[str]:
+        """All chunk digests of `tokens` (the whole chain is hashed, then the first num_skip_chunk digests are
+        dropped, like cache_engine.py:86-96)."""
+        return sha256_prefix_chain(tokens, self.chunk_size)[num_skip_chunk:]
+
+    # ------------------------------------------------------------------ blob helpers
+    def _chunk_shape(self, view: KvView, t: int, fmt: str) -> Tuple[int, ...]:
+        return (view.L, 2, t, view.H, view.D) if fmt == "vllm" else (view.L, 2, view.H, t, view.D)
+
+    def _pack_chunks(self, view: KvView, tok_begin: int, fmt: str) -> List[torch.Tensor]:
+        """Gather tokens [tok_begin, T) of the kv tuple into contiguous per-chunk blobs with one kernel."""
+        n_tok = view.ntokens - tok_begin
+        if n_tok <= 0:
+            return []
+        cs = self.chunk_size
+        n_chunks = (n_tok + cs - 1) // cs
+        last = n_tok - (n_chunks - 1) * cs
+        per_tok = 2 * view.L * view.H * view.D          # halfs per token over all planes
+        stride_elems = per_tok * cs
+        buf = torch.empty(n_chunks * stride_elems, dtype=view.dtype, device=view.device)
+        with torch.cuda.device(view.device):
+            N.check(N.lib().b200kv_pack_chunks(ctypes.byref(view.desc), tok_begin, n_chunks, cs, last,
+                                               1 if fmt == "huggingface" else 0, ctypes.c_void_p(buf.data_ptr()),
+                                               stride_elems * buf.element_size(),
+                                               torch.cuda.current_stream().cuda_stream), "pack_chunks")
+        chunks = []
+        for j in range(n_chunks):
+            t = cs if j < n_chunks - 1 else last
+            chunks.append(buf[j * stride_elems: j * stride_elems + per_tok * t].view(self._chunk_shape(view, t, fmt)))
+        return chunks
+
+    @staticmethod
+    def _as_cuda_kv(kv_tensors_raw: KVCache) -> KVCache:
+        if kv_tensors_raw[0][0].is_cuda:
+            return kv_tensors_raw
+        return tuple((k.cuda(), v.cuda()) for k, v in kv_tensors_raw)
+
+    def _blob_to_tuple_kv(self, blob: torch.Tensor) -> KVCache:
+        return tuple((layer[0], layer[1]) for layer in torch.unbind(blob, dim=0))
+
+    # ------------------------------------------------------------------ store
+    @_lmcache_nvtx_annotate
+    @torch.no_grad()
+    def store(self, tokens: torch.Tensor, kv_tensors_raw: KVCache, skip_existing=True, blocking=True) -> None:
+        """Store the KV cache of `tokens`.  kv_tensors_raw: nested tuple of per-layer (K, V), each
+        [num_tokens, num_heads, head_size] (vllm) or [num_heads, num_tokens, head_size] (huggingface),
+        without a batch dimension."""
+        start_time = time.perf_counter()
+        fmt = self.metadata.fmt
+        assert len(tokens.shape) == 1, f"Invalid shape of tokens: {tokens.shape}"
+        assert len(kv_tensors_raw) > 0, "Empty kv_tensors"
+        assert len(tokens) == self._num_tokens_in_kv(kv_tensors_raw, fmt), \
+            "Number of tokens in the kv cache does not match the input tokens"
+
+        chunk_hashes = self._prefix_hash(tokens)
+        start_chunk_idx = 0
+        if skip_existing:
+            # prefix match: first chunk whose key is absent; everything from there on is stored
+            start_chunk_idx = len(chunk_hashes)
+            for i, h in enumerate(chunk_hashes):
+                if not self.engine_.contains(self._make_key(h, fmt)):
+                    start_chunk_idx = i
+                    break
+        n_chunks = 0
+        if start_chunk_idx < len(chunk_hashes):
+            view = KvView.from_tuple(self._as_cuda_kv(kv_tensors_raw), fmt)
+            chunks = self._pack_chunks(view, start_chunk_idx * self.chunk_size, fmt)
+            end_make_chunks = time.perf_counter()
+            n_chunks = self.engine_.batched_put(
+                ((self._make_key(h, fmt), c) for h, c in zip(chunk_hashes[start_chunk_idx:], chunks)),
+                blocking=blocking)
+        else:
+            end_make_chunks = time.perf_counter()
+        end_time = time.perf_counter()
+        logger.info(f"Stored/updated {n_chunks} chunks, total time {end_time - start_time:.2f}s, "
+                    f"make chunks time {end_make_chunks - start_time:.2f}s")
+
+    # ------------------------------------------------------------------ retrieve
+    @_lmcache_nvtx_annotate
+    @torch.no_grad()
+    def retrieve(self, tokens: torch.Tensor, mask: Optional[torch.Tensor] = None) -> Tuple[KVCache, torch.Tensor]:
+        """Retrieve the longest cached prefix of `tokens` (optionally only the suffix selected by a boolean
+        suffix `mask`).  Returns (kv tuple -- empty tuple on a total miss, ret_mask marking retrieved tokens)."""
+        num_skip_chunk = 0
+        num_skip_tok = 0
+        ret_mask = torch.ones_like(tokens, dtype=torch.bool)
+        if mask is not None:
+            num_skip_tok = int(len(mask) - torch.sum(mask))
+            num_skip_chunk = num_skip_tok // self.chunk_size
+        ret_mask[:num_skip_tok] = False
+
+        st = time.perf_counter()
+        fmt = self.metadata.fmt
+        if fmt not in ("vllm", "huggingface"):
+            raise ValueError(f"Invalid format: {fmt}")
+        chunk_hashes = self._prefix_hash(tokens, num_skip_chunk)
+        retrieved: List[torch.Tensor] = []
+        for chunk in self.engine_.batched_get(self._make_key(h, fmt) for h in chunk_hashes):
+            if chunk is None:
+                break
+            retrieved.append(chunk)
+        if len(retrieved) == 0:
+            logger.info("Retrieved 0 chunks")
+            ret_mask[:] = False
+            return (), ret_mask
+
+        # assemble into one blob; drop the extra leading tokens of the first chunk (suffix mask)
+        tdim = 2 if fmt == "vllm" else 3
+        extra = num_skip_tok - num_skip_chunk * self.chunk_size
+        sizes = [c.shape[tdim] for c in retrieved]
+        total = sum(sizes) - extra
+        first = retrieved[0]
+        shape = list(first.shape)
+        shape[tdim] = total
+        blob = torch.empty(shape, dtype=first.dtype, device=first.device)
+        pos = 0
+        for i, c in enumerate(retrieved):
+            src = c.narrow(tdim, extra, sizes[i] - extra) if i == 0 else c
+            n = src.shape[tdim]
+            blob.narrow(tdim, pos, n).copy_(src)
+            pos += n
+        ret = self._blob_to_tuple_kv(blob)
+        retrieved_token_count = total
+        logger.info(f"Retrieved {len(retrieved)} chunks ({retrieved_token_count} tokens in total) -- "
+                    f"elapsed time {time.perf_counter() - st}")
+        ret_mask[num_skip_tok + retrieved_token_count:] = False
+        return ret, ret_mask
+
+    def close(self):
+        self.engine_.close()
+
+
+class LMCacheEngineBuilder:
+    """Process-wide engine registry (cache_engine.py:387-436)."""
+    _instances: Dict[str, LMCacheEngine] = {}
+    _cfgs: Dict[str, LMCacheEngineConfig] = {}
+    _metadatas: Dict[str, LMCacheEngineMetadata] = {}
+
+    @classmethod
+    def get_or_create(cls, instance_id: str, config: LMCacheEngineConfig,
+                      metadata: LMCacheEngineMetadata) -> LMCacheEngine:
+        if instance_id not in cls._instances:
+            engine = LMCacheEngine(config, metadata)
+            cls._instances[instance_id] = engine
+            cls._cfgs[instance_id] = config
+            cls._metadatas[instance_id] = metadata
+            return engine
+        if cls._cfgs[instance_id] != config or cls._metadatas[instance_id] != metadata:
+            raise ValueError(f"Instance {instance_id} already exists with a different configuration or metadata.")
+        return cls._instances[instance_id]
+
+    @classmethod
+    def get(cls, instance_id: str) -> Optional[LMCacheEngine]:
+        return cls._instances.get(instance_id)
+
+    @classmethod
+    def destroy(cls, instance_id: str) -> None:
+        if instance_id in cls._instances:
+            cls._instances[instance_id].close()
+            cls._instances.pop(instance_id, None)
+            cls._cfgs.pop(instance_id, None)
+            cls._metadatas.pop(instance_id, None)

@@ -1,0 +1,344 @@
+"""Host-side driver of the CUDA codec: descriptors, buffers, and batched encode / decode calls.
+
+This is plumbing above the C ABI (include/b200kv.h): PyTorch supplies device memory and streams,
+libb200kv does all the work.  The serde plugins (storage_backend/serde/cachegen_*.py) and the
+engine fast paths are thin layers over `CacheGenCodec`.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from lmcache_b200 import _native as N
+
+_DTYPE_CODE = {torch.bfloat16: N.DT_BF16, torch.float16: N.DT_FP16}
+_CODE_DTYPE = {v: k for k, v in _DTYPE_CODE.items()}
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream]) -> int:
+    return (stream if stream is not None else torch.cuda.current_stream()).cuda_stream
+
+
+class PinnedBuffer:
+    """Page-locked, device-mapped host memory from b200kv_pinned_alloc (replaces the reference's
+    pageable .to("cpu") staging, local_backend.py:82-100)."""
+
+    def __init__(self, nbytes: int):
+        N.require_cuda()
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        N.check(N.lib().b200kv_pinned_alloc(ctypes.byref(p), self.nbytes), "pinned_alloc")
+        self.host_ptr = p.value
+        d = ctypes.c_void_p()
+        N.check(N.lib().b200kv_host_device_ptr(p, ctypes.byref(d)), "host_device_ptr")
+        self.dev_ptr = d.value
+        self._arr = (ctypes.c_uint8 * self.nbytes).from_address(self.host_ptr)
+
+    def view(self, offset: int = 0, nbytes: Optional[int] = None) -> memoryview:
+        n = self.nbytes - offset if nbytes is None else nbytes
+        return memoryview(self._arr)[offset:offset + n]
+
+    def close(self):
+        if self.host_ptr:
+            self._arr = None
+            N.lib().b200kv_pinned_free(ctypes.c_void_p(self.host_ptr))
+            self.host_ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class KvView:
+    """A KV source / destination for the native library: either one strided blob tensor or the engine's
+    tuple of 2L per-layer tensors (no stack / permute / contiguous copies).  Keeps the tensors alive."""
+
+    def __init__(self, desc: N.KvDesc, keep, ntokens: int, device: torch.device, dtype: torch.dtype):
+        self.desc = desc
+        self._keep = keep
+        self.ntokens = ntokens
+        self.device = device
+        self.dtype = dtype
+
+    @property
+    def L(self): return self.desc.L
+    @property
+    def H(self): return self.desc.H
+    @property
+    def D(self): return self.desc.D
+
+    @staticmethod
+    def _code(dtype: torch.dtype) -> int:
+        if dtype not in _DTYPE_CODE:
+            raise TypeError(f"KV dtype must be bfloat16 or float16, got {dtype}")
+        return _DTYPE_CODE[dtype]
+
+    @staticmethod
+    def from_blob(blob: torch.Tensor, fmt: str) -> "KvView":
+        """blob: [L,2,T,H,D] (vllm) or [L,2,H,T,D] (huggingface); any strides with a contiguous last dim."""
+        if blob.dim() != 5 or blob.shape[1] != 2:
+            raise ValueError(f"expected a [L,2,..] KV blob, got {tuple(blob.shape)}")
+        if not blob.is_cuda:
+            raise RuntimeError("KV blob must live on a CUDA device (no CPU fallback)")
+        if blob.stride(4) != 1:
+            blob = blob.contiguous()
+        if fmt == "vllm":
+            L, _, T, H, D = blob.shape
+            sL, sKV, sT, sH, _ = blob.stride()
+        elif fmt == "huggingface":
+            L, _, H, T, D = blob.shape
+            sL, sKV, sH, sT, _ = blob.stride()
+        else:
+            raise ValueError(f"Invalid format: {fmt}")
+        d = N.KvDesc()
+        d.base = blob.data_ptr()
+        d.planes = None
+        d.sL, d.sKV, d.sT, d.sH = sL, sKV, sT, sH
+        d.L, d.H, d.D = L, H, D
+        d.dtype = KvView._code(blob.dtype)
+        return KvView(d, blob, T, blob.device, blob.dtype)
+
+    @staticmethod
+    def from_tuple(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], fmt: str) -> "KvView":
+        """kv: L pairs of [T,H,D] (vllm) / [H,T,D] (huggingface) tensors, as passed to LMCacheEngine.store."""
+        L = len(kv)
+        if L == 0:
+            raise ValueError("Empty kv_tensors")
+        ref = kv[0][0]
+        if not ref.is_cuda:
+            raise RuntimeError("KV tensors must live on a CUDA device (no CPU fallback)")
+        keep = []
+        ptrs = (ctypes.c_void_p * (2 * L))()
+        for l, (k, v) in enumerate(kv):
+            for kvi, t in ((0, k), (1, v)):
+                if t.shape != ref.shape or t.dtype != ref.dtype or t.device != ref.device:
+                    raise ValueError("all K/V tensors must share shape, dtype and device")
+                if t.stride() != ref.stride() or t.stride(2) != 1:
+                    t = t.contiguous()
+                    if t.stride() != ref.stride():
+                        return KvView.from_tuple(tuple((a.contiguous(), b.contiguous()) for a, b in kv), fmt)
+                keep.append(t)
+                ptrs[kvi * L + l] = t.data_ptr()
+        if fmt == "vllm":
+            T, H, D = ref.shape
+            sT, sH, _ = ref.stride()
+        elif fmt == "huggingface":
+            H, T, D = ref.shape
+            sH, sT, _ = ref.stride()
+        else:
+            raise ValueError(f"Invalid format: {fmt}")
+        d = N.KvDesc()
+        d.base = None
+        d.planes = ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p))
+        d.sL = d.sKV = 0
+        d.sT, d.sH = sT, sH
+        d.L, d.H, d.D = L, H, D
+        d.dtype = KvView._code(ref.dtype)
+        return KvView(d, (keep, ptrs), T, ref.device, ref.dtype)
+
+
+def parse_header(buf) -> N.Header:
+    """Validate and return the 64-byte header of a B2KV container (bytes / bytearray / memoryview)."""
+    mv = memoryview(buf)
+    if mv.nbytes < N.HEADER_BYTES:
+        raise ValueError("buffer too small for a B2KV container")
+    hd = N.Header.from_buffer_copy(bytes(mv[:N.HEADER_BYTES]))
+    if hd.magic != N.MAGIC:
+        raise ValueError("not a B2KV container (bad magic)")
+    if hd.version != 1:
+        raise ValueError(f"unsupported B2KV version {hd.version}")
+    if hd.total_bytes > mv.nbytes:
+        raise ValueError("truncated B2KV container")
+    if hd.status != 0:
+        raise ValueError(f"B2KV container carries encoder error status {hd.status}")
+    return hd
+
+
+@dataclass
+class EncodedBatch:
+    """Device-resident result of one encode call: n containers at `stride` in `buf`."""
+    buf: torch.Tensor            # uint8 device staging
+    stride: int
+    sizes: List[int]             # total bytes per container (host, valid after the call returns)
+
+    def container(self, j: int) -> torch.Tensor:
+        return self.buf[j * self.stride: j * self.stride + self.sizes[j]]
+
+
+class CacheGenCodec:
+    """Batched CacheGen encode / decode on the current CUDA device.
+
+    Thread model: one encoder and one decoder may run concurrently from different threads (the
+    reference's put_worker / deserialize_worker, remote_backend.py:61-69,234-246); each direction owns
+    its buffers and is guarded by its own lock.
+    """
+
+    def __init__(self, model_name: str):
+        from lmcache_b200.storage_backend.serde.cachegen_basics import CacheGenConfig
+        N.require_cuda()
+        self.config = CacheGenConfig.from_model_name(model_name)
+        kb, vb = self.config.key_bins_list(), self.config.value_bins_list()
+        self.nlayers = len(kb)
+        self._kb = N.float_array(kb)
+        self._vb = N.float_array(vb)
+        self._enc_lock = threading.Lock()
+        self._dec_lock = threading.Lock()
+        self._enc_ws: Optional[torch.Tensor] = None
+        self._dec_ws: Optional[torch.Tensor] = None
+        self._enc_out: Optional[torch.Tensor] = None
+        self._sizes: Optional[PinnedBuffer] = None
+        self._dec_in: Optional[torch.Tensor] = None
+        self._dec_event: Optional[torch.cuda.Event] = None
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _grow(t: Optional[torch.Tensor], nbytes: int, device) -> torch.Tensor:
+        if t is None or t.numel() < nbytes or t.device != device:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return t
+
+    def out_stride(self, L: int, H: int, D: int, chunk_tokens: int) -> int:
+        """Bytes reserved per container.  Chunks of <= 256 tokens are coded with their own empirical CDF,
+        so a stream costs <= 8 bits/symbol (+ flush); larger chunks may reach 16 bits/symbol."""
+        lo = N.container_layout(L, H, D, chunk_tokens)
+        if chunk_tokens <= N.GROUP_TOKENS:
+            return (lo.fixed_bytes + 2 * L * H * D * (chunk_tokens + 4) + 16 + 15) & ~15
+        return lo.max_total_bytes
+
+    # ------------------------------------------------------------------ encode
+    def encode(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
+               stream: Optional[torch.cuda.Stream] = None, out: Optional[torch.Tensor] = None) -> EncodedBatch:
+        """Encode tokens [tok_begin, tok_begin + n_tokens) of `view` as ceil(n_tokens / chunk_size) containers.
+        Blocks until the containers' sizes are known (one event wait); payloads stay on the device."""
+        if n_tokens <= 0:
+            raise ValueError("n_tokens must be positive")
+        if view.L > self.nlayers:
+            raise ValueError(f"KV has {view.L} layers but the bin table of this model has {self.nlayers}")
+        n_chunks = (n_tokens + chunk_size - 1) // chunk_size
+        last = n_tokens - (n_chunks - 1) * chunk_size
+        stride = self.out_stride(view.L, view.H, view.D, chunk_size)
+        lib = N.lib()
+        with self._enc_lock, torch.cuda.device(view.device):
+            ws_bytes = lib.b200kv_encode_workspace_bytes(view.L, view.H, view.D, chunk_size, n_chunks)
+            self._enc_ws = self._grow(self._enc_ws, ws_bytes, view.device)
+            if out is None:
+                self._enc_out = self._grow(self._enc_out, stride * n_chunks, view.device)
+                out = self._enc_out
+            elif out.numel() < stride * n_chunks:
+                raise ValueError("encode output buffer too small")
+            if self._sizes is None or self._sizes.nbytes < 8 * n_chunks:
+                self._sizes = PinnedBuffer(max(4096, 8 * n_chunks))
+            sp = _stream_ptr(stream)
+            N.check(lib.b200kv_encode_chunks(ctypes.byref(view.desc), tok_begin, n_chunks, chunk_size, last,
+                                             self._kb, self._vb, out.data_ptr(), stride, self._sizes.dev_ptr,
+                                             self._enc_ws.data_ptr(), self._enc_ws.numel(), sp), "encode_chunks")
+            N.check(lib.b200kv_stream_sync(sp), "stream_sync")
+            sizes = list((ctypes.c_uint64 * n_chunks).from_address(self._sizes.host_ptr))
+            # header status is checked on the device copy lazily by consumers; check it here via sizes sanity
+            for j, s in enumerate(sizes):
+                if s < N.HEADER_BYTES or s > stride:
+                    raise N.NativeError(f"encoder produced an invalid container size {s} for chunk {j}")
+            return EncodedBatch(out, stride, [int(s) for s in sizes])
+
+    def encode_to_host(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
+                       stream: Optional[torch.cuda.Stream] = None) -> List[bytes]:
+        """encode + one device->host copy per container into pinned memory, returned as immutable bytes."""
+        batch = self.encode(view, tok_begin, n_tokens, chunk_size, stream)
+        total = sum((s + 15) & ~15 for s in batch.sizes)
+        pin = PinnedBuffer(total)
+        lib = N.lib()
+        sp = _stream_ptr(stream)
+        offs, o = [], 0
+        with torch.cuda.device(view.device):
+            for j, s in enumerate(batch.sizes):
+                N.check(lib.b200kv_copy_async(pin.host_ptr + o, batch.buf.data_ptr() + j * batch.stride, s, sp), "copy")
+                offs.append(o)
+                o += (s + 15) & ~15
+            N.check(lib.b200kv_stream_sync(sp), "stream_sync")
+        outs = [bytes(pin.view(offs[j], batch.sizes[j])) for j in range(len(offs))]
+        for b in outs:
+            hd = parse_header(b)   # raises on encoder error status
+            del hd
+        pin.close()
+        return outs
+
+    # ------------------------------------------------------------------ decode
+    def decode(self, containers: Sequence[Union[bytes, bytearray, memoryview, torch.Tensor]], dst: KvView,
+               dst_tok: Sequence[int], stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Decode containers into `dst` at token offsets `dst_tok` (asynchronous on `stream`).
+        Host containers are uploaded first; device uint8 tensors are used in place."""
+        n = len(containers)
+        if n == 0:
+            return
+        lib = N.lib()
+        heads = []
+        for c in containers:
+            if isinstance(c, torch.Tensor):
+                hb = c[:N.HEADER_BYTES].cpu().numpy().tobytes() if c.is_cuda else c[:N.HEADER_BYTES].numpy().tobytes()
+                hd = N.Header.from_buffer_copy(hb)
+                if hd.magic != N.MAGIC or hd.status != 0 or hd.total_bytes > c.numel():
+                    raise ValueError("bad B2KV container tensor")
+            else:
+                hd = parse_header(c)
+            if (hd.L, hd.H, hd.D) != (dst.L, dst.H, dst.D):
+                raise ValueError(f"container shape L/H/D={hd.L}/{hd.H}/{hd.D} does not match destination "
+                                 f"{dst.L}/{dst.H}/{dst.D}")
+            heads.append(hd)
+        max_dtype = heads[0].max_dtype
+        if any(h.max_dtype != max_dtype for h in heads):
+            raise ValueError("containers of one decode call must share max_dtype")
+        tmax = max(h.ntokens for h in heads)
+        with self._dec_lock, torch.cuda.device(dst.device):
+            tstream = stream if stream is not None else torch.cuda.current_stream()
+            sp = tstream.cuda_stream
+            if self._dec_event is not None:
+                # staging / workspace are reused: order after the previous decode, and never free a
+                # buffer a kernel may still be reading
+                need_in = sum(((int(h.total_bytes) + 15) & ~15) + 16 for h in heads) + 16
+                need_ws = lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n)
+                if ((self._dec_in is not None and self._dec_in.numel() < need_in) or
+                        (self._dec_ws is not None and self._dec_ws.numel() < need_ws)):
+                    self._dec_event.synchronize()
+                else:
+                    tstream.wait_event(self._dec_event)
+            all_dev = all(isinstance(c, torch.Tensor) and c.is_cuda for c in containers)
+            offsets = []
+            if all_dev and n == 1:
+                base_ptr = containers[0].data_ptr()
+                if base_ptr % 16:
+                    raise ValueError("device container must be 16-byte aligned")
+                offsets = [0]
+            else:
+                total = sum(((int(h.total_bytes) + 15) & ~15) + 16 for h in heads)
+                self._dec_in = self._grow(self._dec_in, total + 16, dst.device)
+                base_ptr = self._dec_in.data_ptr()
+                o = 0
+                for c, h in zip(containers, heads):
+                    nb = int(h.total_bytes)
+                    if isinstance(c, torch.Tensor):
+                        keep = c
+                        src_ptr = c.data_ptr()
+                    else:
+                        keep = np.frombuffer(c, dtype=np.uint8, count=nb)   # zero-copy view of bytes/bytearray/memoryview
+                        src_ptr = keep.ctypes.data
+                    # pageable sources are staged by the driver before the call returns
+                    N.check(lib.b200kv_copy_async(base_ptr + o, src_ptr, nb, sp), "copy")
+                    del keep
+                    offsets.append(o)
+                    o += ((nb + 15) & ~15) + 16
+            ws_bytes = lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n)
+            self._dec_ws = self._grow(self._dec_ws, ws_bytes, dst.device)
+            N.check(lib.b200kv_decode_chunks(base_ptr, N.i64_array(offsets), N.i32_array([h.ntokens for h in heads]),
+                                             N.i64_array(list(dst_tok)), n, int(max_dtype), ctypes.byref(dst.desc),
+                                             self._kb, self._vb, self._dec_ws.data_ptr(), self._dec_ws.numel(), sp),
+                    "decode_chunks")
+            if self._dec_event is None:
+                self._dec_event = torch.cuda.Event()
+            self._dec_event.record(tstream)

@@ -1,0 +1,328 @@
+// ac_core.cuh -- arithmetic shared by every codec kernel: half conversions, the bit-exact
+// CacheGen quantiser / dequantiser, the CDF normalisation and the arithmetic-coder state machines.
+//
+// Everything here is __host__ __device__ so that tests/hostsim can compile the *same* functions with
+// g++ and check them against the oracle on the CPU (test infrastructure only; the product library
+// only ever runs them inside CUDA kernels).
+//
+// Normative behaviour (reference file:line, relative to the LMCache v0.1.2 tree):
+//   quantise    lmcache/storage_backend/serde/cachegen_encoder.py:40-61   fp32 div, mul, add each rounded
+//   dequantise  lmcache/storage_backend/serde/cachegen_decoder.py:24-35   fp32 sub, div, mul each rounded
+//   CDF         cachegen_encoder.py:95-126,185-196 (torch-CPU semantics: fp32 n/t, double cumsum)
+//   coder       torchac lineage as called at cachegen_encoder.py:255-260 / cachegen_decoder.py:65-66
+//               (32-bit low/high, 16-bit CDF, E1/E2/E3 renormalisation, MSB-first bit packing)
+//
+// The coder below produces exactly the bit-by-bit reference bitstream but renormalises in two
+// count-leading-zeros batches per symbol instead of a bit loop:
+//   n = clz(low ^ high)                 E1/E2 shifts: the n leading bits agree and are emitted
+//   m = clz(((~low | high) << 1) | 1)   E3 shifts: m more "pending" bits
+// and the decoder finds the symbol with a 5-step search on the products (span * cdf[s]) >> 16, which
+// is equivalent to the reference's 64-bit division + binary search on the CDF.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b200kv {
+
+constexpr int kLp = 33;       // CDF entries per stream
+constexpr int kMaxSym = 31;   // Lp - 2
+constexpr int kGroup = 256;   // tokens per coder group
+
+// ---------------------------------------------------------------- bit helpers
+B2_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } v; v.f = f; return v.u;
+#endif
+}
+B2_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } v; v.u = u; return v.f;
+#endif
+}
+B2_HD uint32_t clz32(uint32_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)x);
+#else
+    return (uint32_t)__builtin_clz(x);
+#endif
+}
+
+// fp32 ops that must not be contracted / reordered
+B2_HD float fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b; return r;
+#endif
+}
+B2_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+B2_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+B2_HD float frint(float a) {   // round half to even
+#if defined(__CUDA_ARCH__)
+    return rintf(a);
+#else
+    return __builtin_nearbyintf(a);
+#endif
+}
+
+// ---------------------------------------------------------------- half <-> float (bit patterns)
+B2_HD float bf16_to_float(uint16_t h) { return u2f((uint32_t)h << 16); }
+
+B2_HD uint16_t float_to_bf16(float f) {  // RNE, NaN stays NaN (matches torch .to(bfloat16))
+    uint32_t u = f2u(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x0040u);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+B2_HD float fp16_to_float(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1fu;
+    uint32_t man = h & 0x3ffu;
+    if (exp == 0) {
+        if (man == 0) return u2f(sign);
+        // subnormal: value = man * 2^-24
+        float v = (float)man * 5.9604644775390625e-08f;
+        return u2f(f2u(v) | sign);
+    }
+    if (exp == 31) return u2f(sign | 0x7f800000u | (man << 13));
+    return u2f(sign | ((exp + 112u) << 23) | (man << 13));
+}
+
+B2_HD uint16_t float_to_fp16(float f) {  // RNE with overflow to inf, subnormals, NaN kept (torch .to(float16))
+    uint32_t u = f2u(f);
+    uint32_t sign = (u >> 16) & 0x8000u;
+    uint32_t a = u & 0x7fffffffu;
+    if (a > 0x7f800000u) return (uint16_t)(sign | 0x7e00u | ((a >> 13) & 0x3ffu));  // NaN
+    if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);   // >= 65520 rounds to inf (also inf)
+    if (a < 0x38800000u) {                                     // < 2^-14: subnormal or zero
+        if (a < 0x33000000u) return (uint16_t)sign;            // < 2^-25 -> 0 (2^-25 itself ties to even = 0)
+        // value = a_float ; result mantissa = rne(a_float * 2^24)
+        uint32_t e = a >> 23;                    // biased exponent (102..112)
+        uint32_t m = (a & 0x7fffffu) | 0x800000u;
+        uint32_t shift = 126u - e;               // 14..24 : drop this many bits of the 24-bit mantissa
+        uint32_t r = m >> shift;
+        uint32_t rem = m & ((1u << shift) - 1u);
+        uint32_t half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (r & 1u))) r++;
+        return (uint16_t)(sign | r);
+    }
+    uint32_t r = a - 0x38000000u;                // rebias exponent (127 -> 15)
+    uint32_t lsb = (r >> 13) & 1u;
+    r += 0xfffu + lsb;
+    return (uint16_t)(sign | (r >> 13));
+}
+
+B2_HD float half_to_float(uint16_t h, int dtype) { return dtype ? fp16_to_float(h) : bf16_to_float(h); }
+B2_HD uint16_t float_to_half(float f, int dtype) { return dtype ? float_to_fp16(f) : float_to_bf16(f); }
+
+// ---------------------------------------------------------------- quantise (a6) / dequantise (a11)
+// factor = MAX / float(max_half)            (one fp32 division per (plane, token))
+B2_HD float quant_factor(float maxq, float row_max) { return fdiv(maxq, row_max); }
+
+// symbol = int8( round_half_even( x * factor + MAX ) ), NaN -> 0
+B2_HD uint32_t quant_symbol(float x, float factor, float maxq) {
+    float q = frint(fadd(fmul(x, factor), maxq));
+    if (q != q) return 0u;
+    return (uint32_t)(int)q & 0xffu;
+}
+
+// LUT entry: (sym - C) / C ; value = lut * float(max_half)
+B2_HD float dequant_lut(uint32_t sym, float cq) { return fdiv(fadd((float)sym, -cq), cq); }
+B2_HD float dequant_value(float lut, float row_max) { return fmul(lut, row_max); }
+
+// ---------------------------------------------------------------- CDF normalisation (a7)
+// counts n[0..32] over t tokens -> cdf[0..32] as uint16 bit patterns (int16 tensor in the reference).
+// Sequential state so a caller can stream it: feed counts in order.
+struct CdfAccum {
+    double cum;
+    float prev;
+    float tf;
+    B2_HD void init(int t) { cum = 0.0; prev = 0.0f; tf = (float)t; }
+    // returns cdf[i] for the i-th call (i = 0..32), then absorbs n_i
+    B2_HD uint16_t next(uint32_t i, uint32_t n_i) {
+        float r = frint(fmul(prev, 65504.0f));
+        uint16_t v = (uint16_t)((uint32_t)(int)r + i);
+        cum += (double)fdiv((float)n_i, tf);
+        prev = (float)cum;
+        return v;
+    }
+};
+
+// ---------------------------------------------------------------- arithmetic encoder (a8)
+struct EncState {
+    uint32_t low, high, pending;
+    uint64_t acc;   // bit accumulator, newest bits at the bottom
+    uint32_t nb;    // valid bits in acc (< 32 between calls)
+    B2_HD void init() { low = 0u; high = 0xFFFFFFFFu; pending = 0u; acc = 0ull; nb = 0u; }
+};
+
+// Sink concept: void put_word(uint32_t w)  -- w holds 32 stream bits, first bit in the MSB.
+template <class Sink>
+B2_HD void enc_put_bits(EncState& st, uint32_t v, uint32_t k, Sink& sink) {   // 0 <= k <= 32, v < 2^k
+    st.acc = (st.acc << k) | (uint64_t)v;
+    st.nb += k;
+    if (st.nb >= 32u) {
+        st.nb -= 32u;
+        sink.put_word((uint32_t)(st.acc >> st.nb));
+    }
+}
+
+template <class Sink>
+B2_HD void enc_bit_and_pending(EncState& st, uint32_t bit, Sink& sink) {
+    enc_put_bits(st, bit, 1u, sink);
+    uint32_t p = st.pending;
+    const uint32_t fill = bit ? 0u : 0xFFFFFFFFu;
+    while (p) {
+        uint32_t k = p < 32u ? p : 32u;
+        enc_put_bits(st, k == 32u ? fill : (fill & ((1u << k) - 1u)), k, sink);
+        p -= k;
+    }
+    st.pending = 0u;
+}
+
+// code one symbol whose CDF interval is [c_lo, c_lo + width), width >= 1, c_lo + width <= 65536
+template <class Sink>
+B2_HD void enc_symbol(EncState& st, uint32_t c_lo, uint32_t width, Sink& sink) {
+    const uint32_t r = st.high - st.low;                       // span - 1
+    const uint32_t c_hi = c_lo + width;
+    const uint64_t plo = (uint64_t)r * c_lo + c_lo;            // span * c_lo
+    const uint64_t phi = (uint64_t)r * c_hi + c_hi;            // span * c_hi
+    uint32_t low = st.low + (uint32_t)(plo >> 16);
+    uint32_t high = st.low - 1u + (uint32_t)(phi >> 16);
+    // E1/E2: the n leading bits of low and high agree -> they are final
+    const uint32_t n = clz32((low ^ high) | 1u);
+    if (n) {
+        const uint32_t top = low >> (32u - n);
+        if (st.pending == 0u) {
+            enc_put_bits(st, top, n, sink);
+        } else {
+            enc_bit_and_pending(st, top >> (n - 1u), sink);
+            enc_put_bits(st, top & ((1u << (n - 1u)) - 1u), n - 1u, sink);
+        }
+        low <<= n;
+        high = (high << n) | ((1u << n) - 1u);
+    }
+    // E3: while low = 01.., high = 10.. the interval straddles the midpoint
+    const uint32_t m = clz32((((~low) | high) << 1) | 1u);
+    st.pending += m;
+    st.low = (low << m) & 0x7FFFFFFFu;
+    st.high = (high << m) | 0x80000000u | ((1u << m) - 1u);
+}
+
+// terminate the stream; returns the number of trailing bits (0..31) still in st.acc (left to the caller
+// to write, zero padded to a byte), after the final bit + pending bits were queued.
+template <class Sink>
+B2_HD uint32_t enc_finish(EncState& st, Sink& sink) {
+    st.pending += 1u;
+    enc_bit_and_pending(st, st.low < 0x40000000u ? 0u : 1u, sink);
+    return st.nb;
+}
+
+// ---------------------------------------------------------------- arithmetic decoder (a10)
+// Source concept: uint32_t next_word() -- next 32 stream bits (first bit in the MSB), zeros past the end.
+struct DecState {
+    uint32_t low, high, value;
+    uint64_t res;   // bit reservoir, left aligned
+    uint32_t rb;    // valid bits in res
+};
+
+template <class Src>
+B2_HD void dec_refill(DecState& st, Src& src) {
+    if (st.rb < 32u) {
+        st.res |= (uint64_t)src.next_word() << (32u - st.rb);
+        st.rb += 32u;
+    }
+}
+
+template <class Src>
+B2_HD uint32_t dec_take(DecState& st, uint32_t k, Src& src) {   // 1 <= k <= 32
+    dec_refill(st, src);
+    uint32_t v = (uint32_t)(st.res >> (64u - k));
+    st.res <<= k;
+    st.rb -= k;
+    return v;
+}
+
+template <class Src>
+B2_HD void dec_init(DecState& st, Src& src) {
+    st.low = 0u; st.high = 0xFFFFFFFFu; st.res = 0ull; st.rb = 0u;
+    st.value = dec_take(st, 32u, src);
+}
+
+// Decode one symbol.  cdf(i) returns the uint16 CDF entry i (0..31) of this stream.
+// `last` suppresses the state update after the final symbol of the stream (reference: break at i == N-1).
+template <class Src, class CdfFn>
+B2_HD uint32_t dec_symbol(DecState& st, Src& src, CdfFn cdf, bool last) {
+    const uint32_t r = st.high - st.low;
+    const uint32_t off = st.value - st.low;
+    uint32_t lo = 0u, hi = 32u;
+    uint64_t plo = 0ull, phi = (uint64_t)r + 1ull;              // products at lo / hi  (cdf(32) := 65536)
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t c = cdf(mid);
+        const uint64_t pm = ((uint64_t)r * c + c) >> 16;        // (span * cdf[mid]) >> 16
+        if (pm <= (uint64_t)off) { lo = mid; plo = pm; } else { hi = mid; phi = pm; }
+    }
+    if (last) return lo;
+    uint32_t low = st.low + (uint32_t)plo;
+    uint32_t high = st.low - 1u + (uint32_t)phi;
+    uint32_t value = st.value;
+    const uint32_t n = clz32((low ^ high) | 1u);
+    if (n) {
+        value = (value << n) | dec_take(st, n, src);
+        low <<= n;
+        high = (high << n) | ((1u << n) - 1u);
+    }
+    const uint32_t m = clz32((((~low) | high) << 1) | 1u);
+    if (m) {
+        value = ((value << m) ^ 0x80000000u) | dec_take(st, m, src);
+        low = (low << m) & 0x7FFFFFFFu;
+        high = (high << m) | 0x80000000u | ((1u << m) - 1u);
+    }
+    st.low = low; st.high = high; st.value = value;
+    return lo;
+}
+
+// ---------------------------------------------------------------- container layout (host + device)
+B2_HD int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+struct Layout {
+    int64_t off_cdf, off_maxes, off_lengths, off_payload;
+    int32_t ngroups;
+};
+
+B2_HD Layout make_layout(int L, int C, int t) {
+    Layout lo;
+    const int64_t NL = 2 * (int64_t)L;
+    lo.ngroups = (t + kGroup - 1) / kGroup;
+    lo.off_cdf = 64;
+    lo.off_maxes = align16(lo.off_cdf + NL * C * kLp * 2);
+    lo.off_lengths = align16(lo.off_maxes + NL * t * 2);
+    lo.off_payload = align16(lo.off_lengths + (int64_t)lo.ngroups * NL * C * 4);
+    return lo;
+}
+
+}  // namespace b200kv

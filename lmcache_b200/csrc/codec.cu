@@ -1,0 +1,886 @@
+// codec.cu -- CacheGen encode / decode kernels for sm_100a and their C-ABI entry points.
+//
+// Replaces (reference paths relative to the LMCache v0.1.2 tree):
+//   encode: lmcache/storage_backend/serde/cachegen_encoder.py:266-325 (encode_function) incl. the three
+//           torchac_cuda calls, collect_bytes and the pickle container (cachegen_basics.py:131-136)
+//   decode: lmcache/storage_backend/serde/cachegen_decoder.py:52-106,143-202
+//
+// Thread mapping: one arithmetic-coder stream = one (plane nl, channel c) = one thread; a CTA owns a
+// tile of CT consecutive channels of one plane (and one <=256-token group).  Global KV reads/writes are
+// then naturally coalesced along the channel dimension (a warp touches 64 contiguous bytes per token)
+// and the tile's byte streams are contiguous in the container, so they are staged through shared
+// memory and written/read as one contiguous segment.  Stream compaction (collect_bytes in the
+// reference) happens inside the encode kernel with a decoupled look-back prefix over tiles.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ac_core.cuh"
+#include "common.cuh"
+
+namespace b200kv {
+
+constexpr int CT = 128;            // streams (threads) per tile
+constexpr int ROWW = 65;           // fused mode: words per symbol/output row (odd -> conflict-free columns)
+constexpr int ROWW_OUT = 131;      // split mode: words per output staging row (>= 2 B/symbol * 256 + flush)
+constexpr int PAIRW = 33;          // words per CDF-pair row (32 symbols + cdf[32]); odd
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagInc = 2ull << 62;
+constexpr unsigned long long kFlagMask = 3ull << 62;
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+struct EncParams {
+    PlaneTable pt;
+    int64_t sT, sH, tok_begin;
+    int32_t L, H, D, C, dtype;
+    int32_t n_chunks, chunk_tokens, last_chunk_tokens, tpp;   // tpp = tiles per plane
+    uint8_t* out;
+    int64_t out_stride;
+    uint64_t* sizes_out;
+    unsigned int* ticket;
+    unsigned long long* status;
+    unsigned long long* totals;
+    unsigned int* err;
+};
+
+__device__ __forceinline__ int chunk_tokens_of(const EncParams& P, int j) {
+    return j == P.n_chunks - 1 ? P.last_chunk_tokens : P.chunk_tokens;
+}
+
+__device__ __forceinline__ float load_half_as_float(const uint16_t* p, int dtype) {
+    return half_to_float(__ldg(p), dtype);
+}
+
+// ------------------------------------------------------------------------------------------ absmax
+// max1 = amax(|x|, channels) per (plane, token), kept in the input half dtype
+// (cachegen_encoder.py:54-55).  |x| ordering == integer ordering of (bits & 0x7fff); a NaN in the row
+// wins (pattern above inf), like torch.amax.  One warp per row, 128-bit loads when alignment allows.
+template <bool VEC>
+__global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_tokens) {
+    const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t nrows = (int64_t)2 * P.L * total_tokens;
+    if (warp >= nrows) return;
+    const int nl = (int)(warp / total_tokens);
+    const int64_t T = warp % total_tokens;
+    const uint16_t* row = P.pt.p[nl] + (P.tok_begin + T) * P.sT;
+    uint32_t m = 0;
+    if (VEC) {
+        const int vec_per_head = P.D >> 3;
+        const int nvec = P.H * vec_per_head;
+        for (int v = lane; v < nvec; v += 32) {
+            const int h = v / vec_per_head, dv = v - h * vec_per_head;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + (int64_t)h * P.sH + dv * 8));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a = w[k] & 0x7fff7fffu;
+                m = max(m, max(a & 0xffffu, a >> 16));
+            }
+        }
+    } else {
+        for (int c = lane; c < P.C; c += 32) {
+            const int h = c / P.D, d = c - h * P.D;
+            m = max(m, (uint32_t)(__ldg(row + (int64_t)h * P.sH + d) & 0x7fffu));
+        }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) {
+        const int j = (int)(T / P.chunk_tokens);
+        const int tj = chunk_tokens_of(P, j);
+        const Layout lo = make_layout(P.L, P.C, tj);
+        uint16_t* maxes = reinterpret_cast<uint16_t*>(P.out + (int64_t)j * P.out_stride + lo.off_maxes);
+        maxes[(int64_t)nl * tj + (T - (int64_t)j * P.chunk_tokens)] = (uint16_t)m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ helpers
+struct RowSink {
+    uint32_t* row;
+    uint32_t w, cap, ovf;
+    __device__ __forceinline__ void put_word(uint32_t v) {
+        if (w < cap) row[w] = __byte_perm(v, 0u, 0x0123);   // big-endian in memory: first bit first
+        else ovf = 1u;
+        ++w;
+    }
+};
+
+// block-wide exclusive scan of one uint32 per thread (CT threads); returns exclusive prefix, total in *total
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CT / 32; ++w) {
+        const uint32_t s = s_warp[w];
+        if (w < wid) base += s;
+        tot += s;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+// decoupled look-back over tiles [first, tile]; one thread calls.  status words pack flag | value so a
+// single 64-bit store publishes both.  A tile only ever waits on tiles with smaller tickets, which have
+// already been scheduled, so this cannot deadlock; the spin limit turns a logic bug into an error code
+// instead of a hung GPU.
+__device__ unsigned long long lookback_excl(unsigned long long* status, uint32_t tile, uint32_t first,
+                                            unsigned long long agg, unsigned int* err) {
+    if (tile == first) {
+        atomicExch(&status[tile], kFlagInc | agg);
+        return 0ull;
+    }
+    atomicExch(&status[tile], kFlagAgg | agg);
+    unsigned long long excl = 0ull;
+    int64_t idx = (int64_t)tile - 1;
+    uint32_t spins = 0;
+    while (true) {
+        const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(&status[idx]);
+        const unsigned long long f = v & kFlagMask;
+        if (f == 0ull) {
+            if (++spins > kSpinLimit) { atomicOr(err, 2u); break; }
+            __nanosleep(64);
+            continue;
+        }
+        excl += v & ~kFlagMask;
+        if (f == kFlagInc || idx == (int64_t)first) break;
+        --idx;
+    }
+    atomicExch(&status[tile], kFlagInc | (excl + agg));
+    return excl;
+}
+
+// write the 33 uint16 CDF entries of `ncols` streams (low halves of the pair rows, which are contiguous
+// with stride PAIRW == kLp words) to the container, coalesced
+__device__ __forceinline__ void store_cdf_rows(const uint32_t* pair, uint16_t* dst, int ncols) {
+    const int n = ncols * kLp;
+    for (int e = threadIdx.x; e < n; e += CT) dst[e] = (uint16_t)pair[e];
+}
+
+// thread-private: turn 33 counts (read through `cnt(i)`) into the pair row  c_lo | width << 16
+template <class CountFn>
+__device__ __forceinline__ void build_pair_row(uint32_t* prow, int t, CountFn cnt) {
+    CdfAccum acc;
+    acc.init(t);
+    uint32_t prev = acc.next(0u, cnt(0));
+#pragma unroll
+    for (uint32_t i = 1; i <= 32u; ++i) {
+        const uint32_t cur = acc.next(i, i < 32u ? cnt(i) : 0u);
+        const uint32_t hi = (i == 32u) ? 0x10000u : cur;      // coder uses 0x10000 above max_symbol
+        prow[i - 1] = prev | ((hi - prev) << 16);
+        prev = cur;
+    }
+    prow[32] = prev;                                          // cdf[32] (wraps to 0; never read by the coder)
+}
+
+// copy the tile's streams from their staging rows to the compact payload
+__device__ __forceinline__ void copy_rows_out(const uint32_t* rows, int roww, const uint32_t* s_off,
+                                              const uint32_t* s_len, uint8_t* dst) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = wid; r < CT; r += CT / 32) {
+        const uint32_t n = s_len[r];
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(rows + r * roww);
+        uint8_t* d = dst + s_off[r];
+        for (uint32_t i = lane; i < n; i += 32) d[i] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ encode
+// FUSED (chunk <= 256 tokens, one group): quantise -> smem symbols + histogram -> CDF -> arithmetic-code
+// in place over the consumed symbols -> look-back -> compact copy.  KV is read from HBM exactly once
+// here (plus once by absmax).
+// !FUSED (chunk > 256 tokens): CDF was produced by cdf_kernel over the whole chunk; this kernel codes one
+// group per tile, quantising on the fly.
+template <bool FUSED, int DT>
+__global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int RW = FUSED ? ROWW : ROWW_OUT;
+    uint32_t* rows = smem;
+    uint32_t* pair = rows + CT * RW;
+    float* fac = reinterpret_cast<float*>(pair + CT * PAIRW);
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(fac + kGroup);
+    uint32_t* s_len = s_off + CT;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[CT / 32];
+    __shared__ unsigned long long s_excl;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+
+    const int NL = 2 * P.L;
+    const uint32_t per_group = (uint32_t)NL * P.tpp;
+    const uint32_t g_full = (uint32_t)(P.chunk_tokens + kGroup - 1) / kGroup;
+    const uint32_t per_chunk_full = g_full * per_group;
+    uint32_t j = tile / per_chunk_full;
+    if (j >= (uint32_t)P.n_chunks) j = P.n_chunks - 1;
+    const uint32_t rem = tile - j * per_chunk_full;
+    const uint32_t first_tile = j * per_chunk_full;
+    const int t = chunk_tokens_of(P, (int)j);
+    const uint32_t g_here = (uint32_t)(t + kGroup - 1) / kGroup;
+    const uint32_t g = rem / per_group;
+    if (g >= g_here) return;   // cannot happen: the grid is sized exactly (host); defensive
+    const uint32_t rem2 = rem - g * per_group;
+    const int nl = (int)(rem2 / P.tpp);
+    const int ct = (int)(rem2 - (uint32_t)nl * P.tpp);
+    const bool last_tile_of_chunk = (g == g_here - 1) && (rem2 == per_group - 1);
+    const int tok0 = (int)g * kGroup;
+    const int gt = min(kGroup, t - tok0);
+    const int c = ct * CT + tid;
+    const bool active = c < P.C;
+    const int ncols = min(CT, P.C - ct * CT);
+
+    uint8_t* cont = P.out + (int64_t)j * P.out_stride;
+    const Layout lo = make_layout(P.L, P.C, t);
+    const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + tok0;
+    const float maxq = P.pt.maxq[nl];
+
+    for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[i], DT));
+
+    uint32_t* prow = pair + tid * PAIRW;
+    uint32_t* myrow = rows + tid * RW;
+    const int h = active ? c / P.D : 0;
+    const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + tok0) * P.sT +
+                          (int64_t)h * P.sH + (active ? c - h * P.D : 0);
+
+    if (FUSED) {
+        // ---- pass 1: quantise, stash symbols (4 tokens per word), count
+        uint16_t* hist = reinterpret_cast<uint16_t*>(prow);
+#pragma unroll
+        for (int i = 0; i < PAIRW; ++i) prow[i] = 0u;
+        __syncthreads();   // fac ready
+        if (active) {
+            const int nwords = (gt + 3) >> 2;
+            for (int w = 0; w < nwords; ++w) {
+                uint16_t xb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int tok = 4 * w + k;
+                    xb[k] = tok < gt ? __ldg(src + (int64_t)tok * P.sT) : (uint16_t)0;
+                }
+                uint32_t word = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int tok = 4 * w + k;
+                    if (tok < gt) {
+                        const uint32_t s = quant_symbol(half_to_float(xb[k], DT), fac[tok], maxq);
+                        word |= s << (8 * k);
+                        hist[s & 31u] += 1;   // symbols are <= 30 by construction; &31 keeps a corrupt input in-row
+                    }
+                }
+                myrow[w] = word;
+            }
+            // ---- CDF from the thread's own histogram (16 words -> registers), pair row built in place
+            uint32_t hw[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hw[i] = prow[i];
+            build_pair_row(prow, t, [&](uint32_t i) -> uint32_t {
+                return i < 32u ? ((hw[i >> 1] >> ((i & 1u) * 16u)) & 0xffffu) : 0u;
+            });
+        }
+        __syncthreads();
+        store_cdf_rows(pair, reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp,
+                       ncols);
+    } else {
+        // CDF of the whole chunk was written by cdf_kernel: load it and build the pair rows
+        const uint16_t* cdf_src =
+            reinterpret_cast<const uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
+        for (int e = tid; e < ncols * kLp; e += CT) pair[e] = cdf_src[e];
+        __syncthreads();   // also: fac ready
+        if (active) {
+            uint32_t cv[kLp];
+#pragma unroll
+            for (int i = 0; i < kLp; ++i) cv[i] = prow[i] & 0xffffu;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t hi = (i == 31) ? 0x10000u : cv[i + 1];
+                prow[i] = cv[i] | ((hi - cv[i]) << 16);
+            }
+        }
+    }
+
+    // ---- pass 2: arithmetic-code the group
+    uint32_t len = 0u, ovf = 0u;
+    if (active) {
+        EncState st;
+        st.init();
+        RowSink sink{myrow, 0u, (uint32_t)RW, 0u};
+        if (FUSED) {
+            const int nwords = (gt + 3) >> 2;
+            for (int w = 0; w < nwords; ++w) {
+                const uint32_t word = myrow[w];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (4 * w + k < gt) {
+                        const uint32_t pr = prow[(word >> (8 * k)) & 31u];
+                        enc_symbol(st, pr & 0xffffu, pr >> 16, sink);
+                    }
+                }
+            }
+        } else {
+            for (int tk = 0; tk < gt; tk += 4) {
+                uint16_t xb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xb[k] = (tk + k < gt) ? __ldg(src + (int64_t)(tk + k) * P.sT) : (uint16_t)0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (tk + k < gt) {
+                        const uint32_t s = quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq);
+                        const uint32_t pr = prow[s & 31u];
+                        enc_symbol(st, pr & 0xffffu, pr >> 16, sink);
+                    }
+                }
+            }
+        }
+        const uint32_t nb = enc_finish(st, sink);
+        const uint32_t full = sink.w;
+        if (nb) sink.put_word((uint32_t)(st.acc << (32u - nb)));
+        len = 4u * full + ((nb + 7u) >> 3);
+        ovf = sink.ovf;
+    }
+
+    // ---- compaction: tile scan + look-back, then contiguous copy-out
+    uint32_t tile_total;
+    const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
+    s_off[tid] = my_off;
+    s_len[tid] = len;
+    if (ovf) atomicOr(&P.err[j], 1u);
+    if (tid == 0) s_excl = lookback_excl(P.status, tile, first_tile, (unsigned long long)tile_total, &P.err[j]);
+    __syncthreads();
+    const unsigned long long excl = s_excl;
+    if (active) {
+        int32_t* lengths = reinterpret_cast<int32_t*>(cont + lo.off_lengths) + ((int64_t)g * NL + nl) * P.C;
+        lengths[c] = (int32_t)len;
+    }
+    // never write past the slot the caller gave us
+    const int64_t room = P.out_stride - lo.off_payload;
+    if ((int64_t)(excl + tile_total) <= room) {
+        copy_rows_out(rows, RW, s_off, s_len, cont + lo.off_payload + excl);
+    } else if (tid == 0) {
+        atomicOr(&P.err[j], 4u);
+    }
+    if (last_tile_of_chunk && tid == 0) P.totals[j] = excl + tile_total;
+}
+
+// ------------------------------------------------------------------------------------------ cdf (chunks > 256 tokens)
+template <int DT>
+__global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* pair = smem;                                        // CT * PAIRW  (counts, then cdf)
+    float* fac = reinterpret_cast<float*>(pair + CT * PAIRW);     // kGroup
+    const int tid = threadIdx.x;
+    const int NL = 2 * P.L;
+    const uint32_t per_chunk = (uint32_t)NL * P.tpp;
+    const uint32_t j = blockIdx.x / per_chunk;
+    const uint32_t rem = blockIdx.x - j * per_chunk;
+    const int nl = (int)(rem / P.tpp);
+    const int ct = (int)(rem - (uint32_t)nl * P.tpp);
+    const int t = chunk_tokens_of(P, (int)j);
+    const int c = ct * CT + tid;
+    const bool active = c < P.C;
+    const int ncols = min(CT, P.C - ct * CT);
+    uint8_t* cont = P.out + (int64_t)j * P.out_stride;
+    const Layout lo = make_layout(P.L, P.C, t);
+    const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t;
+    const float maxq = P.pt.maxq[nl];
+    uint32_t* prow = pair + tid * PAIRW;
+#pragma unroll
+    for (int i = 0; i < PAIRW; ++i) prow[i] = 0u;
+    const int h = active ? c / P.D : 0;
+    const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens) * P.sT + (int64_t)h * P.sH +
+                          (active ? c - h * P.D : 0);
+    for (int tok0 = 0; tok0 < t; tok0 += kGroup) {
+        const int gt = min(kGroup, t - tok0);
+        __syncthreads();
+        for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[tok0 + i], DT));
+        __syncthreads();
+        if (active) {
+            for (int tk = 0; tk < gt; tk += 4) {
+                uint16_t xb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    xb[k] = (tk + k < gt) ? __ldg(src + (int64_t)(tok0 + tk + k) * P.sT) : (uint16_t)0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (tk + k < gt) prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq) & 31u] += 1u;
+            }
+        }
+    }
+    if (active) {
+        uint32_t cnt[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cnt[i] = prow[i];
+        build_pair_row(prow, t, [&](uint32_t i) -> uint32_t { return i < 32u ? cnt[i] : 0u; });
+    }
+    __syncthreads();
+    store_cdf_rows(pair, reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp, ncols);
+}
+
+// ------------------------------------------------------------------------------------------ finalize
+__global__ void finalize_kernel(EncParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n_chunks) return;
+    const int t = chunk_tokens_of(P, j);
+    const Layout lo = make_layout(P.L, P.C, t);
+    b200kv_header* hd = reinterpret_cast<b200kv_header*>(P.out + (int64_t)j * P.out_stride);
+    hd->magic = B200KV_MAGIC;
+    hd->version = B200KV_VERSION;
+    hd->L = P.L; hd->H = P.H; hd->D = P.D;
+    hd->ntokens = t;
+    hd->ngroups = lo.ngroups;
+    hd->max_dtype = P.dtype;
+    hd->payload_bytes = P.totals[j];
+    hd->total_bytes = (uint64_t)lo.off_payload + P.totals[j];
+    hd->status = P.err[j];
+    hd->reserved[0] = hd->reserved[1] = hd->reserved[2] = 0u;
+    if (P.sizes_out) P.sizes_out[j] = hd->total_bytes;
+}
+
+// ------------------------------------------------------------------------------------------ decode
+struct DecChunk {
+    const uint8_t* base;
+    int64_t dst_tok;
+    int32_t t, ngroups;
+};
+
+struct DecParams {
+    PlaneTable pt;               // destination planes; maxq = C_l = bins // 2 - 1
+    int64_t sT, sH;
+    int32_t L, H, D, C, out_dtype, max_dtype, n_chunks, tpp, tiles_max;
+    const DecChunk* chunks;      // device
+    unsigned long long* tile_base;   // [n_chunks][tiles_max]: tile sums, then exclusive prefix
+};
+
+// tile sums of the stream lengths: one warp per tile
+__global__ void __launch_bounds__(128) tile_sum_kernel(DecParams P) {
+    const int j = blockIdx.y;
+    const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const DecChunk dc = P.chunks[j];
+    const int NL = 2 * P.L;
+    const int ntiles = dc.ngroups * NL * P.tpp;
+    if (tile >= ntiles) return;
+    const int plane_row = tile / P.tpp;          // g * NL + nl
+    const int ct = tile - plane_row * P.tpp;
+    const Layout lo = make_layout(P.L, P.C, dc.t);
+    const int32_t* lengths = reinterpret_cast<const int32_t*>(dc.base + lo.off_lengths) + (int64_t)plane_row * P.C;
+    const int c0 = ct * CT, c1 = min(P.C, c0 + CT);
+    uint32_t s = 0;
+    for (int c = c0 + lane; c < c1; c += 32) s += (uint32_t)lengths[c];
+    s = __reduce_add_sync(0xffffffffu, s);
+    if (lane == 0) P.tile_base[(int64_t)j * P.tiles_max + tile] = s;
+}
+
+// exclusive prefix over a chunk's tile sums (in place); one CTA per chunk
+__global__ void __launch_bounds__(1024) tile_scan_kernel(DecParams P) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    const int j = blockIdx.x;
+    const DecChunk dc = P.chunks[j];
+    const int ntiles = dc.ngroups * 2 * P.L * P.tpp;
+    unsigned long long* tb = P.tile_base + (int64_t)j * P.tiles_max;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < ntiles ? tb[i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0ull, tot = 0ull;
+        for (int w = 0; w < 32; ++w) {
+            const unsigned long long s = s_w[w];
+            if (w < wid) wbase += s;
+            tot += s;
+        }
+        const unsigned long long carry = s_carry;
+        if (i < ntiles) tb[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+}
+
+struct ByteSrc {
+    const uint8_t* p;
+    uint32_t pos, len;
+    __device__ __forceinline__ uint32_t next_word() {
+        uint32_t w = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            w <<= 8;
+            if (pos < len) w |= p[pos];
+            ++pos;
+        }
+        return w;
+    }
+};
+
+constexpr int CDFW = 34;                     // uint16 per staged CDF row (17 words, odd)
+constexpr int DEC_STAGE_BYTES = CT * 160;    // staged compressed bytes per tile (20 KiB); larger tiles read global
+
+// One tile = CT streams of one (chunk, group, plane): stage the tile's contiguous byte segment + CDF rows
+// in shared memory, decode each stream, dequantise through a 32-entry LUT and store the final half values
+// straight into the destination layout (no uint8 / fp32 intermediates in HBM).
+template <int OUT_DT>
+__global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint8_t* stage = reinterpret_cast<uint8_t*>(smem);                               // DEC_STAGE_BYTES + 16
+    uint16_t* cdf_s = reinterpret_cast<uint16_t*>(stage + DEC_STAGE_BYTES + 16);     // CT * CDFW
+    float* mx = reinterpret_cast<float*>(cdf_s + CT * CDFW);                         // kGroup
+    float* lut = mx + kGroup;                                                        // 32
+    __shared__ uint32_t s_warp[CT / 32];
+
+    const int tid = threadIdx.x;
+    const int j = blockIdx.y;
+    const DecChunk dc = P.chunks[j];
+    const int NL = 2 * P.L;
+    const int per_group = NL * P.tpp;
+    const int tile = blockIdx.x;
+    const int g = tile / per_group;
+    if (g >= dc.ngroups) return;
+    const int rem = tile - g * per_group;
+    const int nl = rem / P.tpp;
+    const int ct = rem - nl * P.tpp;
+    const int tok0 = g * kGroup;
+    const int gt = min(kGroup, dc.t - tok0);
+    const int c = ct * CT + tid;
+    const bool active = c < P.C;
+    const int ncols = min(CT, P.C - ct * CT);
+    const Layout lo = make_layout(P.L, P.C, dc.t);
+
+    const int32_t* lengths = reinterpret_cast<const int32_t*>(dc.base + lo.off_lengths) + ((int64_t)g * NL + nl) * P.C;
+    const uint32_t len = active ? (uint32_t)lengths[c] : 0u;
+    uint32_t tile_total;
+    const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
+    const uint8_t* seg = dc.base + lo.off_payload + P.tile_base[(int64_t)j * P.tiles_max + tile];
+
+    // stage CDF rows, row maxima, LUT
+    const uint16_t* cdf_src = reinterpret_cast<const uint16_t*>(dc.base + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
+    for (int e = tid; e < ncols * kLp; e += CT) {
+        const int r = e / kLp;
+        cdf_s[r * CDFW + (e - r * kLp)] = cdf_src[e];
+    }
+    const uint16_t* maxes = reinterpret_cast<const uint16_t*>(dc.base + lo.off_maxes) + (int64_t)nl * dc.t + tok0;
+    for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
+    if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, P.pt.maxq[nl]);
+
+    // stage the tile's byte segment (16-byte aligned window) when it fits
+    const bool staged = tile_total <= (uint32_t)DEC_STAGE_BYTES;
+    const uint8_t* my_bytes;
+    if (staged) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(seg);
+        const uint32_t shift = (uint32_t)(a & 15u);
+        const uint4* src16 = reinterpret_cast<const uint4*>(a - shift);
+        const uint32_t nvec = (shift + tile_total + 15u) >> 4;
+        uint4* dst16 = reinterpret_cast<uint4*>(stage);
+        for (uint32_t v = tid; v < nvec; v += CT) dst16[v] = __ldg(src16 + v);
+        my_bytes = stage + shift + my_off;
+    } else {
+        my_bytes = seg + my_off;
+    }
+    __syncthreads();
+
+    if (!active) return;
+    const int h = c / P.D;
+    uint16_t* dst = const_cast<uint16_t*>(P.pt.p[nl]) + (dc.dst_tok + tok0) * P.sT + (int64_t)h * P.sH + (c - h * P.D);
+    const uint16_t* crow = cdf_s + tid * CDFW;
+    ByteSrc src{my_bytes, 0u, len};
+    DecState st;
+    dec_init(st, src);
+    for (int i = 0; i < gt; ++i) {
+        const uint32_t s = dec_symbol(st, src, [&](uint32_t k) -> uint32_t { return crow[k]; }, i == gt - 1);
+        dst[(int64_t)i * P.sT] = float_to_half(dequant_value(lut[s], mx[i]), OUT_DT);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+int make_plane_table(const b200kv_kv_desc* kv, const float* key_bins, const float* value_bins, PlaneTable* out) {
+    B2_REQUIRE(kv != nullptr, "kv descriptor is NULL");
+    B2_REQUIRE(kv->L > 0 && 2 * kv->L <= B200KV_MAX_PLANES, "L out of range");
+    B2_REQUIRE(kv->H > 0 && kv->D > 0, "H/D must be positive");
+    B2_REQUIRE(kv->dtype == B200KV_DT_BF16 || kv->dtype == B200KV_DT_FP16, "dtype must be bf16 or fp16");
+    B2_REQUIRE(kv->planes != nullptr || kv->base != nullptr, "no KV pointer");
+    for (int kvi = 0; kvi < 2; ++kvi)
+        for (int l = 0; l < kv->L; ++l) {
+            const int nl = kvi * kv->L + l;
+            const uint16_t* p = kv->planes ? static_cast<const uint16_t*>(kv->planes[nl])
+                                           : static_cast<const uint16_t*>(kv->base) + l * kv->sL + kvi * kv->sKV;
+            B2_REQUIRE(p != nullptr, "NULL plane pointer");
+            out->p[nl] = p;
+            const float bins = kvi ? value_bins[l] : key_bins[l];
+            out->maxq[nl] = floorf(bins / 2.0f) - 1.0f;       // bins // 2 - 1  (cachegen_encoder.py:53)
+            B2_REQUIRE(out->maxq[nl] >= 1.0f && out->maxq[nl] <= 15.0f, "bins must be in [4, 32]");
+        }
+    return 0;
+}
+
+static int tiles_per_plane(int C) { return (C + CT - 1) / CT; }
+
+// ---- optional per-kernel timing (bench.py's roofline leg): events around each launch of the last call
+enum { kProfAbsmax = 0, kProfCdf, kProfEncode, kProfFinalize, kProfTileSum, kProfTileScan, kProfDecode, kProfCount };
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[kProfCount][2];
+static bool g_prof_have[kProfCount];
+static bool g_prof_init = false;
+
+struct ProfScope {
+    int slot;
+    cudaStream_t stream;
+    ProfScope(int slot_, cudaStream_t s) : slot(slot_), stream(s) {
+        if (!g_prof_on) return;
+        if (!g_prof_init) {
+            for (int i = 0; i < kProfCount; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); }
+            g_prof_init = true;
+        }
+        cudaEventRecord(g_prof_ev[slot][0], stream);
+    }
+    ~ProfScope() {
+        if (!g_prof_on) return;
+        cudaEventRecord(g_prof_ev[slot][1], stream);
+        g_prof_have[slot] = true;
+    }
+};
+
+static size_t enc_ws_layout(int64_t n_tiles, int n_chunks, size_t* off_status, size_t* off_totals, size_t* off_err) {
+    size_t o = 64;                       // ticket
+    *off_status = o; o += (size_t)n_tiles * 8;
+    *off_totals = o; o += (size_t)n_chunks * 8;
+    *off_err = o;    o += (size_t)n_chunks * 4;
+    return (o + 255) & ~(size_t)255;
+}
+
+static size_t dec_ws_layout(int64_t tiles_max, int n_chunks, size_t* off_tb) {
+    size_t o = ((size_t)n_chunks * sizeof(DecChunk) + 255) & ~(size_t)255;
+    *off_tb = o;
+    o += (size_t)n_chunks * (size_t)tiles_max * 8;
+    return (o + 255) & ~(size_t)255;
+}
+
+}  // namespace b200kv
+
+using namespace b200kv;
+
+extern "C" {
+
+int b200kv_container_layout(int32_t L, int32_t H, int32_t D, int32_t ntokens, b200kv_layout* out) {
+    B2_REQUIRE(out != nullptr && L > 0 && H > 0 && D > 0 && ntokens > 0, "bad shape");
+    const Layout lo = make_layout(L, H * D, ntokens);
+    out->off_cdf = lo.off_cdf;
+    out->off_maxes = lo.off_maxes;
+    out->off_lengths = lo.off_lengths;
+    out->off_payload = lo.off_payload;
+    out->fixed_bytes = lo.off_payload;
+    // <= 16 bits per symbol (CDF width >= 1/65536) + 2 flush bits + pad, per stream per group; +16 read slack
+    const int64_t streams = 2 * (int64_t)L * H * D;
+    out->max_total_bytes = align16(lo.off_payload + streams * (2 * (int64_t)ntokens + 2 * (int64_t)lo.ngroups) + 16);
+    return 0;
+}
+
+int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks) {
+    if (L <= 0 || H <= 0 || D <= 0 || chunk_tokens <= 0 || n_chunks <= 0) return -2;
+    const int64_t G = (chunk_tokens + kGroup - 1) / kGroup;
+    const int64_t n_tiles = (int64_t)n_chunks * G * 2 * L * tiles_per_plane(H * D);
+    size_t a, b, c;
+    return (int64_t)enc_ws_layout(n_tiles, n_chunks, &a, &b, &c);
+}
+
+int64_t b200kv_decode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks) {
+    if (L <= 0 || H <= 0 || D <= 0 || chunk_tokens <= 0 || n_chunks <= 0) return -2;
+    const int64_t G = (chunk_tokens + kGroup - 1) / kGroup;
+    const int64_t tiles_max = G * 2 * L * tiles_per_plane(H * D);
+    size_t a;
+    return (int64_t)dec_ws_layout(tiles_max, n_chunks, &a);
+}
+
+int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_chunks, int32_t chunk_tokens,
+                         int32_t last_chunk_tokens, const float* key_bins, const float* value_bins, void* out,
+                         int64_t out_stride, uint64_t* sizes_out, void* workspace, int64_t workspace_bytes,
+                         void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    EncParams P;
+    B2_REQUIRE(key_bins && value_bins, "bins are NULL");
+    if (int rc = make_plane_table(kv, key_bins, value_bins, &P.pt)) return rc;
+    B2_REQUIRE(n_chunks > 0 && chunk_tokens > 0, "n_chunks / chunk_tokens must be positive");
+    B2_REQUIRE(last_chunk_tokens > 0 && last_chunk_tokens <= chunk_tokens, "last_chunk_tokens out of range");
+    B2_REQUIRE(out != nullptr && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (out_stride & 15) == 0,
+               "out / out_stride must be 16-byte aligned");
+    B2_REQUIRE(tok_begin >= 0, "tok_begin must be >= 0");
+    P.sT = kv->sT; P.sH = kv->sH; P.tok_begin = tok_begin;
+    P.L = kv->L; P.H = kv->H; P.D = kv->D; P.C = kv->H * kv->D; P.dtype = kv->dtype;
+    P.n_chunks = n_chunks; P.chunk_tokens = chunk_tokens; P.last_chunk_tokens = last_chunk_tokens;
+    P.tpp = tiles_per_plane(P.C);
+    P.out = static_cast<uint8_t*>(out);
+    P.out_stride = out_stride;
+    P.sizes_out = sizes_out;
+    const Layout lo = make_layout(P.L, P.C, chunk_tokens);
+    B2_REQUIRE(out_stride >= lo.off_payload + 16, "out_stride smaller than the fixed container sections");
+
+    const int64_t G = lo.ngroups;
+    const int64_t G_last = (last_chunk_tokens + kGroup - 1) / kGroup;
+    const int64_t per_group = 2 * (int64_t)P.L * P.tpp;
+    const int64_t n_tiles = ((int64_t)(n_chunks - 1) * G + G_last) * per_group;
+    const int64_t n_tiles_alloc = (int64_t)n_chunks * G * per_group;
+    size_t off_status, off_totals, off_err;
+    const size_t need = enc_ws_layout(n_tiles_alloc, n_chunks, &off_status, &off_totals, &off_err);
+    B2_REQUIRE(workspace != nullptr && workspace_bytes >= (int64_t)need, "workspace too small");
+    B2_REQUIRE(n_tiles < (1ll << 31), "too many tiles in one call");
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    P.ticket = reinterpret_cast<unsigned int*>(ws);
+    P.status = reinterpret_cast<unsigned long long*>(ws + off_status);
+    P.totals = reinterpret_cast<unsigned long long*>(ws + off_totals);
+    P.err = reinterpret_cast<unsigned int*>(ws + off_err);
+    B2_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, stream));
+
+    // 1) per-(plane, token) absmax -> maxes sections
+    const int64_t total_tokens = (int64_t)(n_chunks - 1) * chunk_tokens + last_chunk_tokens;
+    {
+        bool vec = (kv->D % 8 == 0) && (kv->sT % 8 == 0) && (kv->sH % 8 == 0);
+        for (int nl = 0; nl < 2 * P.L && vec; ++nl) vec = (reinterpret_cast<uintptr_t>(P.pt.p[nl]) & 15) == 0;
+        const int64_t rows = 2 * (int64_t)P.L * total_tokens;
+        const int64_t blocks = (rows + 7) / 8;
+        B2_REQUIRE(blocks < (1ll << 31), "too many rows in one call");
+        ProfScope prof(kProfAbsmax, stream);
+        if (vec) absmax_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        else absmax_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        B2_CHECK_CUDA(cudaGetLastError());
+    }
+    // 2) encode
+    const bool fused = chunk_tokens <= kGroup;
+    const size_t smem_fused = (size_t)(CT * ROWW + CT * PAIRW + kGroup + 2 * CT) * 4;
+    const size_t smem_split = (size_t)(CT * ROWW_OUT + CT * PAIRW + kGroup + 2 * CT) * 4;
+    const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
+#define B2_LAUNCH_ENC(FUSED, DT, SMEM)                                                                     \
+    do {                                                                                                   \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<FUSED, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)(SMEM)));                                                  \
+        encode_kernel<FUSED, DT><<<(unsigned)n_tiles, CT, (SMEM), stream>>>(P);                            \
+    } while (0)
+    if (fused) {
+        ProfScope prof(kProfEncode, stream);
+        if (P.dtype == B200KV_DT_BF16) B2_LAUNCH_ENC(true, 0, smem_fused); else B2_LAUNCH_ENC(true, 1, smem_fused);
+    } else {
+        const unsigned cdf_blocks = (unsigned)((int64_t)n_chunks * per_group);
+        {
+            ProfScope prof(kProfCdf, stream);
+            if (P.dtype == B200KV_DT_BF16) cdf_kernel<0><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+            else cdf_kernel<1><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+        }
+        B2_CHECK_CUDA(cudaGetLastError());
+        ProfScope prof(kProfEncode, stream);
+        if (P.dtype == B200KV_DT_BF16) B2_LAUNCH_ENC(false, 0, smem_split); else B2_LAUNCH_ENC(false, 1, smem_split);
+    }
+#undef B2_LAUNCH_ENC
+    B2_CHECK_CUDA(cudaGetLastError());
+    // 3) headers + sizes
+    {
+        ProfScope prof(kProfFinalize, stream);
+        finalize_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P);
+    }
+    B2_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const int32_t* ntokens,
+                         const int64_t* dst_tok, int32_t n_chunks, int32_t max_dtype, const b200kv_kv_desc* dst,
+                         const float* key_bins, const float* value_bins, void* workspace,
+                         int64_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DecParams P;
+    B2_REQUIRE(key_bins && value_bins, "bins are NULL");
+    if (int rc = make_plane_table(dst, key_bins, value_bins, &P.pt)) return rc;
+    B2_REQUIRE(containers && offsets && ntokens && dst_tok && n_chunks > 0, "bad chunk arrays");
+    B2_REQUIRE(max_dtype == B200KV_DT_BF16 || max_dtype == B200KV_DT_FP16, "bad max_dtype");
+    P.sT = dst->sT; P.sH = dst->sH;
+    P.L = dst->L; P.H = dst->H; P.D = dst->D; P.C = dst->H * dst->D;
+    P.out_dtype = dst->dtype; P.max_dtype = max_dtype; P.n_chunks = n_chunks;
+    P.tpp = tiles_per_plane(P.C);
+    int tmax = 0;
+    for (int j = 0; j < n_chunks; ++j) {
+        B2_REQUIRE(ntokens[j] > 0, "ntokens must be positive");
+        B2_REQUIRE((offsets[j] & 15) == 0, "container offsets must be 16-byte aligned");
+        tmax = ntokens[j] > tmax ? ntokens[j] : tmax;
+    }
+    const int64_t Gmax = (tmax + kGroup - 1) / kGroup;
+    const int64_t tiles_max = Gmax * 2 * P.L * P.tpp;
+    B2_REQUIRE(tiles_max < (1ll << 31) && n_chunks <= 65535, "too many tiles / chunks in one call");
+    P.tiles_max = (int32_t)tiles_max;
+    size_t off_tb;
+    const size_t need = dec_ws_layout(tiles_max, n_chunks, &off_tb);
+    B2_REQUIRE(workspace != nullptr && workspace_bytes >= (int64_t)need, "workspace too small");
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    // chunk descriptors: small pageable -> device copy (staged by the driver before the call returns)
+    {
+        DecChunk* hc = static_cast<DecChunk*>(malloc(sizeof(DecChunk) * (size_t)n_chunks));
+        B2_REQUIRE(hc != nullptr, "out of host memory");
+        for (int j = 0; j < n_chunks; ++j) {
+            hc[j].base = static_cast<const uint8_t*>(containers) + offsets[j];
+            hc[j].dst_tok = dst_tok[j];
+            hc[j].t = ntokens[j];
+            hc[j].ngroups = (ntokens[j] + kGroup - 1) / kGroup;
+        }
+        cudaError_t e = cudaMemcpyAsync(ws, hc, sizeof(DecChunk) * (size_t)n_chunks, cudaMemcpyHostToDevice, stream);
+        free(hc);
+        B2_CHECK_CUDA(e);
+    }
+    P.chunks = reinterpret_cast<const DecChunk*>(ws);
+    P.tile_base = reinterpret_cast<unsigned long long*>(ws + off_tb);
+
+    dim3 gsum((unsigned)((tiles_max + 3) / 4), (unsigned)n_chunks);
+    {
+        ProfScope prof(kProfTileSum, stream);
+        tile_sum_kernel<<<gsum, 128, 0, stream>>>(P);
+    }
+    B2_CHECK_CUDA(cudaGetLastError());
+    {
+        ProfScope prof(kProfTileScan, stream);
+        tile_scan_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(P);
+    }
+    B2_CHECK_CUDA(cudaGetLastError());
+
+    const size_t smem = (size_t)DEC_STAGE_BYTES + 16 + (size_t)CT * CDFW * 2 + (size_t)(kGroup + 32) * 4;
+    dim3 grid((unsigned)tiles_max, (unsigned)n_chunks);
+    ProfScope prof(kProfDecode, stream);
+    if (P.out_dtype == B200KV_DT_BF16) {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_kernel<0><<<grid, CT, smem, stream>>>(P);
+    } else {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_kernel<1><<<grid, CT, smem, stream>>>(P);
+    }
+    B2_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b200kv_profile_enable(int32_t on) {
+    g_prof_on = on != 0;
+    for (int i = 0; i < kProfCount; ++i) g_prof_have[i] = false;
+    return 0;
+}
+
+int b200kv_profile_last(float* ms, int32_t n) {
+    B2_REQUIRE(ms != nullptr && n >= kProfCount, "need room for 7 floats");
+    for (int i = 0; i < kProfCount; ++i) {
+        ms[i] = -1.0f;
+        if (g_prof_on && g_prof_have[i]) {
+            B2_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[i][1]));
+            B2_CHECK_CUDA(cudaEventElapsedTime(&ms[i], g_prof_ev[i][0], g_prof_ev[i][1]));
+        }
+    }
+    return kProfCount;
+}
+
+}  // extern "C"

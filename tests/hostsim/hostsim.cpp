@@ -1,0 +1,84 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE.  Compiles the product's device arithmetic
+// (lmcache_b200/csrc/ac_core.cuh, all __host__ __device__) with g++ so the exact same functions the
+// CUDA kernels call can be checked against the oracle on a machine without a GPU.  Never shipped,
+// never loaded by lmcache_b200/.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../lmcache_b200/csrc/ac_core.cuh"
+
+using namespace b200kv;
+
+namespace {
+struct VecSink {
+    std::vector<uint8_t>* v;
+    void put_word(uint32_t w) {
+        v->push_back((uint8_t)(w >> 24)); v->push_back((uint8_t)(w >> 16));
+        v->push_back((uint8_t)(w >> 8)); v->push_back((uint8_t)w);
+    }
+};
+struct BufSrc {
+    const uint8_t* p; int64_t n, pos;
+    uint32_t next_word() {
+        uint32_t w = 0;
+        for (int i = 0; i < 4; ++i) { w <<= 8; if (pos < n) w |= p[pos]; ++pos; }
+        return w;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// encode `g` symbols (stride sym_stride) with cdf[33] (uint16); returns byte length written to out (cap bytes)
+int64_t sim_encode_stream(const uint16_t* cdf, const int8_t* sym, int64_t sym_stride, int g, uint8_t* out, int64_t cap) {
+    std::vector<uint8_t> v;
+    VecSink sink{&v};
+    EncState st; st.init();
+    for (int i = 0; i < g; ++i) {
+        int s = sym[i * sym_stride];
+        uint32_t c_lo = cdf[s];
+        uint32_t c_hi = (s == kMaxSym) ? 0x10000u : cdf[s + 1];
+        enc_symbol(st, c_lo, c_hi - c_lo, sink);
+    }
+    uint32_t nb = enc_finish(st, sink);
+    if (nb) {
+        uint32_t w = (uint32_t)(st.acc << (32u - nb));
+        for (uint32_t i = 0; i < (nb + 7u) / 8u; ++i) v.push_back((uint8_t)(w >> (24 - 8 * i)));
+    }
+    int64_t n = (int64_t)v.size();
+    if (n <= cap) memcpy(out, v.data(), (size_t)n);
+    return n;
+}
+
+void sim_decode_stream(const uint16_t* cdf, const uint8_t* in, int64_t n, int g, uint8_t* out, int64_t out_stride) {
+    BufSrc src{in, n, 0};
+    DecState st; dec_init(st, src);
+    for (int i = 0; i < g; ++i)
+        out[i * out_stride] = (uint8_t)dec_symbol(st, src, [&](uint32_t k) { return (uint32_t)cdf[k]; }, i == g - 1);
+}
+
+void sim_cdf(const uint32_t* counts, int t, uint16_t* cdf) {
+    CdfAccum a; a.init(t);
+    for (uint32_t i = 0; i < (uint32_t)kLp; ++i) cdf[i] = a.next(i, i < 33 ? counts[i] : 0);
+}
+
+// quantise one row of C halfs given the row max (half bits)
+void sim_quant_row(const uint16_t* x, int dtype, int C, uint16_t max_bits, float maxq, uint8_t* sym) {
+    float f = quant_factor(maxq, half_to_float(max_bits, dtype));
+    for (int c = 0; c < C; ++c) sym[c] = (uint8_t)quant_symbol(half_to_float(x[c], dtype), f, maxq);
+}
+
+void sim_dequant_row(const uint8_t* sym, int C, uint16_t max_bits, int max_dtype, float cq, int out_dtype, uint16_t* out) {
+    float m = half_to_float(max_bits, max_dtype);
+    for (int c = 0; c < C; ++c) out[c] = float_to_half(dequant_value(dequant_lut(sym[c], cq), m), out_dtype);
+}
+
+void sim_half_to_float(const uint16_t* h, int n, int dtype, float* out) { for (int i = 0; i < n; ++i) out[i] = half_to_float(h[i], dtype); }
+void sim_float_to_half(const float* f, int n, int dtype, uint16_t* out) { for (int i = 0; i < n; ++i) out[i] = float_to_half(f[i], dtype); }
+
+void sim_layout(int L, int C, int t, int64_t* out) {
+    Layout lo = make_layout(L, C, t);
+    out[0] = lo.off_cdf; out[1] = lo.off_maxes; out[2] = lo.off_lengths; out[3] = lo.off_payload; out[4] = lo.ngroups;
+}
+}

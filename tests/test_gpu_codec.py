@@ -1,0 +1,304 @@
+"""GPU parity tests of the CUDA codec, through the C ABI (ctypes) and the serde plugins.
+
+Bar: every container section (CDF, maxima, stream lengths, payload bytes) bit-identical to the oracle; decoded KV
+bit-identical to the reference goldens (the north-star tolerance is 1e-3 max-abs; we hold 0)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+MODEL = "lmsys/longchat-7b-16k"
+
+
+def _bits_to_tensor(bits: np.ndarray, dt: int) -> torch.Tensor:
+    return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16 if dt == 0 else torch.float16)
+
+
+def _tensor_bits(t: torch.Tensor) -> np.ndarray:
+    return t.contiguous().cpu().view(torch.int16).numpy().view(np.uint16)
+
+
+def _eq_nan(a: np.ndarray, b: np.ndarray, dt: int) -> bool:
+    """bit equality, except that any NaN matches any NaN (payloads differ between x86 and sm_100)."""
+    if np.array_equal(a, b):
+        return True
+    f = (lambda u: (u.astype(np.uint32) << 16).view(np.float32)) if dt == 0 else (lambda u: u.view(np.float16))
+    fa, fb = f(a), f(b)
+    both_nan = np.isnan(fa) & np.isnan(fb)
+    return bool(np.all((a == b) | both_nan))
+
+
+@pytest.fixture(scope="module")
+def codec():
+    from lmcache_b200.codec import CacheGenCodec
+    return CacheGenCodec(MODEL)
+
+
+def _sections(raw: bytes, L, H, D, t):
+    from lmcache_b200 import _native as N
+    from lmcache_b200.codec import parse_header
+    hd = parse_header(raw)
+    assert (hd.L, hd.H, hd.D, hd.ntokens) == (L, H, D, t)
+    lo = N.container_layout(L, H, D, t)
+    C = H * D
+    G = (t + 255) // 256
+    a = np.frombuffer(raw, np.uint8)
+    cdf = a[lo.off_cdf: lo.off_cdf + 2 * L * C * 33 * 2].view(np.int16).reshape(2 * L, C, 33)
+    maxes = a[lo.off_maxes: lo.off_maxes + 2 * L * t * 2].view(np.uint16).reshape(2, L, t)
+    lengths = a[lo.off_lengths: lo.off_lengths + G * 2 * L * C * 4].view(np.int32).reshape(G, 2 * L, C)
+    payload = a[lo.off_payload: lo.off_payload + hd.payload_bytes]
+    assert hd.total_bytes == lo.off_payload + hd.payload_bytes == len(raw)
+    return cdf, maxes, lengths, payload
+
+
+GOLDEN_CASES = ["bf16_t1", "bf16_t7_L32", "bf16_t40", "bf16_t236", "bf16_t256", "bf16_t300", "bf16_uniform_t16",
+                "fp16_t40", "fp16_uniform_t128"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_encode_container_bit_exact_vs_oracle_and_goldens(codec, golden, name):
+    from lmcache_b200.codec import KvView
+    x = golden[f"{name}/x"]
+    dt = int(golden[f"{name}/dtype"][0])
+    L, _, t, H, D = x.shape
+    kv = _bits_to_tensor(x, dt).cuda()
+    raw = codec.encode_to_host(KvView.from_blob(kv, "vllm"), 0, t, t)[0]
+    cdf, maxes, lengths, payload = _sections(raw, L, H, D, t)
+    # against vectors made by the reference's own functions
+    assert np.array_equal(cdf, golden[f"{name}/cdf"])
+    assert np.array_equal(maxes[0], golden[f"{name}/max_k"].reshape(L, t))
+    assert np.array_equal(maxes[1], golden[f"{name}/max_v"].reshape(L, t))
+    # against the oracle's bitstream
+    kb, vb = golden["key_bins"], golden["value_bins"]
+    enc = O.encode_chunk(x.reshape(L, 2, t, H * D), dt, kb, vb)
+    assert np.array_equal(np.stack([ln for _, ln, _ in enc["groups"]]), lengths)
+    assert np.array_equal(np.concatenate([b for b, _, _ in enc["groups"]]), payload)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+def test_decode_bit_exact_vs_reference_goldens(codec, golden, name, fmt):
+    from lmcache_b200.codec import KvView
+    x = golden[f"{name}/x"]
+    dt = int(golden[f"{name}/dtype"][0])
+    L, _, t, H, D = x.shape
+    kv = _bits_to_tensor(x, dt).cuda()
+    raw = codec.encode_to_host(KvView.from_blob(kv, "vllm"), 0, t, t)[0]
+    if fmt == "vllm":
+        out = torch.zeros((L, 2, t, H, D), dtype=torch.bfloat16, device="cuda")
+        want = golden[f"{name}/deq_vllm_bf16"]
+    else:
+        out = torch.zeros((L, 2, H, t, D), dtype=torch.float16, device="cuda")
+        want = golden[f"{name}/deq_hf_fp16"]
+    codec.decode([raw], KvView.from_blob(out, fmt), [0])
+    torch.cuda.synchronize()
+    assert _eq_nan(_tensor_bits(out), want, 0 if fmt == "vllm" else 1)
+
+
+def test_oracle_made_container_decodes_on_gpu(codec, golden):
+    """Decoder accepts a container assembled entirely on the CPU by the oracle (wire compatibility both ways)."""
+    from lmcache_b200.codec import KvView
+    from lmcache_b200.storage_backend.serde.cachegen_basics import CacheGenGPUBytestream, CacheGenGPUEncoderOutput
+    name = "bf16_t300"
+    x = golden[f"{name}/x"]
+    L, _, t, H, D = x.shape
+    enc = O.encode_chunk(x.reshape(L, 2, t, H * D), 0, golden["key_bins"], golden["value_bins"])
+    mk = torch.from_numpy(enc["maxes"][0].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
+    mv = torch.from_numpy(enc["maxes"][1].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
+    raw = CacheGenGPUEncoderOutput(
+        [CacheGenGPUBytestream(torch.from_numpy(b), torch.from_numpy(ln), g) for b, ln, g in enc["groups"]],
+        torch.from_numpy(enc["cdf"]), mk, mv, H, D).to_bytes()
+    out = torch.zeros((L, 2, t, H, D), dtype=torch.bfloat16, device="cuda")
+    codec.decode([raw], KvView.from_blob(out, "vllm"), [0])
+    torch.cuda.synchronize()
+    assert np.array_equal(_tensor_bits(out), golden[f"{name}/deq_vllm_bf16"])
+
+
+@pytest.mark.parametrize("T,cs", [(600, 256), (256, 64), (700, 300), (100, 256), (1030, 512)])
+@pytest.mark.parametrize("source", ["blob", "tuple", "hf_blob"])
+def test_multichunk_ragged_vs_oracle(codec, T, cs, source):
+    """Several chunks per launch incl. a ragged tail, chunks > 256 tokens (split kernels), tuple and hf sources."""
+    from lmcache_b200.codec import KvView
+    L, H, D = 6, 2, 72                      # C = 144: one full tile + a partial one
+    C = H * D
+    bits = O.synth_kv_bits(L, T, C, seed=T + cs)
+    kv = _bits_to_tensor(bits, 0).reshape(L, 2, T, H, D).cuda()
+    if source == "blob":
+        view = KvView.from_blob(kv, "vllm")
+    elif source == "hf_blob":
+        view = KvView.from_blob(kv.permute(0, 1, 3, 2, 4).contiguous(), "huggingface")
+    else:
+        view = KvView.from_tuple(tuple((kv[l, 0].clone(), kv[l, 1].clone()) for l in range(L)), "vllm")
+    raws = codec.encode_to_host(view, 0, T, cs)
+    kb, vb = O.make_bins(MODEL)
+    n_chunks = (T + cs - 1) // cs
+    assert len(raws) == n_chunks
+    out = torch.zeros((L, 2, T, H, D), dtype=torch.bfloat16, device="cuda")
+    offs = []
+    for j, raw in enumerate(raws):
+        t0, t1 = j * cs, min(T, (j + 1) * cs)
+        enc = O.encode_chunk(bits[:, :, t0:t1], 0, kb, vb)
+        cdf, maxes, lengths, payload = _sections(raw, L, H, D, t1 - t0)
+        assert np.array_equal(cdf, enc["cdf"]), j
+        assert np.array_equal(maxes, enc["maxes"]), j
+        assert np.array_equal(lengths, np.stack([ln for _, ln, _ in enc["groups"]])), j
+        assert np.array_equal(payload, np.concatenate([b for b, _, _ in enc["groups"]])), j
+        offs.append(t0)
+    codec.decode(raws, KvView.from_blob(out, "vllm"), offs)
+    torch.cuda.synchronize()
+    want = np.concatenate([O.decode_chunk(O.encode_chunk(bits[:, :, j * cs:min(T, (j + 1) * cs)], 0, kb, vb), 0, kb, vb, 0)
+                           for j in range(n_chunks)], axis=2)
+    assert np.array_equal(_tensor_bits(out).reshape(L, 2, T, C), want)
+
+
+def test_tok_begin_and_device_container_decode(codec):
+    """Encoding a token sub-range, and decoding straight from the device staging buffer (no host hop)."""
+    from lmcache_b200.codec import KvView
+    L, H, D, T = 4, 1, 128, 512
+    bits = O.synth_kv_bits(L, T, H * D, seed=11)
+    kv = _bits_to_tensor(bits, 0).reshape(L, 2, T, H, D).cuda()
+    batch = codec.encode(KvView.from_blob(kv, "vllm"), 128, 256, 256)
+    dev_container = batch.container(0).clone()
+    out = torch.zeros((L, 2, 256, H, D), dtype=torch.bfloat16, device="cuda")
+    codec.decode([dev_container], KvView.from_blob(out, "vllm"), [0])
+    torch.cuda.synchronize()
+    kb, vb = O.make_bins(MODEL)
+    want = O.decode_chunk(O.encode_chunk(bits[:, :, 128:384], 0, kb, vb), 0, kb, vb, 0)
+    assert np.array_equal(_tensor_bits(out).reshape(L, 2, 256, H * D), want)
+
+
+def test_full_width_chunk_vs_torch_reference_chain(codec):
+    """C = 4096 (Llama-7B width), t = 256: decoded KV vs the reference's torch op chain run on the same GPU
+    (size-independent check; the C oracle is used at small sizes)."""
+    import ref_torch
+    from lmcache_b200.codec import KvView
+    L, H, D, t = 32, 32, 128, 256
+    g = torch.Generator(device="cuda").manual_seed(1)
+    sigma = torch.exp(0.5 * torch.randn((L, 2, 1, H * D), device="cuda", generator=g)).clamp(0.1, 8.0)
+    sigma = torch.where(torch.rand((L, 2, 1, H * D), device="cuda", generator=g) < 0.01, sigma * 10, sigma)
+    kv = (torch.randn((L, 2, t, H * D), device="cuda", generator=g) * sigma).to(torch.bfloat16).reshape(L, 2, t, H, D)
+    kb, vb = (torch.tensor(b) for b in O.make_bins(MODEL))
+    want = ref_torch.roundtrip(kv, kb, vb, "vllm")
+    raw = codec.encode_to_host(KvView.from_blob(kv, "vllm"), 0, t, t)[0]
+    out = torch.empty_like(kv)
+    codec.decode([raw], KvView.from_blob(out, "vllm"), [0])
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), want.view(torch.int16))
+    sym = ref_torch.quantize(kv, kb, vb)[0]
+    bits_per_sym = 8.0 * (len(raw)) / sym.numel()
+    assert bits_per_sym < 8.0
+    # idempotence: re-encoding the decoded KV reproduces the same symbols -> the same decode
+    raw2 = codec.encode_to_host(KvView.from_blob(out, "vllm"), 0, t, t)[0]
+    out2 = torch.empty_like(kv)
+    codec.decode([raw2], KvView.from_blob(out2, "vllm"), [0])
+    torch.cuda.synchronize()
+    assert torch.equal(out2.view(torch.int16), out.view(torch.int16))
+
+
+def test_extreme_inputs(codec):
+    """all-zero block, single outlier rows, +/-inf and NaN rows: no crash, parity with the oracle."""
+    from lmcache_b200.codec import KvView
+    L, H, D, t = 3, 1, 128, 64
+    x = torch.randn(L, 2, t, H, D).to(torch.bfloat16)
+    x[0] = 0
+    x[1, 0, 3, 0, 5] = float("inf")
+    x[1, 1, 4, 0, 6] = float("nan")
+    x[2, 0, :, 0, 7] = 1e30
+    bits = x.view(torch.int16).numpy().view(np.uint16).reshape(L, 2, t, H * D)
+    raw = codec.encode_to_host(KvView.from_blob(x.cuda(), "vllm"), 0, t, t)[0]
+    kb, vb = O.make_bins(MODEL)
+    enc = O.encode_chunk(bits, 0, kb, vb)
+    cdf, maxes, lengths, payload = _sections(raw, L, H, D, t)
+    assert np.array_equal(cdf, enc["cdf"])
+    assert np.array_equal(lengths[0], enc["groups"][0][1])
+    assert np.array_equal(payload, enc["groups"][0][0])
+    out = torch.zeros((L, 2, t, H, D), dtype=torch.bfloat16, device="cuda")
+    codec.decode([raw], KvView.from_blob(out, "vllm"), [0])
+    torch.cuda.synchronize()
+    assert _eq_nan(_tensor_bits(out).reshape(L, 2, t, H * D), O.decode_chunk(enc, 0, kb, vb, 0), 0)
+
+
+# ---------------------------------------------------------------- serde plugins (mirrors reference tests/test_serde.py)
+def _generate_kv_cache(num_tokens, fmt, device):
+    shape = [num_tokens, 8, 128] if fmt == "vllm" else [8, num_tokens, 128]
+    dtype = torch.bfloat16 if fmt == "vllm" else torch.float16
+    return tuple((torch.rand(shape, dtype=dtype, device=device), torch.rand(shape, dtype=dtype, device=device))
+                 for _ in range(32))
+
+
+def _to_blob(kv):
+    return torch.stack([torch.stack(p, dim=0) for p in kv], dim=0)
+
+
+def _meta(fmt):
+    from lmcache_b200.config import LMCacheEngineMetadata
+    return LMCacheEngineMetadata("mistralai/Mistral-7B-Instruct-v0.2", 1, 0, fmt, "bfloat16")
+
+
+@pytest.mark.parametrize("chunk_size", [16, 128, 256])
+def test_cachegen_encoder(chunk_size):
+    from lmcache_b200.config import LMCacheEngineConfig
+    from lmcache_b200.storage_backend.serde.cachegen_basics import CacheGenEncoderOutput
+    from lmcache_b200.storage_backend.serde.cachegen_encoder import CacheGenSerializer
+    cfg = LMCacheEngineConfig.from_defaults(chunk_size=chunk_size)
+    s1, s2 = CacheGenSerializer(cfg, _meta("vllm")), CacheGenSerializer(cfg, _meta("huggingface"))
+    kv = _to_blob(_generate_kv_cache(chunk_size, "vllm", "cuda"))
+    out1 = s1.to_bytes(kv)
+    out2 = s2.to_bytes(kv.permute([0, 1, 3, 2, 4]))
+    assert abs(len(out1) - len(out2)) < 10
+    assert out1 == out2          # same tokens, same bits: the layouts differ only by strides
+    od = CacheGenEncoderOutput.from_bytes(out1)
+    assert od.num_heads == 8 and od.head_size == 128
+
+
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+@pytest.mark.parametrize("chunk_size", [16, 128, 256])
+def test_cachegen_decoder(fmt, chunk_size):
+    import ref_torch
+    from lmcache_b200.config import LMCacheEngineConfig
+    from lmcache_b200.storage_backend.serde import CreateSerde
+    cfg = LMCacheEngineConfig.from_defaults(chunk_size=chunk_size)
+    ser, des = CreateSerde("cachegen", cfg, _meta(fmt))
+    kv = _to_blob(_generate_kv_cache(chunk_size, fmt, "cuda"))
+    dec = des.from_bytes(ser.to_bytes(kv))
+    assert dec.shape == kv.shape and dec.mean() != 0
+    assert dec.dtype == (torch.bfloat16 if fmt == "vllm" else torch.float16)
+    kb, vb = (torch.tensor(b) for b in O.make_bins(MODEL))
+    kv_v = kv if fmt == "vllm" else kv.permute(0, 1, 3, 2, 4)
+    want = ref_torch.roundtrip(kv_v, kb, vb, fmt)
+    assert torch.equal(dec.view(torch.int16), want.contiguous().view(torch.int16))
+    assert torch.equal(des.from_bytes(bytearray(ser.to_bytes(kv))), dec)      # bytearray from the socket path
+
+
+def test_cachegen_unmatched_size():
+    from lmcache_b200.config import LMCacheEngineConfig
+    from lmcache_b200.storage_backend.serde import CreateSerde
+    ser, des = CreateSerde("cachegen", LMCacheEngineConfig.from_defaults(chunk_size=256), _meta("vllm"))
+    kv = _to_blob(_generate_kv_cache(236, "vllm", "cuda"))
+    dec = des.from_bytes(ser.to_bytes(kv))
+    assert dec.shape == kv.shape and dec.mean() != 0
+
+
+def test_batched_plugin_paths_match_per_chunk_calls():
+    from lmcache_b200.config import LMCacheEngineConfig
+    from lmcache_b200.storage_backend.serde.cachegen_decoder import CacheGenDeserializer
+    from lmcache_b200.storage_backend.serde.cachegen_encoder import CacheGenSerializer
+    cfg = LMCacheEngineConfig.from_defaults(chunk_size=128)
+    ser, des = CacheGenSerializer(cfg, _meta("vllm")), CacheGenDeserializer(cfg, _meta("vllm"))
+    kvt = _generate_kv_cache(300, "vllm", "cuda")
+    blob = _to_blob(kvt)
+    per_chunk = [ser.to_bytes(blob[:, :, a:min(300, a + 128)].contiguous()) for a in range(0, 300, 128)]
+    assert ser.to_bytes_batch(blob) == per_chunk
+    assert ser.kv_to_bytes_batch(kvt) == per_chunk
+    whole = des.from_bytes_batch(per_chunk)
+    parts = torch.cat([des.from_bytes(b) for b in per_chunk], dim=2)
+    assert torch.equal(whole, parts)
+
+
+def test_torch_serde_gpu_lossless():
+    from lmcache_b200.storage_backend.serde.torch_serde import TorchDeserializer, TorchSerializer
+    t = torch.randn(4, 2, 256, 4, 64, device="cuda").to(torch.bfloat16)     # BASELINE config 1 shape
+    back = TorchDeserializer().from_bytes(TorchSerializer().to_bytes(t))
+    assert back.device.type == "cpu" and torch.equal(back, t.cpu())

@@ -1,0 +1,367 @@
+"""GPU: engine-level behaviour, mirroring the reference's tests/test_cache_engine.py / test_backends.py
+(lossless round trips, prefix / mixed / suffix-mask semantics, device placement), plus the hash kernel and the
+pack / mover primitives."""
+import hashlib
+import json
+import os
+import socket
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def dumb_metadata(fmt="vllm", model="test_model"):
+    from lmcache_b200.config import LMCacheEngineMetadata
+    return LMCacheEngineMetadata(model, 3, 123, fmt, "half")
+
+
+def generate_kv_cache(num_tokens, fmt, device, num_layers=32, num_heads=8, head_size=128):
+    shape = [num_tokens, num_heads, head_size] if fmt == "vllm" else [num_heads, num_tokens, head_size]
+    dtype = torch.bfloat16 if fmt == "vllm" else torch.float16
+    return tuple((torch.rand(shape, dtype=dtype, device=device), torch.rand(shape, dtype=dtype, device=device))
+                 for _ in range(num_layers))
+
+
+def generate_tokens(num_tokens, device):
+    return torch.randint(0, 10000, size=[num_tokens]).to(device)
+
+
+def concatenate_kv_caches(kv_chunks, fmt):
+    dim = 1 if fmt == "huggingface" else 0
+    return tuple((torch.cat([c[l][0] for c in kv_chunks], dim=dim), torch.cat([c[l][1] for c in kv_chunks], dim=dim))
+                 for l in range(len(kv_chunks[0])))
+
+
+def check_kv_cache_equal(left, right, num_tokens, fmt):
+    for (lk, lv), (rk, rv) in zip(left, right):
+        rk, rv = rk.to(lk.device), rv.to(lv.device)
+        assert lk.dim() == 3 and rk.dim() == 3
+        if fmt == "huggingface":
+            assert (lk[:, :num_tokens, :] == rk[:, :num_tokens, :]).all()
+            assert (lv[:, :num_tokens, :] == rv[:, :num_tokens, :]).all()
+        else:
+            assert (lk[:num_tokens] == rk[:num_tokens]).all()
+            assert (lv[:num_tokens] == rv[:num_tokens]).all()
+
+
+# ---------------------------------------------------------------- hash kernel (a1)
+def test_gpu_hash_matches_reference_goldens():
+    from lmcache_b200.cache_engine import sha256_prefix_chain
+    h = json.load(open(os.path.join(HERE, "golden", "golden_hash.json")))
+    rng = np.random.default_rng(1234)
+    for c in h["cases"]:
+        toks = np.arange(c["n"], dtype=c["dtype"]) if c["label"].startswith("arange") else \
+            rng.integers(0, 32000, c["n"], dtype=np.int64)
+        got = sha256_prefix_chain(torch.from_numpy(toks).cuda(), c["chunk_size"])
+        assert got == c["hashes"], c["label"]
+        assert sha256_prefix_chain(torch.from_numpy(toks), c["chunk_size"]) == c["hashes"]   # host tokens: uploaded
+
+
+def test_gpu_hash_many_sequences_and_sizes():
+    from lmcache_b200.cache_engine import sha256_prefix_chain
+    rng = np.random.default_rng(7)
+    lens = [4096] * 16 + [1, 255, 256, 257, 0, 1000]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    toks = rng.integers(0, 32000, offs[-1], dtype=np.int64)
+    got = sha256_prefix_chain(torch.from_numpy(toks).cuda(), 256, [int(o) for o in offs])
+    want = []
+    for i in range(len(lens)):
+        want += O.sha256_chain(toks[offs[i]:offs[i + 1]], 256)
+    assert got == want
+    # plain sha256 of arbitrary byte strings (chunk_size larger than the message -> single block chain)
+    for n in [1, 55, 56, 63, 64, 65, 119, 120, 1000, 4097]:
+        b = rng.integers(0, 256, n, dtype=np.uint8)
+        assert sha256_prefix_chain(torch.from_numpy(b).cuda(), 1 << 20) == [hashlib.sha256(b.tobytes()).hexdigest()]
+
+
+def test_full_size_chain_property():
+    """65536 tokens / 256: checksum-of-checksums vs the oracle (size-independent property at BASELINE config 3)."""
+    from lmcache_b200.cache_engine import sha256_prefix_chain
+    toks = np.random.default_rng(3).integers(0, 32000, 65536, dtype=np.int64)
+    got = sha256_prefix_chain(torch.from_numpy(toks).cuda(), 256)
+    assert hashlib.sha256("".join(got).encode()).hexdigest() == \
+        hashlib.sha256("".join(O.sha256_chain(toks, 256)).encode()).hexdigest()
+
+
+# ---------------------------------------------------------------- pack / unpack / mover (a4, a14)
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+def test_pack_unpack_match_reference_blob_ops(fmt):
+    import ctypes
+
+    from lmcache_b200 import _native as N
+    from lmcache_b200.codec import KvView
+    L, H, D, T, cs = 5, 3, 64, 300, 128
+    kv = generate_kv_cache(T, fmt, "cuda", L, H, D)
+    # reference: stack/stack/stack/permute then split + contiguous (cache_engine.py:98-161)
+    blob = torch.stack((torch.stack([k for k, _ in kv]), torch.stack([v for _, v in kv]))).permute(1, 0, 2, 3, 4)
+    tdim = 2 if fmt == "vllm" else 3
+    want = [x.contiguous() for x in torch.split(blob, cs, dim=tdim)]
+    view = KvView.from_tuple(kv, fmt)
+    per_tok = 2 * L * H * D
+    buf = torch.zeros(3 * cs * per_tok, dtype=kv[0][0].dtype, device="cuda")
+    N.check(N.lib().b200kv_pack_chunks(ctypes.byref(view.desc), 0, 3, cs, T - 2 * cs, int(fmt == "huggingface"),
+                                       ctypes.c_void_p(buf.data_ptr()), cs * per_tok * 2,
+                                       torch.cuda.current_stream().cuda_stream))
+    for j, w in enumerate(want):
+        got = buf[j * cs * per_tok: j * cs * per_tok + w.numel()].view(w.shape)
+        assert torch.equal(got, w), j
+    # scatter back into fresh tensors
+    kv2 = tuple((torch.zeros_like(k), torch.zeros_like(v)) for k, v in kv)
+    view2 = KvView.from_tuple(kv2, fmt)
+    N.check(N.lib().b200kv_unpack_chunks(ctypes.c_void_p(buf.data_ptr()), cs * per_tok * 2, 3, cs, T - 2 * cs,
+                                         int(fmt == "huggingface"), ctypes.byref(view2.desc), 0,
+                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    check_kv_cache_equal(kv2, kv, T, fmt)
+
+
+def test_mover_primitives_roundtrip():
+    import ctypes
+
+    from lmcache_b200 import _native as N
+    from lmcache_b200.codec import PinnedBuffer
+    lib = N.lib()
+    n = 1 << 20
+    src = torch.randint(0, 255, (n,), dtype=torch.uint8, device="cuda")
+    pin = PinnedBuffer(n)
+    s, e0, e1 = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    N.check(lib.b200kv_stream_create(ctypes.byref(s)))
+    N.check(lib.b200kv_event_create(ctypes.byref(e0)))
+    N.check(lib.b200kv_event_create(ctypes.byref(e1)))
+    torch.cuda.synchronize()
+    N.check(lib.b200kv_event_record(e0, s))
+    N.check(lib.b200kv_copy_async(pin.host_ptr, src.data_ptr(), n, s))
+    N.check(lib.b200kv_event_record(e1, s))
+    N.check(lib.b200kv_event_sync(e1))
+    assert lib.b200kv_event_query(e1) == 0
+    ms = ctypes.c_float()
+    N.check(lib.b200kv_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+    assert ms.value >= 0
+    assert bytes(pin.view()) == src.cpu().numpy().tobytes()
+    dst = torch.zeros_like(src)
+    N.check(lib.b200kv_copy_async(dst.data_ptr(), pin.host_ptr, n, s))
+    # 2-D: rows of 1000 bytes at pitch 1024 -> packed
+    packed = torch.zeros(1000 * 1000, dtype=torch.uint8, device="cuda")
+    N.check(lib.b200kv_copy2d_async(packed.data_ptr(), 1000, src.data_ptr(), 1024, 1000, 1000, s))
+    N.check(lib.b200kv_stream_sync(s))
+    assert torch.equal(dst, src)
+    assert torch.equal(packed.view(1000, 1000), src[:1024 * 1000].view(1000, 1024)[:, :1000])
+    for ev in (e0, e1):
+        N.check(lib.b200kv_event_destroy(ev))
+    N.check(lib.b200kv_stream_destroy(s))
+    pin.close()
+
+
+# ---------------------------------------------------------------- engine (reference tests/test_cache_engine.py)
+@pytest.mark.parametrize("src_device", ["cuda:0", "cuda", "cpu"])
+@pytest.mark.parametrize("backend", ["cuda", "cpu"])
+def test_retrieve_device(backend, src_device, autorelease):
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    tokens = generate_tokens(500, src_device)
+    kv_cache = generate_kv_cache(500, "vllm", src_device)
+    engine = autorelease(LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=256, backend=backend), dumb_metadata()))
+    engine.store(tokens, kv_cache)
+    retrieved, _ = engine.retrieve(tokens)
+    for k, v in retrieved:
+        assert k.device == torch.device("cuda:0") and v.device == torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+@pytest.mark.parametrize("backend", ["cuda", "cpu"])
+@pytest.mark.parametrize("blocking", [True, False])
+def test_same_retrieve_store(fmt, backend, blocking, autorelease):
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    device = "cpu" if backend == "cpu" else "cuda"
+    num_tokens = 2000
+    tokens = generate_tokens(num_tokens, device)
+    kv_cache = generate_kv_cache(num_tokens, fmt, device)
+    engine = autorelease(LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=256, backend=backend), dumb_metadata(fmt)))
+    retrieved, ret_mask = engine.retrieve(tokens)
+    assert len(retrieved) == 0 and torch.sum(ret_mask) == 0
+    engine.store(tokens, kv_cache, blocking=blocking)
+    retrieved, ret_mask = engine.retrieve(tokens)
+    assert torch.sum(ret_mask) == num_tokens
+    check_kv_cache_equal(retrieved, kv_cache, num_tokens, fmt)
+
+
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+@pytest.mark.parametrize("chunk_size", [128, 256])
+@pytest.mark.parametrize("backend", ["cuda", "cpu"])
+def test_retrieve_prefix(fmt, chunk_size, backend, autorelease):
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    num_tokens, new_num_tokens = 2000, 1000
+    tokens = generate_tokens(num_tokens, "cuda")
+    kv_cache = generate_kv_cache(num_tokens, fmt, "cuda")
+    new_tokens = generate_tokens(new_num_tokens, "cuda")
+    engine = autorelease(LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=chunk_size, backend=backend),
+                                       dumb_metadata(fmt)))
+    engine.store(tokens, kv_cache)
+    retrieved, ret_mask = engine.retrieve(torch.cat([tokens, new_tokens]))
+    expected = (num_tokens // chunk_size) * chunk_size
+    assert torch.sum(ret_mask) == expected
+    check_kv_cache_equal(retrieved, kv_cache, expected, fmt)
+
+
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+@pytest.mark.parametrize("chunk_size", [128, 256])
+def test_mixed_retrieve(fmt, chunk_size, autorelease):
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    num_tokens, new_num_tokens = 2000, 1000
+    tokens = generate_tokens(num_tokens, "cuda")
+    kv_cache = generate_kv_cache(num_tokens, fmt, "cuda")
+    new_tokens = generate_tokens(new_num_tokens, "cuda")
+    new_kv_cache = generate_kv_cache(new_num_tokens, fmt, "cuda")
+    engine = autorelease(LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=chunk_size, backend="cuda"),
+                                       dumb_metadata(fmt)))
+    engine.store(tokens, kv_cache)
+    engine.store(new_tokens, new_kv_cache)
+    retrieved, ret_mask = engine.retrieve(torch.cat([tokens, new_tokens]))
+    expected = (num_tokens // chunk_size) * chunk_size
+    assert torch.sum(ret_mask) == expected
+    check_kv_cache_equal(retrieved, kv_cache, expected, fmt)
+    retrieved, ret_mask = engine.retrieve(new_tokens)
+    assert torch.sum(ret_mask) == new_num_tokens
+    check_kv_cache_equal(retrieved, new_kv_cache, new_num_tokens, fmt)
+    final_tokens = torch.cat([tokens, new_tokens])
+    final_kv = concatenate_kv_caches([kv_cache, generate_kv_cache(new_num_tokens, fmt, "cuda")], fmt)
+    engine.store(final_tokens, final_kv)
+    retrieved, ret_mask = engine.retrieve(final_tokens)
+    assert torch.sum(ret_mask) == num_tokens + new_num_tokens
+    check_kv_cache_equal(retrieved, final_kv, num_tokens + new_num_tokens, fmt)
+
+
+def test_golden_engine_semantics(autorelease):
+    """The scalars recorded from the reference engine in this container (tests/golden/golden_engine.json)."""
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    gold = json.load(open(os.path.join(HERE, "golden", "golden_engine.json")))
+    engine = autorelease(LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=256, backend="cpu"), dumb_metadata()))
+    T = 600
+    tokens = torch.arange(T, dtype=torch.int64)
+    kv = generate_kv_cache(T, "vllm", "cuda", 3, 2, 8)
+    r0, m0 = engine.retrieve(tokens)
+    assert (len(r0), int(m0.sum())) == (gold["empty_retrieve"]["n_layers"], gold["empty_retrieve"]["mask_sum"])
+    engine.store(tokens, kv)
+    r1, m1 = engine.retrieve(tokens)
+    assert (int(m1.sum()), r1[0][0].shape[0]) == (gold["full_retrieve"]["mask_sum"], gold["full_retrieve"]["ntok"])
+    check_kv_cache_equal(r1, kv, T, "vllm")
+    longer = torch.cat([tokens, torch.arange(1000, 1400, dtype=torch.int64)])
+    r2, m2 = engine.retrieve(longer)
+    assert (int(m2.sum()), r2[0][0].shape[0]) == (gold["prefix_of_longer"]["mask_sum"], gold["prefix_of_longer"]["ntok"])
+    nz = m2.nonzero()
+    assert [int(nz[0]), int(nz[-1])] == gold["prefix_of_longer"]["mask_true_idx"]
+    mask = torch.ones(T, dtype=torch.bool)
+    mask[:300] = False
+    r3, m3 = engine.retrieve(tokens, mask)
+    assert (int(m3.sum()), r3[0][0].shape[0], int(m3.nonzero()[0])) == \
+        (gold["suffix_mask_300"]["mask_sum"], gold["suffix_mask_300"]["ntok"], gold["suffix_mask_300"]["first_true"])
+    assert torch.equal(r3[0][0], kv[0][0][300:])
+    r4, m4 = engine.retrieve(torch.arange(5000, 5300, dtype=torch.int64))
+    assert (len(r4), int(m4.sum())) == (gold["miss"]["n_layers"], gold["miss"]["mask_sum"])
+
+
+def test_store_asserts_and_builder(autorelease):
+    from lmcache_b200.cache_engine import LMCacheEngine, LMCacheEngineBuilder
+    from lmcache_b200.config import LMCacheEngineConfig
+    cfg = LMCacheEngineConfig.from_legacy(chunk_size=256, backend="cuda")
+    engine = autorelease(LMCacheEngine(cfg, dumb_metadata()))
+    kv = generate_kv_cache(10, "vllm", "cuda", 2, 2, 8)
+    with pytest.raises(AssertionError):
+        engine.store(torch.zeros(2, 5, dtype=torch.int64), kv)
+    with pytest.raises(AssertionError):
+        engine.store(torch.arange(11), kv)
+    with pytest.raises(AssertionError):
+        engine.store(torch.arange(10), ())
+    assert LMCacheEngineBuilder.get("test_b200") is None
+    e1 = autorelease(LMCacheEngineBuilder.get_or_create("test_b200", cfg, dumb_metadata()))
+    assert LMCacheEngineBuilder.get("test_b200") is e1
+    with pytest.raises(ValueError):
+        LMCacheEngineBuilder.get_or_create("test_b200", LMCacheEngineConfig.from_legacy(chunk_size=512, backend="cuda"),
+                                           dumb_metadata())
+    LMCacheEngineBuilder.destroy("test_b200")
+
+
+# ---------------------------------------------------------------- engine over lm:// (serde plugin boundary)
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.fixture(scope="module")
+def lmserver():
+    port = _free_port()
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    proc = subprocess.Popen([sys.executable, "-m", "lmcache_b200.server", "127.0.0.1", str(port)], env=env)
+    for _ in range(100):
+        try:
+            socket.create_connection(("127.0.0.1", port), timeout=0.2).close()
+            break
+        except OSError:
+            time.sleep(0.1)
+    yield f"lm://127.0.0.1:{port}"
+    proc.terminate()
+    proc.wait()
+
+
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+def test_remote_torch_serde_lossless(fmt, lmserver, autorelease):
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    tokens = generate_tokens(600, "cuda")
+    kv = generate_kv_cache(600, fmt, "cuda", 4, 2, 64)
+    cfg = LMCacheEngineConfig.from_legacy(chunk_size=256, backend=lmserver, remote_serde="torch")
+    engine = autorelease(LMCacheEngine(cfg, dumb_metadata(fmt, "m_torch_" + fmt)))
+    engine.store(tokens, kv)
+    r, m = engine.retrieve(tokens)
+    assert torch.sum(m) == 600
+    check_kv_cache_equal(r, kv, 600, fmt)
+    # a second engine (another "instance") sees the same chunks through the shared server
+    engine2 = autorelease(LMCacheEngine(cfg, dumb_metadata(fmt, "m_torch_" + fmt)))
+    r2, m2 = engine2.retrieve(torch.cat([tokens, generate_tokens(100, "cuda")]))
+    assert torch.sum(m2) == 512
+    check_kv_cache_equal(r2, kv, 512, fmt)
+
+
+@pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_remote_cachegen_matches_reference_chain(fmt, pipelined, lmserver, autorelease):
+    import ref_torch
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    model = "mistralai/Mistral-7B-Instruct-v0.2"
+    T = 700
+    tokens = generate_tokens(T, "cuda")
+    kv = generate_kv_cache(T, fmt, "cuda", 32, 8, 128)
+    cfg = LMCacheEngineConfig(256, None, lmserver, "cachegen", pipelined, False)
+    engine = autorelease(LMCacheEngine(cfg, dumb_metadata(fmt, model)))
+    engine.store(tokens, kv, blocking=not pipelined)
+    if pipelined:
+        engine.engine_.put_queue.join()     # non-blocking store: wait for the put worker to drain
+    r, m = engine.retrieve(tokens)
+    assert torch.sum(m) == T
+    kb, vb = (torch.tensor(b) for b in O.make_bins(model))
+    blob = torch.stack((torch.stack([k for k, _ in kv]), torch.stack([v for _, v in kv]))).permute(1, 0, 2, 3, 4)
+    blob_v = blob if fmt == "vllm" else blob.permute(0, 1, 3, 2, 4)
+    tdim = 2
+    want = torch.cat([ref_torch.roundtrip(c, kb, vb, fmt) for c in torch.split(blob_v, 256, dim=tdim)],
+                     dim=2 if fmt == "vllm" else 3)
+    got = torch.stack([torch.stack(p) for p in r])
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert torch.equal(got.view(torch.int16), want.contiguous().view(torch.int16))

@@ -1,0 +1,162 @@
+"""CPU: the product's device arithmetic (lmcache_b200/csrc/ac_core.cuh, compiled for the host by
+tests/hostsim) against the oracle -- same functions the CUDA kernels call."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    S = ctypes.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    S.sim_encode_stream.restype = i64
+    S.sim_encode_stream.argtypes = [vp, vp, i64, i32, vp, i64]
+    S.sim_decode_stream.argtypes = [vp, vp, i64, i32, vp, i64]
+    S.sim_cdf.argtypes = [vp, i32, vp]
+    S.sim_quant_row.argtypes = [vp, i32, i32, ctypes.c_uint16, ctypes.c_float, vp]
+    S.sim_dequant_row.argtypes = [vp, i32, ctypes.c_uint16, i32, ctypes.c_float, i32, vp]
+    S.sim_half_to_float.argtypes = [vp, i32, i32, vp]
+    S.sim_float_to_half.argtypes = [vp, i32, i32, vp]
+    S.sim_layout.argtypes = [i32, i32, i32, vp]
+    return S
+
+
+def P(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _symbols(rng, kind, shape):
+    if kind == "peaked":
+        return np.clip(np.rint(rng.normal(15, 1.5, size=shape)), 0, 30).astype(np.int8)
+    if kind == "uniform":
+        return rng.integers(0, 31, size=shape).astype(np.int8)
+    if kind == "rare":
+        return np.where(rng.random(shape) < 0.02, rng.integers(0, 31, shape), 7).astype(np.int8)
+    if kind == "mid":   # two symbols straddling the midpoint: long E3 (pending) runs
+        return np.where(rng.random(shape) < 0.5, 14, 15).astype(np.int8)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["peaked", "uniform", "rare", "mid"])
+@pytest.mark.parametrize("t", [1, 2, 3, 7, 100, 236, 256])
+def test_coder_bit_exact_vs_oracle(sim, kind, t):
+    rng = np.random.default_rng(hash((kind, t)) & 0xffff)
+    NL, C = 2, 6
+    sym = _symbols(rng, kind, (NL, t, C))
+    cdf = O.cdf(sym)
+    bs, ln = O.encode_group(cdf, sym, 0, t)
+    off = 0
+    for nl in range(NL):
+        for c in range(C):
+            col = np.ascontiguousarray(sym[nl, :, c])
+            cd = np.ascontiguousarray(cdf[nl, c]).view(np.uint16)
+            out = np.zeros(2 * t + 16, np.uint8)
+            n = sim.sim_encode_stream(P(cd), P(col), 1, t, P(out), out.size)
+            ref = np.ascontiguousarray(bs[off:off + ln[nl, c]])
+            assert n == ln[nl, c] and np.array_equal(out[:n], ref)
+            dec = np.zeros(t, np.uint8)
+            sim.sim_decode_stream(P(cd), P(ref), ref.size, t, P(dec), 1)
+            assert np.array_equal(dec, col.view(np.uint8))
+            off += ln[nl, c]
+
+
+def test_coder_foreign_cdf_expensive_symbols(sim):
+    """Group coded with a CDF that is NOT its own histogram (chunk > 256 tokens): symbols may cost up to 16
+    bits and pending runs get long; encoder and decoder must still match the bit-by-bit oracle."""
+    rng = np.random.default_rng(99)
+    t_total, g, NL, C = 8192, 256, 1, 8
+    base = np.full((NL, t_total, C), 15, np.int8)
+    base[:, :g, :] = rng.integers(0, 31, size=(NL, g, C))      # first group uses symbols that are rare chunk-wide
+    cdf = O.cdf(base)
+    bs, ln = O.encode_group(cdf, base, 0, g)
+    assert ln.max() > g                                         # > 8 bits / symbol really happens
+    off = 0
+    for c in range(C):
+        col = np.ascontiguousarray(base[0, :g, c])
+        cd = np.ascontiguousarray(cdf[0, c]).view(np.uint16)
+        out = np.zeros(2 * g + 16, np.uint8)
+        n = sim.sim_encode_stream(P(cd), P(col), 1, g, P(out), out.size)
+        ref = np.ascontiguousarray(bs[off:off + ln[0, c]])
+        assert n == ln[0, c] and np.array_equal(out[:n], ref)
+        dec = np.zeros(g, np.uint8)
+        sim.sim_decode_stream(P(cd), P(ref), ref.size, g, P(dec), 1)
+        assert np.array_equal(dec, col.view(np.uint8))
+        off += ln[0, c]
+
+
+def test_cdf_bit_exact_vs_golden(sim, golden, golden_names):
+    for n in golden_names:
+        sym, cdf = golden[f"{n}/sym"], golden[f"{n}/cdf"]
+        NL, t, C = sym.shape
+        for nl in range(0, NL, 5):
+            for c in range(0, C, 7):
+                counts = np.bincount(sym[nl, :, c], minlength=33)[:33].astype(np.uint32)
+                out = np.zeros(33, np.uint16)
+                sim.sim_cdf(P(counts), t, P(out))
+                assert np.array_equal(out.view(np.int16), cdf[nl, c]), (n, nl, c)
+
+
+def test_quant_dequant_bit_exact_vs_golden(sim, golden, golden_names):
+    kb, vb = golden["key_bins"], golden["value_bins"]
+    for n in golden_names:
+        x = golden[f"{n}/x"]
+        dt = int(golden[f"{n}/dtype"][0])
+        L, _, t, H, D = x.shape
+        C = H * D
+        x = x.reshape(L, 2, t, C)
+        sym = golden[f"{n}/sym"]
+        mk, mv = golden[f"{n}/max_k"].reshape(L, t), golden[f"{n}/max_v"].reshape(L, t)
+        deq = golden[f"{n}/deq_vllm_bf16"].reshape(L, 2, t, C)
+        for l in range(L):
+            for kv in range(2):
+                bins = (vb if kv else kb)[l]
+                maxq = float(bins // 2 - 1)
+                for tok in range(0, t, max(1, t // 5)):
+                    mb = int((mv if kv else mk)[l, tok])
+                    row = np.ascontiguousarray(x[l, kv, tok])
+                    out = np.zeros(C, np.uint8)
+                    sim.sim_quant_row(P(row), dt, C, mb, maxq, P(out))
+                    assert np.array_equal(out, sym[kv * L + l, tok].view(np.uint8)), (n, l, kv, tok)
+                    dq = np.zeros(C, np.uint16)
+                    sim.sim_dequant_row(P(out), C, mb, dt, maxq, 0, P(dq))
+                    assert np.array_equal(dq, deq[l, kv, tok]), (n, l, kv, tok)
+
+
+def test_half_conversions_exhaustive(sim):
+    allh = np.arange(65536, dtype=np.uint16)
+    f = np.zeros(65536, np.float32)
+    sim.sim_half_to_float(P(allh), 65536, 1, P(f))
+    ref = allh.view(np.float16).astype(np.float32)
+    assert np.array_equal(f.view(np.uint32), ref.view(np.uint32))
+    sim.sim_half_to_float(P(allh), 65536, 0, P(f))
+    assert np.array_equal(f.view(np.uint32), allh.astype(np.uint32) << 16)
+    # float -> half, RNE, over a dense sample incl. ties, subnormals, overflow
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([
+        rng.standard_normal(200000).astype(np.float32) * np.float32(10.0) ** rng.integers(-9, 6, 200000).astype(np.float32),
+        ref[np.isfinite(ref)], np.array([65504.0, 65519.9, 65520.0, 1e9, -1e9, 2.0 ** -24, 2.0 ** -25, 1.5 * 2.0 ** -25,
+                                          np.inf, -np.inf, 0.0, -0.0], np.float32)])
+    mids = (ref[:-1].astype(np.float64) + ref[1:].astype(np.float64)) / 2   # exact ties between neighbours
+    vals = np.concatenate([vals, mids[np.isfinite(mids)].astype(np.float32)]).astype(np.float32)
+    out = np.zeros(vals.size, np.uint16)
+    sim.sim_float_to_half(P(vals), vals.size, 1, P(out))
+    with np.errstate(over="ignore"):
+        assert np.array_equal(out, vals.astype(np.float16).view(np.uint16))
+    sim.sim_float_to_half(P(vals), vals.size, 0, P(out))
+    assert np.array_equal(out, O.f32_to_bf16_bits(vals))
+
+
+def test_layout_matches_c_abi(sim):
+    from lmcache_b200 import _native as N
+    for (L, H, D, t) in [(32, 32, 128, 256), (12, 1, 16, 300), (40, 2, 128, 17), (1, 1, 1, 1)]:
+        lo = N.container_layout(L, H, D, t)
+        out = np.zeros(5, np.int64)
+        sim.sim_layout(L, H * D, t, P(out))
+        assert (lo.off_cdf, lo.off_maxes, lo.off_lengths, lo.off_payload) == tuple(out[:4])
+        assert lo.off_payload % 16 == 0 and lo.max_total_bytes >= lo.off_payload
