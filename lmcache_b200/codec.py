@@ -167,6 +167,7 @@ class EncodedBatch:
     buf: torch.Tensor            # uint8 device staging
     stride: int
     sizes: List[int]             # total bytes per container (host, valid after the call returns)
+    max_dtype: int = 0           # dtype code of the stored row maxima (== input dtype)
 
     def container(self, j: int) -> torch.Tensor:
         return self.buf[j * self.stride: j * self.stride + self.sizes[j]]
@@ -245,7 +246,7 @@ class CacheGenCodec:
             for j, s in enumerate(sizes):
                 if s < N.HEADER_BYTES or s > stride:
                     raise N.NativeError(f"encoder produced an invalid container size {s} for chunk {j}")
-            return EncodedBatch(out, stride, [int(s) for s in sizes])
+            return EncodedBatch(out, stride, [int(s) for s in sizes], int(view.desc.dtype))
 
     def encode_to_host(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
                        stream: Optional[torch.cuda.Stream] = None) -> List[bytes]:
@@ -270,10 +271,57 @@ class CacheGenCodec:
         return outs
 
     # ------------------------------------------------------------------ decode
+    def _order_decode(self, tstream, need_in: int, need_ws: int) -> None:
+        """staging / workspace are reused across calls: order after the previous decode and never free a
+        buffer a kernel may still be reading."""
+        if self._dec_event is None:
+            return
+        if ((self._dec_in is not None and self._dec_in.numel() < need_in) or
+                (self._dec_ws is not None and self._dec_ws.numel() < need_ws)):
+            self._dec_event.synchronize()
+        else:
+            tstream.wait_event(self._dec_event)
+
+    def decode_raw(self, base_ptr: int, offsets: Sequence[int], ntokens: Sequence[int], dst: KvView,
+                   dst_tok: Sequence[int], max_dtype: int, stream: Optional[torch.cuda.Stream] = None,
+                   _locked: bool = False) -> None:
+        """Decode containers that already sit in device memory at base_ptr + offsets[j] (asynchronous)."""
+        n = len(offsets)
+        if n == 0:
+            return
+        lib = N.lib()
+        tmax = max(ntokens)
+
+        def run():
+            tstream = stream if stream is not None else torch.cuda.current_stream()
+            ws_bytes = lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n)
+            if not _locked:
+                self._order_decode(tstream, 0, ws_bytes)
+            self._dec_ws = self._grow(self._dec_ws, ws_bytes, dst.device)
+            N.check(lib.b200kv_decode_chunks(base_ptr, N.i64_array(list(offsets)), N.i32_array(list(ntokens)),
+                                             N.i64_array(list(dst_tok)), n, int(max_dtype), ctypes.byref(dst.desc),
+                                             self._kb, self._vb, self._dec_ws.data_ptr(), self._dec_ws.numel(),
+                                             tstream.cuda_stream), "decode_chunks")
+            if self._dec_event is None:
+                self._dec_event = torch.cuda.Event()
+            self._dec_event.record(tstream)
+
+        if _locked:
+            run()
+        else:
+            with self._dec_lock, torch.cuda.device(dst.device):
+                run()
+
+    def decode_device_batch(self, batch: EncodedBatch, ntokens: Sequence[int], dst: KvView, dst_tok: Sequence[int],
+                            stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Decode an EncodedBatch straight from its device staging buffer (no host hop, no header reads)."""
+        self.decode_raw(batch.buf.data_ptr(), [j * batch.stride for j in range(len(batch.sizes))], ntokens, dst,
+                        dst_tok, batch.max_dtype, stream)
+
     def decode(self, containers: Sequence[Union[bytes, bytearray, memoryview, torch.Tensor]], dst: KvView,
                dst_tok: Sequence[int], stream: Optional[torch.cuda.Stream] = None) -> None:
         """Decode containers into `dst` at token offsets `dst_tok` (asynchronous on `stream`).
-        Host containers are uploaded first; device uint8 tensors are used in place."""
+        Host containers are uploaded first; a single 16-byte-aligned device tensor is used in place."""
         n = len(containers)
         if n == 0:
             return
@@ -281,7 +329,7 @@ class CacheGenCodec:
         heads = []
         for c in containers:
             if isinstance(c, torch.Tensor):
-                hb = c[:N.HEADER_BYTES].cpu().numpy().tobytes() if c.is_cuda else c[:N.HEADER_BYTES].numpy().tobytes()
+                hb = c[:N.HEADER_BYTES].cpu().numpy().tobytes()
                 hd = N.Header.from_buffer_copy(hb)
                 if hd.magic != N.MAGIC or hd.status != 0 or hd.total_bytes > c.numel():
                     raise ValueError("bad B2KV container tensor")
@@ -294,51 +342,32 @@ class CacheGenCodec:
         max_dtype = heads[0].max_dtype
         if any(h.max_dtype != max_dtype for h in heads):
             raise ValueError("containers of one decode call must share max_dtype")
-        tmax = max(h.ntokens for h in heads)
+        ntoks = [int(h.ntokens) for h in heads]
+        tmax = max(ntoks)
         with self._dec_lock, torch.cuda.device(dst.device):
             tstream = stream if stream is not None else torch.cuda.current_stream()
             sp = tstream.cuda_stream
-            if self._dec_event is not None:
-                # staging / workspace are reused: order after the previous decode, and never free a
-                # buffer a kernel may still be reading
-                need_in = sum(((int(h.total_bytes) + 15) & ~15) + 16 for h in heads) + 16
-                need_ws = lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n)
-                if ((self._dec_in is not None and self._dec_in.numel() < need_in) or
-                        (self._dec_ws is not None and self._dec_ws.numel() < need_ws)):
-                    self._dec_event.synchronize()
+            need_in = sum(((int(h.total_bytes) + 15) & ~15) + 16 for h in heads) + 16
+            self._order_decode(tstream, need_in, lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n))
+            if n == 1 and isinstance(containers[0], torch.Tensor) and containers[0].is_cuda \
+                    and containers[0].data_ptr() % 16 == 0:
+                keep_dev = containers[0]
+                self.decode_raw(keep_dev.data_ptr(), [0], ntoks, dst, dst_tok, max_dtype, tstream, _locked=True)
+                return
+            self._dec_in = self._grow(self._dec_in, need_in, dst.device)
+            base_ptr = self._dec_in.data_ptr()
+            offsets, o = [], 0
+            for c, h in zip(containers, heads):
+                nb = int(h.total_bytes)
+                if isinstance(c, torch.Tensor):
+                    keep = c
+                    src_ptr = c.data_ptr()
                 else:
-                    tstream.wait_event(self._dec_event)
-            all_dev = all(isinstance(c, torch.Tensor) and c.is_cuda for c in containers)
-            offsets = []
-            if all_dev and n == 1:
-                base_ptr = containers[0].data_ptr()
-                if base_ptr % 16:
-                    raise ValueError("device container must be 16-byte aligned")
-                offsets = [0]
-            else:
-                total = sum(((int(h.total_bytes) + 15) & ~15) + 16 for h in heads)
-                self._dec_in = self._grow(self._dec_in, total + 16, dst.device)
-                base_ptr = self._dec_in.data_ptr()
-                o = 0
-                for c, h in zip(containers, heads):
-                    nb = int(h.total_bytes)
-                    if isinstance(c, torch.Tensor):
-                        keep = c
-                        src_ptr = c.data_ptr()
-                    else:
-                        keep = np.frombuffer(c, dtype=np.uint8, count=nb)   # zero-copy view of bytes/bytearray/memoryview
-                        src_ptr = keep.ctypes.data
-                    # pageable sources are staged by the driver before the call returns
-                    N.check(lib.b200kv_copy_async(base_ptr + o, src_ptr, nb, sp), "copy")
-                    del keep
-                    offsets.append(o)
-                    o += ((nb + 15) & ~15) + 16
-            ws_bytes = lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n)
-            self._dec_ws = self._grow(self._dec_ws, ws_bytes, dst.device)
-            N.check(lib.b200kv_decode_chunks(base_ptr, N.i64_array(offsets), N.i32_array([h.ntokens for h in heads]),
-                                             N.i64_array(list(dst_tok)), n, int(max_dtype), ctypes.byref(dst.desc),
-                                             self._kb, self._vb, self._dec_ws.data_ptr(), self._dec_ws.numel(), sp),
-                    "decode_chunks")
-            if self._dec_event is None:
-                self._dec_event = torch.cuda.Event()
-            self._dec_event.record(tstream)
+                    keep = np.frombuffer(c, dtype=np.uint8, count=nb)   # zero-copy view of bytes/bytearray/memoryview
+                    src_ptr = keep.ctypes.data
+                # pageable sources are staged by the driver before the call returns
+                N.check(lib.b200kv_copy_async(base_ptr + o, src_ptr, nb, sp), "copy")
+                del keep
+                offsets.append(o)
+                o += ((nb + 15) & ~15) + 16
+            self.decode_raw(base_ptr, offsets, ntoks, dst, dst_tok, max_dtype, tstream, _locked=True)
