@@ -56,6 +56,30 @@ B2_HD uint32_t clz32(uint32_t x) {  // x != 0
 #endif
 }
 
+// upper 32 bits of (hi:lo) << n, 0 <= n <= 31
+B2_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, n);
+#else
+    return n ? ((hi << n) | (lo >> (32u - n))) : hi;
+#endif
+}
+// lower 32 bits of (hi:lo) >> n, 0 <= n <= 31
+B2_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, n);
+#else
+    return n ? ((lo >> n) | (hi << (32u - n))) : lo;
+#endif
+}
+B2_HD uint32_t bswap32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0u, 0x0123);
+#else
+    return __builtin_bswap32(v);
+#endif
+}
+
 // fp32 ops that must not be contracted / reordered
 B2_HD float fdiv(float a, float b) {
 #if defined(__CUDA_ARCH__)
@@ -143,9 +167,15 @@ B2_HD float quant_factor(float maxq, float row_max) { return fdiv(maxq, row_max)
 
 // symbol = int8( round_half_even( x * factor + MAX ) ), NaN -> 0
 B2_HD uint32_t quant_symbol(float x, float factor, float maxq) {
-    float q = frint(fadd(fmul(x, factor), maxq));
-    if (q != q) return 0u;
-    return (uint32_t)(int)q & 0xffu;
+    const float v = fadd(fmul(x, factor), maxq);
+#if defined(__CUDA_ARCH__)
+    const uint32_t q = (uint32_t)__float2int_rn(v);       // round-half-even; NaN -> 0; +-inf saturate
+#else
+    const float r = frint(v);
+    const uint32_t q = (r >= -1.0f && r <= 1000.0f) ? (uint32_t)(int)r : 0xffffffffu;
+#endif
+    // valid symbols are 0..2*MAX <= 30; NaN / +-inf rows give 0, as torch's float->int8 cast does on x86
+    return q <= 30u ? q : 0u;
 }
 
 // LUT entry: (sym - C) / C ; value = lut * float(max_half)
@@ -231,6 +261,89 @@ B2_HD void enc_symbol(EncState& st, uint32_t c_lo, uint32_t width, Sink& sink) {
     st.high = (high << m) | 0x80000000u | ((1u << m) - 1u);
 }
 
+// ---- production encoder step: same bitstream as enc_symbol, organised for SIMT execution.
+// State keeps `rng = high - low` instead of high; emission is predicated instead of branched:
+//   n leading agreed bits + p pending bits form ONE (n+p)-bit value  V = top + ((2^p - 1) << (n-1))
+// (b0 followed by p copies of !b0 followed by the other n-1 bits, written as a carry), appended to a 64-bit
+// accumulator; at most one 32-bit word leaves the accumulator per symbol.  Only p + n > 32 (a pending run
+// longer than a word) takes a real branch.
+struct EncState2 {
+    uint32_t low, rng, pending;
+    uint64_t acc;
+    uint32_t nb;     // valid bits in acc, < 32 between calls
+    uint32_t w;      // words written to the row so far
+    B2_HD void init() { low = 0u; rng = 0xFFFFFFFFu; pending = 0u; acc = 0ull; nb = 0u; w = 0u; }
+};
+
+// row: word-addressed output row with capacity `cap` words (stores are clamped to the last word so a
+// violated size bound can never write outside the row; the bound itself is proven in DESIGN.md 3.2)
+B2_HD void enc_symbol2(EncState2& st, uint32_t c_lo, uint32_t width, uint32_t* row, uint32_t cap) {
+    const uint32_t r = st.rng;
+    const uint32_t c_hi = c_lo + width;
+    const uint32_t plo = (uint32_t)(((uint64_t)r * c_lo + c_lo) >> 16);
+    const uint32_t phi = (uint32_t)(((uint64_t)r * c_hi + c_hi) >> 16);   // wraps to 0 when it is 2^32
+    uint32_t low = st.low + plo;
+    uint32_t high = st.low + phi - 1u;
+    const uint32_t n = clz32((low ^ high) | 1u);
+    const uint32_t top = funnel_l(low, 0u, n);                 // n leading bits of low (0 when n == 0)
+    low <<= n;
+    high = (high << n) | ((1u << n) - 1u);
+    const uint32_t m = clz32((((~low) | high) << 1) | 1u);
+    uint32_t p = st.pending;
+    uint32_t v, k;
+    if (p + n > 32u && n != 0u) {                               // rare, warp-uniformly not taken: long pending run
+        const uint32_t b0 = top >> (n - 1u);
+        const uint32_t fill = b0 ? 0u : 0xFFFFFFFFu;
+        st.acc = (st.acc << 1) | b0; st.nb += 1u;
+        if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
+        while (p) {
+            const uint32_t kk = p < 32u ? p : 32u;
+            st.acc = (st.acc << kk) | (kk == 32u ? fill : (fill & ((1u << kk) - 1u)));
+            st.nb += kk;
+            if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
+            p -= kk;
+        }
+        v = top & ((1u << (n - 1u)) - 1u);
+        k = n - 1u;
+    } else {
+        // predicated: mask = all ones iff bits are emitted
+        const uint32_t mask = n != 0u ? 0xFFFFFFFFu : 0u;
+        v = (top + ((((1u << (p & 31u)) - 1u) << ((n - 1u) & 31u)))) & mask;
+        k = (n + p) & mask;
+        p &= ~mask;
+    }
+    st.pending = p + m;
+    st.low = (low << m) & 0x7FFFFFFFu;
+    st.rng = ((high << m) | 0x80000000u | ((1u << m) - 1u)) - st.low;
+    st.acc = (st.acc << k) | (uint64_t)v;
+    const uint32_t nb = st.nb + k;
+    const bool flush = nb >= 32u;
+    const uint32_t nb2 = nb & 31u;                              // nb < 64: subtract 32 iff flushing
+    const uint32_t word = bswap32((uint32_t)(st.acc >> nb2));   // meaningful only when flushing
+    if (flush) row[st.w < cap ? st.w : cap - 1u] = word;        // single predicated store
+    st.w += flush ? 1u : 0u;
+    st.nb = nb2;
+}
+
+// terminate: final bit + pending, zero pad; returns the stream's byte length
+B2_HD uint32_t enc_finish2(EncState2& st, uint32_t* row, uint32_t cap) {
+    uint32_t p = st.pending + 1u;
+    const uint32_t bit = st.low < 0x40000000u ? 0u : 1u;
+    const uint32_t fill = bit ? 0u : 0xFFFFFFFFu;
+    st.acc = (st.acc << 1) | bit; st.nb += 1u;
+    if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
+    while (p) {
+        const uint32_t kk = p < 32u ? p : 32u;
+        st.acc = (st.acc << kk) | (kk == 32u ? fill : (fill & ((1u << kk) - 1u)));
+        st.nb += kk;
+        if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
+        p -= kk;
+    }
+    const uint32_t full = st.w;
+    if (st.nb) { row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc << (32u - st.nb))); st.w++; }
+    return 4u * full + ((st.nb + 7u) >> 3);
+}
+
 // terminate the stream; returns the number of trailing bits (0..31) still in st.acc (left to the caller
 // to write, zero padded to a byte), after the final bit + pending bits were queued.
 template <class Sink>
@@ -304,6 +417,100 @@ B2_HD uint32_t dec_symbol(DecState& st, Src& src, CdfFn cdf, bool last) {
     }
     st.low = low; st.high = high; st.value = value;
     return lo;
+}
+
+// ---- production decoder step: same symbols as dec_symbol, organised for SIMT execution.
+//  * symbol search: a per-stream 32-entry inverse table gives a guaranteed lower bound s0 <= s from an
+//    approximate bucket of (value - low) / span (one float reciprocal, error margins below), then a short
+//    upward walk on exact products (span * cdf[s+1]) >> 16 <= off finds s; typically 0-1 steps.
+//    Products fit 32 bits for every real CDF entry (cdf <= 65535); the sentinel cdf(32) = 65536 is never
+//    multiplied (phi = span, computed as rng + 1 with 32-bit wrap, matching the reference's uint32 maths).
+//  * renormalisation consumes n + m <= 18 bits per symbol from a 64-bit left-aligned reservoir that is kept
+//    at >= 32 valid bits by one predicated aligned-word refill per symbol.
+constexpr uint32_t kInvBuckets = 32;       // buckets of 2048 counts
+constexpr uint32_t kInvRowBytes = 36;      // 32 entries + pad (9 words, odd -> conflict-free columns)
+
+struct DecState2 {
+    uint32_t low, rng, value;
+    uint64_t res;      // left-aligned bit reservoir
+    uint32_t rb;       // valid bits in res (>= 32 at the start of every symbol)
+};
+
+// Word source concept: uint32_t next_be() -- next 4 stream bytes as a big-endian word (aligned load + swap).
+template <class Src>
+B2_HD void dec_refill2(DecState2& st, Src& src) {
+    if (st.rb < 32u) {
+        st.res |= (uint64_t)src.next_be() << (32u - st.rb);
+        st.rb += 32u;
+    }
+}
+
+// `skip` = number of leading bytes of the first aligned word that belong to the previous stream (0..3)
+template <class Src>
+B2_HD void dec_init2(DecState2& st, Src& src, uint32_t skip) {
+    st.low = 0u; st.rng = 0xFFFFFFFFu;
+    const uint32_t w0 = src.next_be();
+    st.res = (uint64_t)w0 << (32u + 8u * skip);
+    st.rb = 32u - 8u * skip;
+    dec_refill2(st, src);
+    st.value = (uint32_t)(st.res >> 32);
+    st.res <<= 32;
+    st.rb -= 32u;
+    dec_refill2(st, src);
+}
+
+// Build the inverse table of one stream: inv[b] = max{ s in 0..31 : cdf(s) <= b * 2048 }
+template <class CdfFn, class PutFn>
+B2_HD void dec_build_inv(CdfFn cdf, PutFn put) {
+    uint32_t s = 0u;
+    for (uint32_t b = 0u; b < kInvBuckets; ++b) {
+        const uint32_t target = b * 2048u;
+        while (s < 31u && cdf(s + 1u) <= target) ++s;
+        put(b, s);
+    }
+}
+
+B2_HD uint32_t dec_bucket(uint32_t off, uint32_t rng) {
+    // A = off * 32 / span, pushed down by more than 1/2048 + float error so that floor(A) * 2048 <= count
+#if defined(__CUDA_ARCH__)
+    const float a = __fmaf_rn(__fdividef(__uint2float_rn(off), __uint2float_rn(rng)), 31.99968f, -0.002f);
+    return (uint32_t)max(__float2int_rz(a), 0);
+#else
+    const float a = ((float)off * (1.0f / (float)rng)) * 31.99968f - 0.002f;
+    const int b = (int)a;
+    return (uint32_t)(b < 0 ? 0 : b);
+#endif
+}
+
+template <class Src, class CdfFn, class InvFn>
+B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, CdfFn cdf, InvFn inv, bool last) {
+    const uint32_t r = st.rng;
+    const uint32_t off = st.value - st.low;
+    uint32_t s = inv(dec_bucket(off, r));
+    const uint32_t c0 = cdf(s);
+    uint32_t plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
+    uint32_t phi;
+    for (;;) {
+        if (s == 31u) { phi = r + 1u; break; }
+        const uint32_t c1 = cdf(s + 1u);
+        const uint32_t p1 = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);
+        if (p1 <= off) { ++s; plo = p1; } else { phi = p1; break; }
+    }
+    if (last) return s;
+    uint32_t low = st.low + plo;
+    uint32_t high = st.low + phi - 1u;
+    const uint32_t n = clz32((low ^ high) | 1u);
+    low <<= n;
+    high = (high << n) | ((1u << n) - 1u);
+    const uint32_t m = clz32((((~low) | high) << 1) | 1u);
+    const uint32_t k = n + m;                                    // <= 18 for 16-bit CDFs
+    st.value = funnel_l((uint32_t)(st.res >> 32), st.value, k) ^ (m ? 0x80000000u : 0u);
+    st.res <<= k;
+    st.rb -= k;
+    st.low = (low << m) & 0x7FFFFFFFu;
+    st.rng = ((high << m) | 0x80000000u | ((1u << m) - 1u)) - st.low;
+    dec_refill2(st, src);
+    return s;
 }
 
 // ---------------------------------------------------------------- container layout (host + device)

@@ -11,6 +11,8 @@
 // and the tile's byte streams are contiguous in the container, so they are staged through shared
 // memory and written/read as one contiguous segment.  Stream compaction (collect_bytes in the
 // reference) happens inside the encode kernel with a decoupled look-back prefix over tiles.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     constexpr int RW = FUSED ? ROWW : ROWW_OUT;
     uint32_t* rows = smem;
     uint32_t* pair = rows + CT * RW;
-    float* fac = reinterpret_cast<float*>(pair + CT * PAIRW);
+    float* fac = reinterpret_cast<float*>(smem + ((CT * RW + CT * PAIRW + 3) & ~3));   // 16-byte aligned (float4 loads)
     uint32_t* s_off = reinterpret_cast<uint32_t*>(fac + kGroup);
     uint32_t* s_len = s_off + CT;
     __shared__ uint32_t s_tile;
@@ -257,25 +259,29 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
         for (int i = 0; i < PAIRW; ++i) prow[i] = 0u;
         __syncthreads();   // fac ready
         if (active) {
-            const int nwords = (gt + 3) >> 2;
-            for (int w = 0; w < nwords; ++w) {
-                uint16_t xb[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int tok = 4 * w + k;
-                    xb[k] = tok < gt ? __ldg(src + (int64_t)tok * P.sT) : (uint16_t)0;
-                }
+            // full words: 4 tokens per iteration, no per-token predicates; pointer strides instead of 64-bit multiplies
+            const int nfull = gt >> 2;
+            const int64_t s1 = P.sT;
+            const uint16_t* p = src;
+#pragma unroll 2
+            for (int w = 0; w < nfull; ++w, p += 4 * s1) {
+                const uint16_t x0 = __ldg(p), x1 = __ldg(p + s1), x2 = __ldg(p + 2 * s1), x3 = __ldg(p + 3 * s1);
+                const float4 f = *reinterpret_cast<const float4*>(fac + 4 * w);
+                const uint32_t q0 = quant_symbol(half_to_float(x0, DT), f.x, maxq);
+                const uint32_t q1 = quant_symbol(half_to_float(x1, DT), f.y, maxq);
+                const uint32_t q2 = quant_symbol(half_to_float(x2, DT), f.z, maxq);
+                const uint32_t q3 = quant_symbol(half_to_float(x3, DT), f.w, maxq);
+                hist[q0] += 1; hist[q1] += 1; hist[q2] += 1; hist[q3] += 1;     // symbols are <= 30 by construction
+                myrow[w] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            }
+            if (gt & 3) {
                 uint32_t word = 0u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int tok = 4 * w + k;
-                    if (tok < gt) {
-                        const uint32_t s = quant_symbol(half_to_float(xb[k], DT), fac[tok], maxq);
-                        word |= s << (8 * k);
-                        hist[s & 31u] += 1;   // symbols are <= 30 by construction; &31 keeps a corrupt input in-row
-                    }
+                for (int k = 0; k < (gt & 3); ++k) {
+                    const uint32_t q = quant_symbol(half_to_float(__ldg(p + k * s1), DT), fac[4 * nfull + k], maxq);
+                    hist[q] += 1;
+                    word |= q << (8 * k);
                 }
-                myrow[w] = word;
+                myrow[nfull] = word;
             }
             // ---- CDF from the thread's own histogram (16 words -> registers), pair row built in place
             uint32_t hw[16];
@@ -306,44 +312,48 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
         }
     }
 
-    // ---- pass 2: arithmetic-code the group
-    uint32_t len = 0u, ovf = 0u;
+    // ---- pass 2: arithmetic-code the group (branch-light core, see ac_core.cuh)
+    uint32_t len = 0u;
     if (active) {
-        EncState st;
+        EncState2 st;
         st.init();
-        RowSink sink{myrow, 0u, (uint32_t)RW, 0u};
         if (FUSED) {
-            const int nwords = (gt + 3) >> 2;
-            for (int w = 0; w < nwords; ++w) {
+            // in place: after n symbols at most n bytes have been emitted (own CDF => <= 8 bits/symbol), and word w is
+            // already in a register when the coder may overwrite it
+            const int nfull = gt >> 2;
+            for (int w = 0; w < nfull; ++w) {
                 const uint32_t word = myrow[w];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (4 * w + k < gt) {
-                        const uint32_t pr = prow[(word >> (8 * k)) & 31u];
-                        enc_symbol(st, pr & 0xffffu, pr >> 16, sink);
-                    }
+                    const uint32_t pr = prow[(word >> (8 * k)) & 31u];
+                    enc_symbol2(st, pr & 0xffffu, pr >> 16, myrow, (uint32_t)RW);
+                }
+            }
+            if (gt & 3) {
+                const uint32_t word = myrow[nfull];
+                for (int k = 0; k < (gt & 3); ++k) {
+                    const uint32_t pr = prow[(word >> (8 * k)) & 31u];
+                    enc_symbol2(st, pr & 0xffffu, pr >> 16, myrow, (uint32_t)RW);
                 }
             }
         } else {
-            for (int tk = 0; tk < gt; tk += 4) {
+            const int64_t s1 = P.sT;
+            const uint16_t* p = src;
+            for (int tk = 0; tk < gt; tk += 4, p += 4 * s1) {
                 uint16_t xb[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) xb[k] = (tk + k < gt) ? __ldg(src + (int64_t)(tk + k) * P.sT) : (uint16_t)0;
+                for (int k = 0; k < 4; ++k) xb[k] = (tk + k < gt) ? __ldg(p + k * s1) : (uint16_t)0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (tk + k < gt) {
-                        const uint32_t s = quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq);
-                        const uint32_t pr = prow[s & 31u];
-                        enc_symbol(st, pr & 0xffffu, pr >> 16, sink);
+                        const uint32_t pr = prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq)];
+                        enc_symbol2(st, pr & 0xffffu, pr >> 16, myrow, (uint32_t)RW);
                     }
                 }
             }
         }
-        const uint32_t nb = enc_finish(st, sink);
-        const uint32_t full = sink.w;
-        if (nb) sink.put_word((uint32_t)(st.acc << (32u - nb)));
-        len = 4u * full + ((nb + 7u) >> 3);
-        ovf = sink.ovf;
+        len = enc_finish2(st, myrow, (uint32_t)RW);
+        if (st.w > (uint32_t)RW) atomicOr(&P.err[j], 1u);   // size bound violated (cannot happen; stores were clamped)
     }
 
     // ---- compaction: tile scan + look-back, then contiguous copy-out
@@ -351,7 +361,6 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
     s_off[tid] = my_off;
     s_len[tid] = len;
-    if (ovf) atomicOr(&P.err[j], 1u);
     if (tid == 0) s_excl = lookback_excl(P.status, tile, first_tile, (unsigned long long)tile_total, &P.err[j]);
     __syncthreads();
     const unsigned long long excl = s_excl;
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
                     xb[k] = (tk + k < gt) ? __ldg(src + (int64_t)(tok0 + tk + k) * P.sT) : (uint16_t)0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (tk + k < gt) prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq) & 31u] += 1u;
+                    if (tk + k < gt) prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq)] += 1u;
             }
         }
     }
@@ -514,33 +523,48 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(DecParams P) {
     }
 }
 
-struct ByteSrc {
-    const uint8_t* p;
-    uint32_t pos, len;
-    __device__ __forceinline__ uint32_t next_word() {
-        uint32_t w = 0u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            w <<= 8;
-            if (pos < len) w |= p[pos];
-            ++pos;
-        }
-        return w;
-    }
+// aligned big-endian word reader (shared or global memory)
+struct WordSrc {
+    const uint32_t* p;
+    __device__ __forceinline__ uint32_t next_be() { return __byte_perm(*p++, 0u, 0x0123); }
 };
 
 constexpr int CDFW = 34;                     // uint16 per staged CDF row (17 words, odd)
 constexpr int DEC_STAGE_BYTES = CT * 160;    // staged compressed bytes per tile (20 KiB); larger tiles read global
 
+__device__ __forceinline__ uint16_t out_half(float v, int dt) {
+    // hardware RNE converts (NaN payloads are canonicalised; every finite / inf value matches torch's cast)
+    return dt ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+
+// per-thread decode loop: one stream, gt symbols, straight to the destination layout
+template <int OUT_DT>
+__device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint16_t* crow, const uint8_t* irow,
+                                              const float* lut, const float* mx, uint16_t* dst, int64_t sT, int gt) {
+    const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(my_bytes) & 3u);
+    WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip)};
+    DecState2 st;
+    dec_init2(st, src, skip);
+    auto cdf = [&](uint32_t k) -> uint32_t { return crow[k]; };
+    auto inv = [&](uint32_t b) -> uint32_t { return irow[b]; };
+    for (int i = 0; i < gt - 1; ++i, dst += sT) {
+        const uint32_t s = dec_symbol2(st, src, cdf, inv, false);
+        *dst = out_half(dequant_value(lut[s], mx[i]), OUT_DT);
+    }
+    const uint32_t s = dec_symbol2(st, src, cdf, inv, true);
+    *dst = out_half(dequant_value(lut[s], mx[gt - 1]), OUT_DT);
+}
+
 // One tile = CT streams of one (chunk, group, plane): stage the tile's contiguous byte segment + CDF rows
-// in shared memory, decode each stream, dequantise through a 32-entry LUT and store the final half values
-// straight into the destination layout (no uint8 / fp32 intermediates in HBM).
+// in shared memory, build each stream's inverse table, decode, dequantise through a 32-entry LUT and store
+// the final half values straight into the destination layout (no uint8 / fp32 intermediates in HBM).
 template <int OUT_DT>
 __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint8_t* stage = reinterpret_cast<uint8_t*>(smem);                               // DEC_STAGE_BYTES + 16
     uint16_t* cdf_s = reinterpret_cast<uint16_t*>(stage + DEC_STAGE_BYTES + 16);     // CT * CDFW
-    float* mx = reinterpret_cast<float*>(cdf_s + CT * CDFW);                         // kGroup
+    uint8_t* inv_s = reinterpret_cast<uint8_t*>(cdf_s + CT * CDFW);                  // CT * kInvRowBytes
+    float* mx = reinterpret_cast<float*>(inv_s + CT * kInvRowBytes);                 // kGroup
     float* lut = mx + kGroup;                                                        // 32
     __shared__ uint32_t s_warp[CT / 32];
 
@@ -595,15 +619,16 @@ __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     __syncthreads();
 
     if (!active) return;
+    const uint16_t* crow = cdf_s + tid * CDFW;
+    uint8_t* irow = inv_s + tid * kInvRowBytes;
+    dec_build_inv([&](uint32_t k) -> uint32_t { return crow[k]; }, [&](uint32_t b, uint32_t s) { irow[b] = (uint8_t)s; });
     const int h = c / P.D;
     uint16_t* dst = const_cast<uint16_t*>(P.pt.p[nl]) + (dc.dst_tok + tok0) * P.sT + (int64_t)h * P.sH + (c - h * P.D);
-    const uint16_t* crow = cdf_s + tid * CDFW;
-    ByteSrc src{my_bytes, 0u, len};
-    DecState st;
-    dec_init(st, src);
-    for (int i = 0; i < gt; ++i) {
-        const uint32_t s = dec_symbol(st, src, [&](uint32_t k) -> uint32_t { return crow[k]; }, i == gt - 1);
-        dst[(int64_t)i * P.sT] = float_to_half(dequant_value(lut[s], mx[i]), OUT_DT);
+    if (staged) {
+        // re-derive the pointer from the shared array so the loads compile to LDS
+        decode_stream<OUT_DT>(stage + (my_bytes - stage), crow, irow, lut, mx, dst, P.sT, gt);
+    } else {
+        decode_stream<OUT_DT>(my_bytes, crow, irow, lut, mx, dst, P.sT, gt);
     }
 }
 
@@ -760,8 +785,8 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     }
     // 2) encode
     const bool fused = chunk_tokens <= kGroup;
-    const size_t smem_fused = (size_t)(CT * ROWW + CT * PAIRW + kGroup + 2 * CT) * 4;
-    const size_t smem_split = (size_t)(CT * ROWW_OUT + CT * PAIRW + kGroup + 2 * CT) * 4;
+    const size_t smem_fused = (size_t)(((CT * ROWW + CT * PAIRW + 3) & ~3) + kGroup + 2 * CT) * 4;
+    const size_t smem_split = (size_t)(((CT * ROWW_OUT + CT * PAIRW + 3) & ~3) + kGroup + 2 * CT) * 4;
     const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
 #define B2_LAUNCH_ENC(FUSED, DT, SMEM)                                                                     \
     do {                                                                                                   \
@@ -851,7 +876,8 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     }
     B2_CHECK_CUDA(cudaGetLastError());
 
-    const size_t smem = (size_t)DEC_STAGE_BYTES + 16 + (size_t)CT * CDFW * 2 + (size_t)(kGroup + 32) * 4;
+    const size_t smem = (size_t)DEC_STAGE_BYTES + 16 + (size_t)CT * CDFW * 2 + (size_t)CT * kInvRowBytes +
+                        (size_t)(kGroup + 32) * 4;
     dim3 grid((unsigned)tiles_max, (unsigned)n_chunks);
     ProfScope prof(kProfDecode, stream);
     if (P.out_dtype == B200KV_DT_BF16) {

@@ -58,6 +58,46 @@ void sim_decode_stream(const uint16_t* cdf, const uint8_t* in, int64_t n, int g,
         out[i * out_stride] = (uint8_t)dec_symbol(st, src, [&](uint32_t k) { return (uint32_t)cdf[k]; }, i == g - 1);
 }
 
+// production (branch-light) coder paths -- the functions the kernels actually call
+int64_t sim_encode_stream2(const uint16_t* cdf, const int8_t* sym, int64_t sym_stride, int g, uint8_t* out, int64_t cap) {
+    const uint32_t capw = (uint32_t)(2 * g + 16) / 4 + 2;
+    std::vector<uint32_t> row(capw, 0u);
+    EncState2 st; st.init();
+    for (int i = 0; i < g; ++i) {
+        int s = sym[i * sym_stride];
+        uint32_t c_lo = cdf[s];
+        uint32_t c_hi = (s == kMaxSym) ? 0x10000u : cdf[s + 1];
+        enc_symbol2(st, c_lo, c_hi - c_lo, row.data(), capw);
+    }
+    uint32_t n = enc_finish2(st, row.data(), capw);
+    if ((int64_t)n <= cap) memcpy(out, row.data(), n);
+    return n;
+}
+
+namespace {
+struct WordSrc {   // aligned big-endian word reader over a byte buffer that may start mid-word
+    const uint8_t* base; int64_t pos;   // pos: byte index of the next aligned word (may be negative offset handled by caller)
+    const uint8_t* buf; int64_t n;
+    uint32_t next_be() {
+        uint32_t w = 0;
+        for (int i = 0; i < 4; ++i) { int64_t p = pos + i; w = (w << 8) | ((p >= 0 && p < n) ? buf[p] : 0xA5u); }  // garbage past the end: must not matter
+        pos += 4;
+        return w;
+    }
+};
+}
+
+// `skip` leading bytes (0..3) precede the stream inside its first aligned word (they hold foreign data)
+void sim_decode_stream2(const uint16_t* cdf, const uint8_t* in, int64_t n, int g, uint8_t* out, int64_t out_stride, int skip) {
+    uint8_t inv[kInvBuckets];
+    dec_build_inv([&](uint32_t k) { return (uint32_t)cdf[k]; }, [&](uint32_t b, uint32_t s) { inv[b] = (uint8_t)s; });
+    WordSrc src{nullptr, -(int64_t)skip, in, n};
+    DecState2 st; dec_init2(st, src, (uint32_t)skip);
+    for (int i = 0; i < g; ++i)
+        out[i * out_stride] = (uint8_t)dec_symbol2(st, src, [&](uint32_t k) { return (uint32_t)cdf[k]; },
+                                                   [&](uint32_t b) { return (uint32_t)inv[b]; }, i == g - 1);
+}
+
 void sim_cdf(const uint32_t* counts, int t, uint16_t* cdf) {
     CdfAccum a; a.init(t);
     for (uint32_t i = 0; i < (uint32_t)kLp; ++i) cdf[i] = a.next(i, i < 33 ? counts[i] : 0);

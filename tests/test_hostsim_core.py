@@ -18,6 +18,9 @@ def sim():
     S.sim_encode_stream.restype = i64
     S.sim_encode_stream.argtypes = [vp, vp, i64, i32, vp, i64]
     S.sim_decode_stream.argtypes = [vp, vp, i64, i32, vp, i64]
+    S.sim_encode_stream2.restype = i64
+    S.sim_encode_stream2.argtypes = [vp, vp, i64, i32, vp, i64]
+    S.sim_decode_stream2.argtypes = [vp, vp, i64, i32, vp, i64, i32]
     S.sim_cdf.argtypes = [vp, i32, vp]
     S.sim_quant_row.argtypes = [vp, i32, i32, ctypes.c_uint16, ctypes.c_float, vp]
     S.sim_dequant_row.argtypes = [vp, i32, ctypes.c_uint16, i32, ctypes.c_float, i32, vp]
@@ -64,6 +67,68 @@ def test_coder_bit_exact_vs_oracle(sim, kind, t):
             sim.sim_decode_stream(P(cd), P(ref), ref.size, t, P(dec), 1)
             assert np.array_equal(dec, col.view(np.uint8))
             off += ln[nl, c]
+
+
+def _check_v2(sim, cdf, sym, tok0, g):
+    """production (branch-light) encoder / decoder of ac_core.cuh vs the bit-by-bit oracle, incl. a stream that
+    starts mid-word (foreign bytes before it) and garbage after its end"""
+    NL, _, C = sym.shape
+    bs, ln = O.encode_group(cdf, sym, tok0, g)
+    off = 0
+    for nl in range(NL):
+        for c in range(C):
+            col = np.ascontiguousarray(sym[nl, tok0:tok0 + g, c])
+            cd = np.ascontiguousarray(cdf[nl, c]).view(np.uint16)
+            out = np.zeros(2 * g + 64, np.uint8)
+            n = sim.sim_encode_stream2(P(cd), P(col), 1, g, P(out), out.size)
+            ref = np.ascontiguousarray(bs[off:off + ln[nl, c]])
+            assert n == ln[nl, c] and np.array_equal(out[:n], ref)
+            for skip in (0, 1, 2, 3):
+                buf = np.concatenate([np.full(skip, 0x5A, np.uint8), ref])
+                dec = np.zeros(g, np.uint8)
+                sim.sim_decode_stream2(P(cd), ctypes.c_void_p(buf.ctypes.data + skip), ref.size, g, P(dec), 1, skip)
+                assert np.array_equal(dec, col.view(np.uint8)), (nl, c, skip)
+            off += ln[nl, c]
+
+
+@pytest.mark.parametrize("kind", ["peaked", "uniform", "rare", "mid"])
+@pytest.mark.parametrize("t", [1, 2, 3, 5, 16, 100, 236, 256])
+def test_production_coder_bit_exact_vs_oracle(sim, kind, t):
+    rng = np.random.default_rng(hash((kind, t, 2)) & 0xffff)
+    sym = _symbols(rng, kind, (2, t, 5))
+    _check_v2(sim, O.cdf(sym), sym, 0, t)
+
+
+def test_production_coder_foreign_cdf(sim):
+    rng = np.random.default_rng(17)
+    base = np.full((1, 8192, 6), 15, np.int8)
+    base[:, :256, :] = rng.integers(0, 31, size=(1, 256, 6))                      # ~10 bits / symbol
+    base[:, 256:512, :] = np.where(rng.random((1, 256, 6)) < 0.5, 14, 15)         # straddles the midpoint
+    base[:, 512:768, :] = np.where(rng.random((1, 256, 6)) < 0.03, 3, 15)
+    cdf = O.cdf(base)
+    for tok0 in (0, 256, 512, 4096):
+        _check_v2(sim, cdf, base, tok0, 256)
+
+
+def test_production_coder_long_pending_run(sim):
+    """hand-made CDF whose two symbols meet exactly at the midpoint: E3 runs far longer than one 32-bit word"""
+    cdf = np.zeros((1, 1, 33), np.uint16)
+    cdf[0, 0, 1:] = 32768 + np.arange(32)            # symbol 0: [0, 32768), symbol 1: [32768, 32769), ...
+    cdf[0, 0, 32] = 0
+    sym = np.zeros((1, 256, 1), np.int8)
+    sym[0, ::2, 0] = 1                               # 1,0,1,0,... hugs the midpoint from above / below
+    sym[0, 200:, 0] = 0
+    _check_v2(sim, cdf.view(np.int16), sym, 0, 256)
+    sym2 = np.zeros((1, 256, 1), np.int8)
+    sym2[0, 0, 0] = 1
+    _check_v2(sim, cdf.view(np.int16), sym2, 0, 256)
+    # middle symbol [0.25, 0.75): every occurrence is one E3 step -> pending grows by one per symbol
+    cdf3 = np.zeros((1, 1, 33), np.uint16)
+    cdf3[0, 0, 1], cdf3[0, 0, 2] = 16384, 49152
+    cdf3[0, 0, 3:32] = 65000 + np.arange(29)
+    for pattern in ([1] * 60 + [0] + [1] * 100 + [2] + [1] * 33 + [0] + [1] * 60, [1] * 256, [1] * 255 + [2]):
+        sym3 = np.array(pattern, np.int8).reshape(1, 256, 1)
+        _check_v2(sim, cdf3.view(np.int16), sym3, 0, 256)
 
 
 def test_coder_foreign_cdf_expensive_symbols(sim):
