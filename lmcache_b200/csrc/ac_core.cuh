@@ -191,10 +191,12 @@ struct CdfAccum {
     float tf;
     B2_HD void init(int t) { cum = 0.0; prev = 0.0f; tf = (float)t; }
     // returns cdf[i] for the i-th call (i = 0..32), then absorbs n_i
-    B2_HD uint16_t next(uint32_t i, uint32_t n_i) {
+    B2_HD uint16_t next(uint32_t i, uint32_t n_i) { return next_p(i, fdiv((float)n_i, tf)); }
+    // same, with p_i = fl32(n_i / t) supplied by the caller (e.g. from a per-tile table of n / t)
+    B2_HD uint16_t next_p(uint32_t i, float p_i) {
         float r = frint(fmul(prev, 65504.0f));
         uint16_t v = (uint16_t)((uint32_t)(int)r + i);
-        cum += (double)fdiv((float)n_i, tf);
+        cum += (double)p_i;
         prev = (float)cum;
         return v;
     }
@@ -420,16 +422,11 @@ B2_HD uint32_t dec_symbol(DecState& st, Src& src, CdfFn cdf, bool last) {
 }
 
 // ---- production decoder step: same symbols as dec_symbol, organised for SIMT execution.
-//  * symbol search: a per-stream 32-entry inverse table gives a guaranteed lower bound s0 <= s from an
-//    approximate bucket of (value - low) / span (one float reciprocal, error margins below), then a short
-//    upward walk on exact products (span * cdf[s+1]) >> 16 <= off finds s; typically 0-1 steps.
-//    Products fit 32 bits for every real CDF entry (cdf <= 65535); the sentinel cdf(32) = 65536 is never
-//    multiplied (phi = span, computed as rng + 1 with 32-bit wrap, matching the reference's uint32 maths).
+//  * symbol search: fixed-depth, branch-free lower bound on the exact products (span * cdf[s]) >> 16 <= off
+//    (warp lanes never diverge; a data-dependent walk was measured 2x slower because a warp pays the
+//    longest lane).  Products fit 32 bits for every real CDF entry (cdf <= 65535).
 //  * renormalisation consumes n + m <= 18 bits per symbol from a 64-bit left-aligned reservoir that is kept
 //    at >= 32 valid bits by one predicated aligned-word refill per symbol.
-constexpr uint32_t kInvBuckets = 32;       // buckets of 2048 counts
-constexpr uint32_t kInvRowBytes = 36;      // 32 entries + pad (9 words, odd -> conflict-free columns)
-
 struct DecState2 {
     uint32_t low, rng, value;
     uint64_t res;      // left-aligned bit reservoir
@@ -459,44 +456,27 @@ B2_HD void dec_init2(DecState2& st, Src& src, uint32_t skip) {
     dec_refill2(st, src);
 }
 
-// Build the inverse table of one stream: inv[b] = max{ s in 0..31 : cdf(s) <= b * 2048 }
-template <class CdfFn, class PutFn>
-B2_HD void dec_build_inv(CdfFn cdf, PutFn put) {
-    uint32_t s = 0u;
-    for (uint32_t b = 0u; b < kInvBuckets; ++b) {
-        const uint32_t target = b * 2048u;
-        while (s < 31u && cdf(s + 1u) <= target) ++s;
-        put(b, s);
-    }
-}
-
-B2_HD uint32_t dec_bucket(uint32_t off, uint32_t rng) {
-    // A = off * 32 / span, pushed down by more than 1/2048 + float error so that floor(A) * 2048 <= count
-#if defined(__CUDA_ARCH__)
-    const float a = __fmaf_rn(__fdividef(__uint2float_rn(off), __uint2float_rn(rng)), 31.99968f, -0.002f);
-    return (uint32_t)max(__float2int_rz(a), 0);
-#else
-    const float a = ((float)off * (1.0f / (float)rng)) * 31.99968f - 0.002f;
-    const int b = (int)a;
-    return (uint32_t)(b < 0 ? 0 : b);
-#endif
-}
-
-template <class Src, class CdfFn, class InvFn>
-B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, CdfFn cdf, InvFn inv, bool last) {
+// Decode one symbol.  cdf(i) returns the uint16 CDF entry i of this stream.  NSTEPS = 5 searches symbols
+// 0..31, NSTEPS = 4 symbols 0..15 (planes with <= 16 bins only ever code symbols 0..14).
+// Branch-free descending-step lower bound: pos = max{ s : (span * cdf[s]) >> 16 <= off }.  The last rejected
+// candidate is always pos + 1, so both interval products are simply recomputed at the end.
+template <int NSTEPS, class Src, class CdfFn>
+B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, CdfFn cdf, bool last) {
     const uint32_t r = st.rng;
     const uint32_t off = st.value - st.low;
-    uint32_t s = inv(dec_bucket(off, r));
-    const uint32_t c0 = cdf(s);
-    uint32_t plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
-    uint32_t phi;
-    for (;;) {
-        if (s == 31u) { phi = r + 1u; break; }
-        const uint32_t c1 = cdf(s + 1u);
-        const uint32_t p1 = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);
-        if (p1 <= off) { ++s; plo = p1; } else { phi = p1; break; }
+    uint32_t s = 0u;
+#pragma unroll
+    for (int step = 1 << (NSTEPS - 1); step > 0; step >>= 1) {
+        const uint32_t cand = s + (uint32_t)step;
+        const uint32_t c = cdf(cand);
+        const uint32_t p = (uint32_t)(((uint64_t)r * c + c) >> 16);    // < 2^32 for every real entry (c <= 65535)
+        s = p <= off ? cand : s;
     }
     if (last) return s;
+    const uint32_t c0 = cdf(s);
+    const uint32_t plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
+    const uint32_t c1 = s == 31u ? 0x10000u : cdf(s + 1u);
+    const uint32_t phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);    // wraps to 0 when it is 2^32 (uint32 maths)
     uint32_t low = st.low + plo;
     uint32_t high = st.low + phi - 1u;
     const uint32_t n = clz32((low ^ high) | 1u);

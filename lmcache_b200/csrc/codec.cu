@@ -24,7 +24,7 @@ namespace b200kv {
 constexpr int CT = 128;            // streams (threads) per tile
 constexpr int ROWW = 65;           // fused mode: words per symbol/output row (odd -> conflict-free columns)
 constexpr int ROWW_OUT = 131;      // split mode: words per output staging row (>= 2 B/symbol * 256 + flush)
-constexpr int PAIRW = 33;          // words per CDF-pair row (32 symbols + cdf[32]); odd
+constexpr int PAIRW = 33;          // split mode: words per CDF-pair row (32 symbols + cdf[32]); odd
 constexpr unsigned long long kFlagAgg = 1ull << 62;
 constexpr unsigned long long kFlagInc = 2ull << 62;
 constexpr unsigned long long kFlagMask = 3ull << 62;
@@ -203,10 +203,15 @@ template <bool FUSED, int DT>
 __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int RW = FUSED ? ROWW : ROWW_OUT;
+    // FUSED : rows | cdf rows u16[CT][33] (66 B, contiguous; also the histogram) | fac | n/t table | s_off | s_len
+    // !FUSED: rows | pair rows u32[CT][33]                                         | fac |           | s_off | s_len
+    constexpr int TABW = FUSED ? (CT * kLp * 2 + 3) / 4 : CT * PAIRW;
     uint32_t* rows = smem;
     uint32_t* pair = rows + CT * RW;
-    float* fac = reinterpret_cast<float*>(smem + ((CT * RW + CT * PAIRW + 3) & ~3));   // 16-byte aligned (float4 loads)
-    uint32_t* s_off = reinterpret_cast<uint32_t*>(fac + kGroup);
+    uint16_t* cdfr = reinterpret_cast<uint16_t*>(pair);
+    float* fac = reinterpret_cast<float*>(smem + ((CT * RW + TABW + 3) & ~3));   // 16-byte aligned (float4 loads)
+    float* ptab = fac + kGroup;                                                   // FUSED: fl32(n / t), n = 0..t
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(ptab + (FUSED ? kGroup + 4 : 0));
     uint32_t* s_len = s_off + CT;
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[CT / 32];
@@ -245,55 +250,68 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     const float maxq = P.pt.maxq[nl];
 
     for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[i], DT));
+    if (FUSED) {
+        const float tf = (float)t;
+        for (int n = tid; n <= t; n += CT) ptab[n] = fdiv((float)n, tf);   // the 33 fp32 divisions per stream become lookups
+    }
 
-    uint32_t* prow = pair + tid * PAIRW;
+    uint32_t* prow = pair + tid * PAIRW;          // split mode only
     uint32_t* myrow = rows + tid * RW;
     const int h = active ? c / P.D : 0;
     const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + tok0) * P.sT +
                           (int64_t)h * P.sH + (active ? c - h * P.D : 0);
 
+    uint16_t* crow = cdfr + tid * kLp;
     if (FUSED) {
         // ---- pass 1: quantise, stash symbols (4 tokens per word), count
-        uint16_t* hist = reinterpret_cast<uint16_t*>(prow);
+        uint16_t* hist = crow;
 #pragma unroll
-        for (int i = 0; i < PAIRW; ++i) prow[i] = 0u;
-        __syncthreads();   // fac ready
+        for (int i = 0; i < kLp; ++i) crow[i] = 0;
+        __syncthreads();   // fac / ptab ready
         if (active) {
-            // full words: 4 tokens per iteration, no per-token predicates; pointer strides instead of 64-bit multiplies
-            const int nfull = gt >> 2;
+            // 16 tokens per iteration: all 16 loads are issued before the first use (DRAM latency overlaps)
             const int64_t s1 = P.sT;
             const uint16_t* p = src;
-#pragma unroll 2
-            for (int w = 0; w < nfull; ++w, p += 4 * s1) {
-                const uint16_t x0 = __ldg(p), x1 = __ldg(p + s1), x2 = __ldg(p + 2 * s1), x3 = __ldg(p + 3 * s1);
-                const float4 f = *reinterpret_cast<const float4*>(fac + 4 * w);
-                const uint32_t q0 = quant_symbol(half_to_float(x0, DT), f.x, maxq);
-                const uint32_t q1 = quant_symbol(half_to_float(x1, DT), f.y, maxq);
-                const uint32_t q2 = quant_symbol(half_to_float(x2, DT), f.z, maxq);
-                const uint32_t q3 = quant_symbol(half_to_float(x3, DT), f.w, maxq);
-                hist[q0] += 1; hist[q1] += 1; hist[q2] += 1; hist[q3] += 1;     // symbols are <= 30 by construction
-                myrow[w] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            int w = 0;
+            for (; w + 4 <= (gt >> 2); w += 4, p += 16 * s1) {
+                uint16_t x[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) x[k] = __ldg(p + k * s1);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 f = *reinterpret_cast<const float4*>(fac + 4 * (w + q4));
+                    const uint32_t q0 = quant_symbol(half_to_float(x[4 * q4 + 0], DT), f.x, maxq);
+                    const uint32_t q1 = quant_symbol(half_to_float(x[4 * q4 + 1], DT), f.y, maxq);
+                    const uint32_t q2 = quant_symbol(half_to_float(x[4 * q4 + 2], DT), f.z, maxq);
+                    const uint32_t q3 = quant_symbol(half_to_float(x[4 * q4 + 3], DT), f.w, maxq);
+                    hist[q0] += 1; hist[q1] += 1; hist[q2] += 1; hist[q3] += 1;     // symbols are <= 30 by construction
+                    myrow[w + q4] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                }
             }
-            if (gt & 3) {
+            for (int tk = 4 * w; tk < gt; tk += 4, ++w, p += 4 * s1) {               // ragged tail
                 uint32_t word = 0u;
-                for (int k = 0; k < (gt & 3); ++k) {
-                    const uint32_t q = quant_symbol(half_to_float(__ldg(p + k * s1), DT), fac[4 * nfull + k], maxq);
+                for (int k = 0; k < 4 && tk + k < gt; ++k) {
+                    const uint32_t q = quant_symbol(half_to_float(__ldg(p + k * s1), DT), fac[tk + k], maxq);
                     hist[q] += 1;
                     word |= q << (8 * k);
                 }
-                myrow[nfull] = word;
+                myrow[w] = word;
             }
-            // ---- CDF from the thread's own histogram (16 words -> registers), pair row built in place
-            uint32_t hw[16];
+            // ---- CDF from the thread's own histogram, written over it (counts -> registers first)
+            uint32_t cnt[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) hw[i] = prow[i];
-            build_pair_row(prow, t, [&](uint32_t i) -> uint32_t {
-                return i < 32u ? ((hw[i >> 1] >> ((i & 1u) * 16u)) & 0xffffu) : 0u;
-            });
+            for (int i = 0; i < 32; ++i) cnt[i] = hist[i];
+            CdfAccum acc;
+            acc.init(t);
+#pragma unroll
+            for (uint32_t i = 0; i < 32u; ++i) crow[i] = acc.next_p(i, ptab[cnt[i]]);
+            crow[32] = acc.next_p(32u, 0.0f);
         }
         __syncthreads();
-        store_cdf_rows(pair, reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp,
-                       ncols);
+        {   // the tile's 33-entry rows are contiguous in smem and in the container: straight coalesced copy
+            uint16_t* dstc = reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
+            for (int e = tid; e < ncols * kLp; e += CT) dstc[e] = cdfr[e];
+        }
     } else {
         // CDF of the whole chunk was written by cdf_kernel: load it and build the pair rows
         const uint16_t* cdf_src =
@@ -325,15 +343,17 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
                 const uint32_t word = myrow[w];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t pr = prow[(word >> (8 * k)) & 31u];
-                    enc_symbol2(st, pr & 0xffffu, pr >> 16, myrow, (uint32_t)RW);
+                    const uint32_t sidx = (word >> (8 * k)) & 31u;       // <= 30: crow[sidx + 1] is a real entry
+                    const uint32_t c_lo = crow[sidx];
+                    enc_symbol2(st, c_lo, (uint32_t)crow[sidx + 1u] - c_lo, myrow, (uint32_t)RW);
                 }
             }
             if (gt & 3) {
                 const uint32_t word = myrow[nfull];
                 for (int k = 0; k < (gt & 3); ++k) {
-                    const uint32_t pr = prow[(word >> (8 * k)) & 31u];
-                    enc_symbol2(st, pr & 0xffffu, pr >> 16, myrow, (uint32_t)RW);
+                    const uint32_t sidx = (word >> (8 * k)) & 31u;
+                    const uint32_t c_lo = crow[sidx];
+                    enc_symbol2(st, c_lo, (uint32_t)crow[sidx + 1u] - c_lo, myrow, (uint32_t)RW);
                 }
             }
         } else {
@@ -523,14 +543,19 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(DecParams P) {
     }
 }
 
-// aligned big-endian word reader (shared or global memory)
+// Aligned big-endian word reader over the stream's bytes in global memory with a one-word look-ahead: the
+// load for word i+1 is issued when word i is consumed, so its L2/L1 latency overlaps ~8+ symbols of decoding.
+// Each lane walks its own stream; a 32-byte sector serves 8 consecutive refills from L1.
 struct WordSrc {
     const uint32_t* p;
-    __device__ __forceinline__ uint32_t next_be() { return __byte_perm(*p++, 0u, 0x0123); }
+    uint32_t ahead;
+    __device__ __forceinline__ void prime() { ahead = __ldg(p++); }
+    __device__ __forceinline__ uint32_t next_be() {
+        const uint32_t w = ahead;
+        ahead = __ldg(p++);
+        return __byte_perm(w, 0u, 0x0123);
+    }
 };
-
-constexpr int CDFW = 34;                     // uint16 per staged CDF row (17 words, odd)
-constexpr int DEC_STAGE_BYTES = CT * 160;    // staged compressed bytes per tile (20 KiB); larger tiles read global
 
 __device__ __forceinline__ uint16_t out_half(float v, int dt) {
     // hardware RNE converts (NaN payloads are canonicalised; every finite / inf value matches torch's cast)
@@ -538,33 +563,32 @@ __device__ __forceinline__ uint16_t out_half(float v, int dt) {
 }
 
 // per-thread decode loop: one stream, gt symbols, straight to the destination layout
-template <int OUT_DT>
-__device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint16_t* crow, const uint8_t* irow,
-                                              const float* lut, const float* mx, uint16_t* dst, int64_t sT, int gt) {
+template <int OUT_DT, int NSTEPS>
+__device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint16_t* crow, const float* lut,
+                                              const float* mx, uint16_t* dst, int64_t sT, int gt) {
     const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(my_bytes) & 3u);
-    WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip)};
+    WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip), 0u};
+    src.prime();
     DecState2 st;
     dec_init2(st, src, skip);
     auto cdf = [&](uint32_t k) -> uint32_t { return crow[k]; };
-    auto inv = [&](uint32_t b) -> uint32_t { return irow[b]; };
     for (int i = 0; i < gt - 1; ++i, dst += sT) {
-        const uint32_t s = dec_symbol2(st, src, cdf, inv, false);
+        const uint32_t s = dec_symbol2<NSTEPS>(st, src, cdf, false);
         *dst = out_half(dequant_value(lut[s], mx[i]), OUT_DT);
     }
-    const uint32_t s = dec_symbol2(st, src, cdf, inv, true);
+    const uint32_t s = dec_symbol2<NSTEPS>(st, src, cdf, true);
     *dst = out_half(dequant_value(lut[s], mx[gt - 1]), OUT_DT);
 }
 
-// One tile = CT streams of one (chunk, group, plane): stage the tile's contiguous byte segment + CDF rows
-// in shared memory, build each stream's inverse table, decode, dequantise through a 32-entry LUT and store
-// the final half values straight into the destination layout (no uint8 / fp32 intermediates in HBM).
+// One tile = CT streams of one (chunk, group, plane).  Only the CDF rows (66 B per stream, contiguous in the
+// container so they are staged with one coalesced copy), the row maxima and a 32-entry dequantisation LUT live in
+// shared memory (~10 KB per CTA), so many CTAs stay resident and hide the serial latency of each stream's coder.
+// Symbols are dequantised and stored straight into the destination layout (no uint8 / fp32 intermediates in HBM).
 template <int OUT_DT>
 __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint8_t* stage = reinterpret_cast<uint8_t*>(smem);                               // DEC_STAGE_BYTES + 16
-    uint16_t* cdf_s = reinterpret_cast<uint16_t*>(stage + DEC_STAGE_BYTES + 16);     // CT * CDFW
-    uint8_t* inv_s = reinterpret_cast<uint8_t*>(cdf_s + CT * CDFW);                  // CT * kInvRowBytes
-    float* mx = reinterpret_cast<float*>(inv_s + CT * kInvRowBytes);                 // kGroup
+    uint16_t* cdf_s = reinterpret_cast<uint16_t*>(smem);                             // CT * kLp (rows of 33, contiguous)
+    float* mx = reinterpret_cast<float*>(smem + ((CT * kLp * 2 + 15) / 16) * 4);     // kGroup
     float* lut = mx + kGroup;                                                        // 32
     __shared__ uint32_t s_warp[CT / 32];
 
@@ -590,46 +614,23 @@ __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     const uint32_t len = active ? (uint32_t)lengths[c] : 0u;
     uint32_t tile_total;
     const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
-    const uint8_t* seg = dc.base + lo.off_payload + P.tile_base[(int64_t)j * P.tiles_max + tile];
+    const uint8_t* my_bytes = dc.base + lo.off_payload + P.tile_base[(int64_t)j * P.tiles_max + tile] + my_off;
 
-    // stage CDF rows, row maxima, LUT
+    // stage CDF rows (one contiguous run of ncols * 33 halfwords), row maxima, LUT
     const uint16_t* cdf_src = reinterpret_cast<const uint16_t*>(dc.base + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
-    for (int e = tid; e < ncols * kLp; e += CT) {
-        const int r = e / kLp;
-        cdf_s[r * CDFW + (e - r * kLp)] = cdf_src[e];
-    }
+    for (int e = tid; e < ncols * kLp; e += CT) cdf_s[e] = __ldg(cdf_src + e);
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(dc.base + lo.off_maxes) + (int64_t)nl * dc.t + tok0;
     for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
-    if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, P.pt.maxq[nl]);
-
-    // stage the tile's byte segment (16-byte aligned window) when it fits
-    const bool staged = tile_total <= (uint32_t)DEC_STAGE_BYTES;
-    const uint8_t* my_bytes;
-    if (staged) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(seg);
-        const uint32_t shift = (uint32_t)(a & 15u);
-        const uint4* src16 = reinterpret_cast<const uint4*>(a - shift);
-        const uint32_t nvec = (shift + tile_total + 15u) >> 4;
-        uint4* dst16 = reinterpret_cast<uint4*>(stage);
-        for (uint32_t v = tid; v < nvec; v += CT) dst16[v] = __ldg(src16 + v);
-        my_bytes = stage + shift + my_off;
-    } else {
-        my_bytes = seg + my_off;
-    }
+    const float cq = P.pt.maxq[nl];
+    if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
     __syncthreads();
 
     if (!active) return;
-    const uint16_t* crow = cdf_s + tid * CDFW;
-    uint8_t* irow = inv_s + tid * kInvRowBytes;
-    dec_build_inv([&](uint32_t k) -> uint32_t { return crow[k]; }, [&](uint32_t b, uint32_t s) { irow[b] = (uint8_t)s; });
+    const uint16_t* crow = cdf_s + tid * kLp;
     const int h = c / P.D;
     uint16_t* dst = const_cast<uint16_t*>(P.pt.p[nl]) + (dc.dst_tok + tok0) * P.sT + (int64_t)h * P.sH + (c - h * P.D);
-    if (staged) {
-        // re-derive the pointer from the shared array so the loads compile to LDS
-        decode_stream<OUT_DT>(stage + (my_bytes - stage), crow, irow, lut, mx, dst, P.sT, gt);
-    } else {
-        decode_stream<OUT_DT>(my_bytes, crow, irow, lut, mx, dst, P.sT, gt);
-    }
+    if (cq <= 7.0f) decode_stream<OUT_DT, 4>(my_bytes, crow, lut, mx, dst, P.sT, gt);   // <= 16 bins: symbols 0..14
+    else decode_stream<OUT_DT, 5>(my_bytes, crow, lut, mx, dst, P.sT, gt);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -785,7 +786,7 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     }
     // 2) encode
     const bool fused = chunk_tokens <= kGroup;
-    const size_t smem_fused = (size_t)(((CT * ROWW + CT * PAIRW + 3) & ~3) + kGroup + 2 * CT) * 4;
+    const size_t smem_fused = (size_t)(((CT * ROWW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + (kGroup + 4) + 2 * CT) * 4;
     const size_t smem_split = (size_t)(((CT * ROWW_OUT + CT * PAIRW + 3) & ~3) + kGroup + 2 * CT) * 4;
     const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
 #define B2_LAUNCH_ENC(FUSED, DT, SMEM)                                                                     \
@@ -876,8 +877,7 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     }
     B2_CHECK_CUDA(cudaGetLastError());
 
-    const size_t smem = (size_t)DEC_STAGE_BYTES + 16 + (size_t)CT * CDFW * 2 + (size_t)CT * kInvRowBytes +
-                        (size_t)(kGroup + 32) * 4;
+    const size_t smem = (size_t)((CT * kLp * 2 + 15) / 16) * 16 + (size_t)(kGroup + 32) * 4;
     dim3 grid((unsigned)tiles_max, (unsigned)n_chunks);
     ProfScope prof(kProfDecode, stream);
     if (P.out_dtype == B200KV_DT_BF16) {

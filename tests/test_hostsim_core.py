@@ -20,7 +20,7 @@ def sim():
     S.sim_decode_stream.argtypes = [vp, vp, i64, i32, vp, i64]
     S.sim_encode_stream2.restype = i64
     S.sim_encode_stream2.argtypes = [vp, vp, i64, i32, vp, i64]
-    S.sim_decode_stream2.argtypes = [vp, vp, i64, i32, vp, i64, i32]
+    S.sim_decode_stream2.argtypes = [vp, vp, i64, i32, vp, i64, i32, i32]
     S.sim_cdf.argtypes = [vp, i32, vp]
     S.sim_quant_row.argtypes = [vp, i32, i32, ctypes.c_uint16, ctypes.c_float, vp]
     S.sim_dequant_row.argtypes = [vp, i32, ctypes.c_uint16, i32, ctypes.c_float, i32, vp]
@@ -86,8 +86,11 @@ def _check_v2(sim, cdf, sym, tok0, g):
             for skip in (0, 1, 2, 3):
                 buf = np.concatenate([np.full(skip, 0x5A, np.uint8), ref])
                 dec = np.zeros(g, np.uint8)
-                sim.sim_decode_stream2(P(cd), ctypes.c_void_p(buf.ctypes.data + skip), ref.size, g, P(dec), 1, skip)
+                sim.sim_decode_stream2(P(cd), ctypes.c_void_p(buf.ctypes.data + skip), ref.size, g, P(dec), 1, skip, 5)
                 assert np.array_equal(dec, col.view(np.uint8)), (nl, c, skip)
+                if col.max() <= 15:      # 16-bin planes: the 4-step search covers every symbol they can hold
+                    sim.sim_decode_stream2(P(cd), ctypes.c_void_p(buf.ctypes.data + skip), ref.size, g, P(dec), 1, skip, 4)
+                    assert np.array_equal(dec, col.view(np.uint8)), (nl, c, skip, "4-step")
             off += ln[nl, c]
 
 
