@@ -176,7 +176,7 @@ int b200kv_event_elapsed_ms(void* start, void* stop, float* ms);
 /*
  * Per-kernel device timing of the most recent encode / decode call (CUDA events recorded on the call's
  * stream around each launch).  Not part of the reference surface: bench.py's roofline leg uses it so the
- * dominant kernel is timed live, outside any profiler.  Slots: 0 absmax, 1 cdf, 2 encode, 3 finalize,
+ * dominant kernel is timed live, outside any profiler.  Slots: 0 absmax, 1 cdf, 2 encode, 3 scan+compact+finalize,
  * 4 tile_sum, 5 tile_scan, 6 decode; -1 = not launched.  Not thread-safe; enable only while benchmarking.
  */
 int b200kv_profile_enable(int32_t on);

@@ -93,7 +93,7 @@ SIGNATURES = {
     "b200kv_profile_enable": (c_i32, [c_i32]),
     "b200kv_profile_last": (c_i32, [ctypes.POINTER(ctypes.c_float), c_i32]),
 }
-PROFILE_SLOTS = ("absmax", "cdf", "encode", "finalize", "tile_sum", "tile_scan", "decode")
+PROFILE_SLOTS = ("absmax", "cdf", "encode", "compact", "tile_sum", "tile_scan", "decode")
 
 _lib: Optional[ctypes.CDLL] = None
 _lock = threading.Lock()

@@ -80,6 +80,20 @@ B2_HD uint32_t bswap32(uint32_t v) {
 #endif
 }
 
+// (x << n) | ones(n), 0 <= n <= 31 : one funnel shift with an all-ones low word
+B2_HD uint32_t shl_fill1(uint32_t x, uint32_t n) { return funnel_l(0xFFFFFFFFu, x, n); }
+
+// number of E3 ("straddle") steps for a normalised interval low = 0..., high = 1...:
+// count of leading positions (from bit 30 down) where low has 1 and high has 0
+B2_HD uint32_t e3_count(uint32_t low, uint32_t high) {
+    const uint32_t x = ((~low) | high) & 0x7FFFFFFFu;        // one LOP3
+#if defined(__CUDA_ARCH__)
+    return 30u - (uint32_t)(31 - __clz((int)x));               // FLO of 0 is -1 -> 31
+#else
+    return x ? 30u - (31u - (uint32_t)__builtin_clz(x)) : 31u;
+#endif
+}
+
 // fp32 ops that must not be contracted / reordered
 B2_HD float fdiv(float a, float b) {
 #if defined(__CUDA_ARCH__)
@@ -289,8 +303,8 @@ B2_HD void enc_symbol2(EncState2& st, uint32_t c_lo, uint32_t width, uint32_t* r
     const uint32_t n = clz32((low ^ high) | 1u);
     const uint32_t top = funnel_l(low, 0u, n);                 // n leading bits of low (0 when n == 0)
     low <<= n;
-    high = (high << n) | ((1u << n) - 1u);
-    const uint32_t m = clz32((((~low) | high) << 1) | 1u);
+    high = shl_fill1(high, n);
+    const uint32_t m = e3_count(low, high);
     uint32_t p = st.pending;
     uint32_t v, k;
     if (p + n > 32u && n != 0u) {                               // rare, warp-uniformly not taken: long pending run
@@ -316,7 +330,7 @@ B2_HD void enc_symbol2(EncState2& st, uint32_t c_lo, uint32_t width, uint32_t* r
     }
     st.pending = p + m;
     st.low = (low << m) & 0x7FFFFFFFu;
-    st.rng = ((high << m) | 0x80000000u | ((1u << m) - 1u)) - st.low;
+    st.rng = (shl_fill1(high, m) | 0x80000000u) - st.low;
     st.acc = (st.acc << k) | (uint64_t)v;
     const uint32_t nb = st.nb + k;
     const bool flush = nb >= 32u;
@@ -422,9 +436,8 @@ B2_HD uint32_t dec_symbol(DecState& st, Src& src, CdfFn cdf, bool last) {
 }
 
 // ---- production decoder step: same symbols as dec_symbol, organised for SIMT execution.
-//  * symbol search: fixed-depth, branch-free lower bound on the exact products (span * cdf[s]) >> 16 <= off
-//    (warp lanes never diverge; a data-dependent walk was measured 2x slower because a warp pays the
-//    longest lane).  Products fit 32 bits for every real CDF entry (cdf <= 65535).
+//  * symbol search: fixed-depth and branch-free (warp lanes never diverge; a data-dependent walk was measured
+//    2x slower because a warp pays for its longest lane), see dec_symbol2.
 //  * renormalisation consumes n + m <= 18 bits per symbol from a 64-bit left-aligned reservoir that is kept
 //    at >= 32 valid bits by one predicated aligned-word refill per symbol.
 struct DecState2 {
@@ -456,39 +469,65 @@ B2_HD void dec_init2(DecState2& st, Src& src, uint32_t skip) {
     dec_refill2(st, src);
 }
 
+// Approximate count ~ floor((value - low) * 2^16 / span), within +-1 of the reference's exact
+//   count = ((value - low + 1) * 2^16 - 1) / span      (one reciprocal instead of a 64-bit division).
+B2_HD uint32_t dec_count_approx(uint32_t off, uint32_t rng) {
+#if defined(__CUDA_ARCH__)
+    const float q = __fdividef(__uint2float_rn(off), __uint2float_rn(rng)) * 65536.0f;
+    const uint32_t c = (uint32_t)__float2int_rz(q);
+#else
+    const float q = ((float)off / (float)rng) * 65536.0f;
+    const uint32_t c = (uint32_t)(int)q;
+#endif
+    return c < 65535u ? c : 65535u;
+}
+
 // Decode one symbol.  cdf(i) returns the uint16 CDF entry i of this stream.  NSTEPS = 5 searches symbols
 // 0..31, NSTEPS = 4 symbols 0..15 (planes with <= 16 bins only ever code symbols 0..14).
-// Branch-free descending-step lower bound: pos = max{ s : (span * cdf[s]) >> 16 <= off }.  The last rejected
-// candidate is always pos + 1, so both interval products are simply recomputed at the end.
+//  1. s~ = max{ s : cdf[s] <= count~ } by a fixed-depth, branch-free lower-bound search in the count domain
+//     (compares only -- the 64-bit multiplies of a product-domain search made the FMA pipe the bottleneck).
+//  2. the exact interval products plo = (span*cdf[s])>>16, phi = (span*cdf[s+1])>>16 are needed for the state
+//     update anyway; the symbol is exact iff plo <= off < phi, which is the reference's decision rule
+//     (cdf[s] <= count  <=>  (span*cdf[s])>>16 <= off).  count~ is within +-1 of count, so at most one step of
+//     correction is ever needed; the loops below make the result exact whatever the approximation did.
 template <int NSTEPS, class Src, class CdfFn>
 B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, CdfFn cdf, bool last) {
     const uint32_t r = st.rng;
     const uint32_t off = st.value - st.low;
+    const uint32_t cnt = dec_count_approx(off, r);
+    constexpr uint32_t kTop = (1u << NSTEPS) - 1u;               // highest searchable symbol
     uint32_t s = 0u;
 #pragma unroll
     for (int step = 1 << (NSTEPS - 1); step > 0; step >>= 1) {
         const uint32_t cand = s + (uint32_t)step;
-        const uint32_t c = cdf(cand);
-        const uint32_t p = (uint32_t)(((uint64_t)r * c + c) >> 16);    // < 2^32 for every real entry (c <= 65535)
-        s = p <= off ? cand : s;
+        s = cdf(cand) <= cnt ? cand : s;
+    }
+    uint32_t c0 = cdf(s);
+    uint32_t plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
+    uint32_t c1 = s == 31u ? 0x10000u : cdf(s + 1u);
+    uint32_t phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);          // 2^32 wraps to 0 (uint32 maths), see below
+    // exactness fix-up (rare, warp-uniformly skipped): phi == 0 with c1 == 65536 means 2^32, i.e. "off < phi" holds
+    while (off < plo && s > 0u) {
+        --s; phi = plo; c0 = cdf(s);
+        plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
+    }
+    while (s < kTop && !(c1 == 0x10000u && phi == 0u) && off >= phi) {
+        ++s; plo = phi; c1 = s == 31u ? 0x10000u : cdf(s + 1u);
+        phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);
     }
     if (last) return s;
-    const uint32_t c0 = cdf(s);
-    const uint32_t plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
-    const uint32_t c1 = s == 31u ? 0x10000u : cdf(s + 1u);
-    const uint32_t phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);    // wraps to 0 when it is 2^32 (uint32 maths)
     uint32_t low = st.low + plo;
     uint32_t high = st.low + phi - 1u;
     const uint32_t n = clz32((low ^ high) | 1u);
     low <<= n;
-    high = (high << n) | ((1u << n) - 1u);
-    const uint32_t m = clz32((((~low) | high) << 1) | 1u);
+    high = shl_fill1(high, n);
+    const uint32_t m = e3_count(low, high);
     const uint32_t k = n + m;                                    // <= 18 for 16-bit CDFs
     st.value = funnel_l((uint32_t)(st.res >> 32), st.value, k) ^ (m ? 0x80000000u : 0u);
     st.res <<= k;
     st.rb -= k;
     st.low = (low << m) & 0x7FFFFFFFu;
-    st.rng = ((high << m) | 0x80000000u | ((1u << m) - 1u)) - st.low;
+    st.rng = (shl_fill1(high, m) | 0x80000000u) - st.low;
     dec_refill2(st, src);
     return s;
 }

@@ -22,34 +22,30 @@
 namespace b200kv {
 
 constexpr int CT = 128;            // streams (threads) per tile
-constexpr int ROWW = 65;           // fused mode: words per symbol/output row (odd -> conflict-free columns)
-constexpr int ROWW_OUT = 131;      // split mode: words per output staging row (>= 2 B/symbol * 256 + flush)
+constexpr int SPW = 6;             // 5-bit symbols packed per 32-bit word in shared memory
+constexpr int SYMW = 43;           // words per symbol row: ceil(256 / 6); odd -> conflict-free columns
 constexpr int PAIRW = 33;          // split mode: words per CDF-pair row (32 symbols + cdf[32]); odd
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagInc = 2ull << 62;
-constexpr unsigned long long kFlagMask = 3ull << 62;
-constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr int TEMPW_FUSED = 40;    // words per stream in the tile's temp rows: own-CDF streams of <= 256 symbols
+                                   //   cost <= 256*log2(31) + 2 bits = 159 bytes
+constexpr int TEMPW_SPLIT = 131;   // foreign CDF (chunk > 256 tokens): <= 16 bits / symbol + termination
 
 struct EncParams {
     PlaneTable pt;
     int64_t sT, sH, tok_begin;
     int32_t L, H, D, C, dtype;
     int32_t n_chunks, chunk_tokens, last_chunk_tokens, tpp;   // tpp = tiles per plane
+    int32_t tiles_full, tempw;                                 // tiles per full chunk; words per temp row
     uint8_t* out;
     int64_t out_stride;
     uint64_t* sizes_out;
-    unsigned int* ticket;
-    unsigned long long* status;
-    unsigned long long* totals;
-    unsigned int* err;
+    uint32_t* temp;                  // [n_tiles][CT][tempw] coder output before compaction
+    uint32_t* tile_tot;              // [n_chunks][tiles_full] bytes per tile, then exclusive prefix (in place)
+    unsigned long long* totals;      // [n_chunks] payload bytes
+    unsigned int* err;               // [n_chunks]
 };
 
 __device__ __forceinline__ int chunk_tokens_of(const EncParams& P, int j) {
     return j == P.n_chunks - 1 ? P.last_chunk_tokens : P.chunk_tokens;
-}
-
-__device__ __forceinline__ float load_half_as_float(const uint16_t* p, int dtype) {
-    return half_to_float(__ldg(p), dtype);
 }
 
 // ------------------------------------------------------------------------------------------ absmax
@@ -58,7 +54,7 @@ __device__ __forceinline__ float load_half_as_float(const uint16_t* p, int dtype
 // wins (pattern above inf), like torch.amax.  One warp per row, 128-bit loads when alignment allows.
 template <bool VEC>
 __global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_tokens) {
-    const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t nrows = (int64_t)2 * P.L * total_tokens;
     if (warp >= nrows) return;
@@ -96,16 +92,6 @@ __global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_
 }
 
 // ------------------------------------------------------------------------------------------ helpers
-struct RowSink {
-    uint32_t* row;
-    uint32_t w, cap, ovf;
-    __device__ __forceinline__ void put_word(uint32_t v) {
-        if (w < cap) row[w] = __byte_perm(v, 0u, 0x0123);   // big-endian in memory: first bit first
-        else ovf = 1u;
-        ++w;
-    }
-};
-
 // block-wide exclusive scan of one uint32 per thread (CT threads); returns exclusive prefix, total in *total
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -128,175 +114,116 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
     return base + inc - v;
 }
 
-// decoupled look-back over tiles [first, tile]; one thread calls.  status words pack flag | value so a
-// single 64-bit store publishes both.  A tile only ever waits on tiles with smaller tickets, which have
-// already been scheduled, so this cannot deadlock; the spin limit turns a logic bug into an error code
-// instead of a hung GPU.
-__device__ unsigned long long lookback_excl(unsigned long long* status, uint32_t tile, uint32_t first,
-                                            unsigned long long agg, unsigned int* err) {
-    if (tile == first) {
-        atomicExch(&status[tile], kFlagInc | agg);
-        return 0ull;
-    }
-    atomicExch(&status[tile], kFlagAgg | agg);
-    unsigned long long excl = 0ull;
-    int64_t idx = (int64_t)tile - 1;
-    uint32_t spins = 0;
-    while (true) {
-        const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(&status[idx]);
-        const unsigned long long f = v & kFlagMask;
-        if (f == 0ull) {
-            if (++spins > kSpinLimit) { atomicOr(err, 2u); break; }
-            __nanosleep(64);
-            continue;
-        }
-        excl += v & ~kFlagMask;
-        if (f == kFlagInc || idx == (int64_t)first) break;
-        --idx;
-    }
-    atomicExch(&status[tile], kFlagInc | (excl + agg));
-    return excl;
-}
-
-// write the 33 uint16 CDF entries of `ncols` streams (low halves of the pair rows, which are contiguous
-// with stride PAIRW == kLp words) to the container, coalesced
-__device__ __forceinline__ void store_cdf_rows(const uint32_t* pair, uint16_t* dst, int ncols) {
-    const int n = ncols * kLp;
-    for (int e = threadIdx.x; e < n; e += CT) dst[e] = (uint16_t)pair[e];
-}
-
-// thread-private: turn 33 counts (read through `cnt(i)`) into the pair row  c_lo | width << 16
-template <class CountFn>
-__device__ __forceinline__ void build_pair_row(uint32_t* prow, int t, CountFn cnt) {
-    CdfAccum acc;
-    acc.init(t);
-    uint32_t prev = acc.next(0u, cnt(0));
-#pragma unroll
-    for (uint32_t i = 1; i <= 32u; ++i) {
-        const uint32_t cur = acc.next(i, i < 32u ? cnt(i) : 0u);
-        const uint32_t hi = (i == 32u) ? 0x10000u : cur;      // coder uses 0x10000 above max_symbol
-        prow[i - 1] = prev | ((hi - prev) << 16);
-        prev = cur;
-    }
-    prow[32] = prev;                                          // cdf[32] (wraps to 0; never read by the coder)
-}
-
-// copy the tile's streams from their staging rows to the compact payload
-__device__ __forceinline__ void copy_rows_out(const uint32_t* rows, int roww, const uint32_t* s_off,
-                                              const uint32_t* s_len, uint8_t* dst) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int r = wid; r < CT; r += CT / 32) {
-        const uint32_t n = s_len[r];
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(rows + r * roww);
-        uint8_t* d = dst + s_off[r];
-        for (uint32_t i = lane; i < n; i += 32) d[i] = src[i];
-    }
+// tile -> (chunk j, group g, plane nl, channel tile ct); tiles of a chunk are ordered (g, nl, ct), which is the
+// order of the streams in the container payload.  Returns false for tiles beyond the (ragged) last chunk.
+struct TileId { int j, g, nl, ct, t, tok0, gt, tile_in_chunk; };
+__device__ __forceinline__ bool decode_tile(const EncParams& P, uint32_t tile, TileId* id) {
+    const uint32_t per_group = 2u * P.L * P.tpp;
+    const uint32_t j = tile / (uint32_t)P.tiles_full;
+    const uint32_t rem = tile - j * (uint32_t)P.tiles_full;
+    id->j = (int)j;
+    id->tile_in_chunk = (int)rem;
+    id->t = chunk_tokens_of(P, (int)j);
+    id->g = (int)(rem / per_group);
+    if (id->g * kGroup >= id->t) return false;
+    const uint32_t rem2 = rem - (uint32_t)id->g * per_group;
+    id->nl = (int)(rem2 / P.tpp);
+    id->ct = (int)(rem2 - (uint32_t)id->nl * P.tpp);
+    id->tok0 = id->g * kGroup;
+    id->gt = min(kGroup, id->t - id->tok0);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------ encode
-// FUSED (chunk <= 256 tokens, one group): quantise -> smem symbols + histogram -> CDF -> arithmetic-code
-// in place over the consumed symbols -> look-back -> compact copy.  KV is read from HBM exactly once
-// here (plus once by absmax).
-// !FUSED (chunk > 256 tokens): CDF was produced by cdf_kernel over the whole chunk; this kernel codes one
-// group per tile, quantising on the fly.
+// One tile = CT consecutive channels of one plane and one <= 256-token group; one thread = one coder stream.
+// FUSED (chunk <= 256 tokens): quantise -> 5-bit symbols in shared memory + thread-private histogram -> CDF (the
+//   33-entry rows are contiguous in smem and in the container: one coalesced copy) -> arithmetic coding.  KV is read
+//   from HBM exactly once here (plus once by absmax).
+// !FUSED (chunk > 256 tokens): the chunk-wide CDF was produced by cdf_kernel; one tile codes one group, quantising
+//   on the fly.
+// Coder output goes to the tile's temp rows in global memory (sparse 32-bit stores, merged in L2); stream lengths go to
+// the container; the tile's byte total goes to tile_tot.  Compaction into the contiguous payload (collect_bytes in the
+// reference) is done by scan_kernel + compact_kernel afterwards, so no CTA ever waits on another one.
 template <bool FUSED, int DT>
 __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
-    constexpr int RW = FUSED ? ROWW : ROWW_OUT;
-    // FUSED : rows | cdf rows u16[CT][33] (66 B, contiguous; also the histogram) | fac | n/t table | s_off | s_len
-    // !FUSED: rows | pair rows u32[CT][33]                                         | fac |           | s_off | s_len
-    constexpr int TABW = FUSED ? (CT * kLp * 2 + 3) / 4 : CT * PAIRW;
+    // FUSED : symbol rows u32[CT][SYMW] | cdf rows u16[CT][33] (also the histogram) | fac[256] (later fl32(n/t)[257])
+    // !FUSED: pair rows u32[CT][33]                                                 | fac[256]
+    constexpr int ROWS_W = FUSED ? CT * SYMW : 0;
+    constexpr int TAB_W = FUSED ? (CT * kLp * 2 + 3) / 4 : CT * PAIRW;
     uint32_t* rows = smem;
-    uint32_t* pair = rows + CT * RW;
-    uint16_t* cdfr = reinterpret_cast<uint16_t*>(pair);
-    float* fac = reinterpret_cast<float*>(smem + ((CT * RW + TABW + 3) & ~3));   // 16-byte aligned (float4 loads)
-    float* ptab = fac + kGroup;                                                   // FUSED: fl32(n / t), n = 0..t
-    uint32_t* s_off = reinterpret_cast<uint32_t*>(ptab + (FUSED ? kGroup + 4 : 0));
-    uint32_t* s_len = s_off + CT;
-    __shared__ uint32_t s_tile;
+    uint32_t* tab = smem + ROWS_W;
+    float* fac = reinterpret_cast<float*>(smem + ((ROWS_W + TAB_W + 3) & ~3));
     __shared__ uint32_t s_warp[CT / 32];
-    __shared__ unsigned long long s_excl;
 
     const int tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-
+    TileId id;
+    if (!decode_tile(P, blockIdx.x, &id)) return;
     const int NL = 2 * P.L;
-    const uint32_t per_group = (uint32_t)NL * P.tpp;
-    const uint32_t g_full = (uint32_t)(P.chunk_tokens + kGroup - 1) / kGroup;
-    const uint32_t per_chunk_full = g_full * per_group;
-    uint32_t j = tile / per_chunk_full;
-    if (j >= (uint32_t)P.n_chunks) j = P.n_chunks - 1;
-    const uint32_t rem = tile - j * per_chunk_full;
-    const uint32_t first_tile = j * per_chunk_full;
-    const int t = chunk_tokens_of(P, (int)j);
-    const uint32_t g_here = (uint32_t)(t + kGroup - 1) / kGroup;
-    const uint32_t g = rem / per_group;
-    if (g >= g_here) return;   // cannot happen: the grid is sized exactly (host); defensive
-    const uint32_t rem2 = rem - g * per_group;
-    const int nl = (int)(rem2 / P.tpp);
-    const int ct = (int)(rem2 - (uint32_t)nl * P.tpp);
-    const bool last_tile_of_chunk = (g == g_here - 1) && (rem2 == per_group - 1);
-    const int tok0 = (int)g * kGroup;
-    const int gt = min(kGroup, t - tok0);
+    const int j = id.j, nl = id.nl, ct = id.ct, t = id.t, gt = id.gt;
     const int c = ct * CT + tid;
     const bool active = c < P.C;
     const int ncols = min(CT, P.C - ct * CT);
 
     uint8_t* cont = P.out + (int64_t)j * P.out_stride;
     const Layout lo = make_layout(P.L, P.C, t);
-    const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + tok0;
+    const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + id.tok0;
     const float maxq = P.pt.maxq[nl];
-
     for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[i], DT));
-    if (FUSED) {
-        const float tf = (float)t;
-        for (int n = tid; n <= t; n += CT) ptab[n] = fdiv((float)n, tf);   // the 33 fp32 divisions per stream become lookups
-    }
 
-    uint32_t* prow = pair + tid * PAIRW;          // split mode only
-    uint32_t* myrow = rows + tid * RW;
     const int h = active ? c / P.D : 0;
-    const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + tok0) * P.sT +
+    const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0) * P.sT +
                           (int64_t)h * P.sH + (active ? c - h * P.D : 0);
+    const int64_t s1 = P.sT;
+    uint32_t* trow = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
+    const uint32_t cap = (uint32_t)P.tempw;
+    uint32_t len = 0u;
 
-    uint16_t* crow = cdfr + tid * kLp;
     if (FUSED) {
-        // ---- pass 1: quantise, stash symbols (4 tokens per word), count
+        uint32_t* myrow = rows + tid * SYMW;
+        uint16_t* cdfr = reinterpret_cast<uint16_t*>(tab);
+        uint16_t* crow = cdfr + tid * kLp;
         uint16_t* hist = crow;
 #pragma unroll
         for (int i = 0; i < kLp; ++i) crow[i] = 0;
-        __syncthreads();   // fac / ptab ready
+        __syncthreads();   // fac ready
         if (active) {
-            // 16 tokens per iteration: all 16 loads are issued before the first use (DRAM latency overlaps)
-            const int64_t s1 = P.sT;
+            // ---- pass 1: 12 tokens (two packed words) per iteration, all loads issued before the first use
             const uint16_t* p = src;
-            int w = 0;
-            for (; w + 4 <= (gt >> 2); w += 4, p += 16 * s1) {
-                uint16_t x[16];
+            int tk = 0, w = 0;
+            for (; tk + 2 * SPW <= gt; tk += 2 * SPW, w += 2, p += 2 * SPW * s1) {
+                uint16_t x[2 * SPW];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) x[k] = __ldg(p + k * s1);
+                for (int k = 0; k < 2 * SPW; ++k) x[k] = __ldg(p + k * s1);
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const float4 f = *reinterpret_cast<const float4*>(fac + 4 * (w + q4));
-                    const uint32_t q0 = quant_symbol(half_to_float(x[4 * q4 + 0], DT), f.x, maxq);
-                    const uint32_t q1 = quant_symbol(half_to_float(x[4 * q4 + 1], DT), f.y, maxq);
-                    const uint32_t q2 = quant_symbol(half_to_float(x[4 * q4 + 2], DT), f.z, maxq);
-                    const uint32_t q3 = quant_symbol(half_to_float(x[4 * q4 + 3], DT), f.w, maxq);
-                    hist[q0] += 1; hist[q1] += 1; hist[q2] += 1; hist[q3] += 1;     // symbols are <= 30 by construction
-                    myrow[w + q4] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t word = 0u;
+#pragma unroll
+                    for (int k = 0; k < SPW; ++k) {
+                        const uint32_t q = quant_symbol(half_to_float(x[half * SPW + k], DT), fac[tk + half * SPW + k], maxq);
+                        hist[q] += 1;                                   // symbols are <= 30 by construction
+                        word |= q << (5 * k);
+                    }
+                    myrow[w + half] = word;
                 }
             }
-            for (int tk = 4 * w; tk < gt; tk += 4, ++w, p += 4 * s1) {               // ragged tail
+            for (; tk < gt; tk += SPW, ++w, p += SPW * s1) {              // ragged tail: up to SPW tokens per word
                 uint32_t word = 0u;
-                for (int k = 0; k < 4 && tk + k < gt; ++k) {
+                for (int k = 0; k < SPW && tk + k < gt; ++k) {
                     const uint32_t q = quant_symbol(half_to_float(__ldg(p + k * s1), DT), fac[tk + k], maxq);
                     hist[q] += 1;
-                    word |= q << (8 * k);
+                    word |= q << (5 * k);
                 }
                 myrow[w] = word;
             }
+        }
+        __syncthreads();   // every thread is done with fac: reuse it as the fl32(n / t) table
+        {
+            const float tf = (float)t;
+            for (int n = tid; n <= t; n += CT) fac[n] = fdiv((float)n, tf);
+        }
+        __syncthreads();
+        if (active) {
             // ---- CDF from the thread's own histogram, written over it (counts -> registers first)
             uint32_t cnt[32];
 #pragma unroll
@@ -304,7 +231,7 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
             CdfAccum acc;
             acc.init(t);
 #pragma unroll
-            for (uint32_t i = 0; i < 32u; ++i) crow[i] = acc.next_p(i, ptab[cnt[i]]);
+            for (uint32_t i = 0; i < 32u; ++i) crow[i] = acc.next_p(i, fac[cnt[i]]);
             crow[32] = acc.next_p(32u, 0.0f);
         }
         __syncthreads();
@@ -312,11 +239,38 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
             uint16_t* dstc = reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
             for (int e = tid; e < ncols * kLp; e += CT) dstc[e] = cdfr[e];
         }
+        // ---- pass 2: arithmetic-code the stream (branch-light core, see ac_core.cuh)
+        if (active) {
+            EncState2 st;
+            st.init();
+            int tk = 0;
+            for (int w = 0; tk < gt; ++w) {
+                const uint32_t word = myrow[w];
+                if (tk + SPW <= gt) {
+#pragma unroll
+                    for (int k = 0; k < SPW; ++k) {
+                        const uint32_t sidx = (word >> (5 * k)) & 31u;       // <= 30: crow[sidx + 1] is a real entry
+                        const uint32_t c_lo = crow[sidx];
+                        enc_symbol2(st, c_lo, (uint32_t)crow[sidx + 1u] - c_lo, trow, cap);
+                    }
+                    tk += SPW;
+                } else {
+                    for (int k = 0; tk < gt; ++k, ++tk) {
+                        const uint32_t sidx = (word >> (5 * k)) & 31u;
+                        const uint32_t c_lo = crow[sidx];
+                        enc_symbol2(st, c_lo, (uint32_t)crow[sidx + 1u] - c_lo, trow, cap);
+                    }
+                }
+            }
+            len = enc_finish2(st, trow, cap);
+            if (st.w > cap) atomicOr(&P.err[j], 1u);   // size bound violated (cannot happen; stores were clamped)
+        }
     } else {
-        // CDF of the whole chunk was written by cdf_kernel: load it and build the pair rows
+        // CDF of the whole chunk was written by cdf_kernel: load it and build the (c_lo | width << 16) rows
+        uint32_t* prow = tab + tid * PAIRW;
         const uint16_t* cdf_src =
             reinterpret_cast<const uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
-        for (int e = tid; e < ncols * kLp; e += CT) pair[e] = cdf_src[e];
+        for (int e = tid; e < ncols * kLp; e += CT) tab[e] = cdf_src[e];
         __syncthreads();   // also: fac ready
         if (active) {
             uint32_t cv[kLp];
@@ -327,37 +281,8 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
                 const uint32_t hi = (i == 31) ? 0x10000u : cv[i + 1];
                 prow[i] = cv[i] | ((hi - cv[i]) << 16);
             }
-        }
-    }
-
-    // ---- pass 2: arithmetic-code the group (branch-light core, see ac_core.cuh)
-    uint32_t len = 0u;
-    if (active) {
-        EncState2 st;
-        st.init();
-        if (FUSED) {
-            // in place: after n symbols at most n bytes have been emitted (own CDF => <= 8 bits/symbol), and word w is
-            // already in a register when the coder may overwrite it
-            const int nfull = gt >> 2;
-            for (int w = 0; w < nfull; ++w) {
-                const uint32_t word = myrow[w];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t sidx = (word >> (8 * k)) & 31u;       // <= 30: crow[sidx + 1] is a real entry
-                    const uint32_t c_lo = crow[sidx];
-                    enc_symbol2(st, c_lo, (uint32_t)crow[sidx + 1u] - c_lo, myrow, (uint32_t)RW);
-                }
-            }
-            if (gt & 3) {
-                const uint32_t word = myrow[nfull];
-                for (int k = 0; k < (gt & 3); ++k) {
-                    const uint32_t sidx = (word >> (8 * k)) & 31u;
-                    const uint32_t c_lo = crow[sidx];
-                    enc_symbol2(st, c_lo, (uint32_t)crow[sidx + 1u] - c_lo, myrow, (uint32_t)RW);
-                }
-            }
-        } else {
-            const int64_t s1 = P.sT;
+            EncState2 st;
+            st.init();
             const uint16_t* p = src;
             for (int tk = 0; tk < gt; tk += 4, p += 4 * s1) {
                 uint16_t xb[4];
@@ -367,43 +292,31 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
                 for (int k = 0; k < 4; ++k) {
                     if (tk + k < gt) {
                         const uint32_t pr = prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq)];
-                        enc_symbol2(st, pr & 0xffffu, pr >> 16, myrow, (uint32_t)RW);
+                        enc_symbol2(st, pr & 0xffffu, pr >> 16, trow, cap);
                     }
                 }
             }
+            len = enc_finish2(st, trow, cap);
+            if (st.w > cap) atomicOr(&P.err[j], 1u);
         }
-        len = enc_finish2(st, myrow, (uint32_t)RW);
-        if (st.w > (uint32_t)RW) atomicOr(&P.err[j], 1u);   // size bound violated (cannot happen; stores were clamped)
     }
 
-    // ---- compaction: tile scan + look-back, then contiguous copy-out
-    uint32_t tile_total;
-    const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
-    s_off[tid] = my_off;
-    s_len[tid] = len;
-    if (tid == 0) s_excl = lookback_excl(P.status, tile, first_tile, (unsigned long long)tile_total, &P.err[j]);
-    __syncthreads();
-    const unsigned long long excl = s_excl;
+    // ---- stream lengths to the container, tile total for the compaction scan
     if (active) {
-        int32_t* lengths = reinterpret_cast<int32_t*>(cont + lo.off_lengths) + ((int64_t)g * NL + nl) * P.C;
+        int32_t* lengths = reinterpret_cast<int32_t*>(cont + lo.off_lengths) + ((int64_t)id.g * NL + nl) * P.C;
         lengths[c] = (int32_t)len;
     }
-    // never write past the slot the caller gave us
-    const int64_t room = P.out_stride - lo.off_payload;
-    if ((int64_t)(excl + tile_total) <= room) {
-        copy_rows_out(rows, RW, s_off, s_len, cont + lo.off_payload + excl);
-    } else if (tid == 0) {
-        atomicOr(&P.err[j], 4u);
-    }
-    if (last_tile_of_chunk && tid == 0) P.totals[j] = excl + tile_total;
+    uint32_t tile_total;
+    (void)block_excl_scan(len, s_warp, &tile_total);
+    if (tid == 0) P.tile_tot[(int64_t)j * P.tiles_full + id.tile_in_chunk] = tile_total;
 }
 
 // ------------------------------------------------------------------------------------------ cdf (chunks > 256 tokens)
 template <int DT>
 __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* pair = smem;                                        // CT * PAIRW  (counts, then cdf)
-    float* fac = reinterpret_cast<float*>(pair + CT * PAIRW);     // kGroup
+    uint32_t* cnts = smem;                                        // CT * PAIRW counters
+    float* fac = reinterpret_cast<float*>(cnts + CT * PAIRW);     // kGroup
     const int tid = threadIdx.x;
     const int NL = 2 * P.L;
     const uint32_t per_chunk = (uint32_t)NL * P.tpp;
@@ -419,7 +332,7 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
     const Layout lo = make_layout(P.L, P.C, t);
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t;
     const float maxq = P.pt.maxq[nl];
-    uint32_t* prow = pair + tid * PAIRW;
+    uint32_t* prow = cnts + tid * PAIRW;
 #pragma unroll
     for (int i = 0; i < PAIRW; ++i) prow[i] = 0u;
     const int h = active ? c / P.D : 0;
@@ -442,14 +355,96 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
             }
         }
     }
-    if (active) {
+    if (active) {   // counts -> CDF values, written back over the counter row
         uint32_t cnt[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) cnt[i] = prow[i];
-        build_pair_row(prow, t, [&](uint32_t i) -> uint32_t { return i < 32u ? cnt[i] : 0u; });
+        CdfAccum acc;
+        acc.init(t);
+#pragma unroll
+        for (uint32_t i = 0; i < 32u; ++i) prow[i] = acc.next(i, cnt[i]);
+        prow[32] = acc.next(32u, 0u);
     }
     __syncthreads();
-    store_cdf_rows(pair, reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp, ncols);
+    uint16_t* dstc = reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
+    for (int e = tid; e < ncols * kLp; e += CT) dstc[e] = (uint16_t)cnts[e];   // rows are PAIRW == kLp words: e maps 1:1
+}
+
+// ------------------------------------------------------------------------------------------ compaction
+// exclusive prefix over a chunk's tile totals (in place) + the chunk's payload size; one CTA per chunk
+__global__ void __launch_bounds__(1024) enc_scan_kernel(EncParams P) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    const int j = blockIdx.x;
+    const int t = chunk_tokens_of(P, j);
+    const int ntiles = ((t + kGroup - 1) / kGroup) * 2 * P.L * P.tpp;
+    uint32_t* tb = P.tile_tot + (int64_t)j * P.tiles_full;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < ntiles ? tb[i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0ull, tot = 0ull;
+        for (int w = 0; w < 32; ++w) {
+            const unsigned long long s = s_w[w];
+            if (w < wid) wbase += s;
+            tot += s;
+        }
+        const unsigned long long carry = s_carry;
+        const unsigned long long excl = carry + wbase + inc - v;
+        if (i < ntiles) {
+            if (excl + v >= (1ull << 32)) atomicOr(&P.err[j], 8u);     // payload offsets are 32-bit per chunk
+            tb[i] = (uint32_t)excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) P.totals[j] = s_carry;
+}
+
+// move each tile's streams from its temp rows to their final, contiguous place in the payload
+// (collect_bytes, cachegen_encoder.py:225-238): one warp per stream, byte-granular coalesced copies
+__global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
+    __shared__ uint32_t s_warp[CT / 32];
+    __shared__ uint32_t s_off[CT], s_len[CT];
+    const int tid = threadIdx.x;
+    TileId id;
+    if (!decode_tile(P, blockIdx.x, &id)) return;
+    const int NL = 2 * P.L;
+    const int c = id.ct * CT + tid;
+    uint8_t* cont = P.out + (int64_t)id.j * P.out_stride;
+    const Layout lo = make_layout(P.L, P.C, id.t);
+    const int32_t* lengths = reinterpret_cast<const int32_t*>(cont + lo.off_lengths) + ((int64_t)id.g * NL + id.nl) * P.C;
+    const uint32_t len = c < P.C ? (uint32_t)lengths[c] : 0u;
+    uint32_t tile_total;
+    s_off[tid] = block_excl_scan(len, s_warp, &tile_total);
+    s_len[tid] = len;
+    __syncthreads();
+    const uint64_t base = P.tile_tot[(int64_t)id.j * P.tiles_full + id.tile_in_chunk];
+    const int64_t room = P.out_stride - lo.off_payload;
+    if ((int64_t)(base + tile_total) > room) {          // never write past the slot the caller gave us
+        if (tid == 0) atomicOr(&P.err[id.j], 4u);
+        return;
+    }
+    uint8_t* dst = cont + lo.off_payload + base;
+    const uint8_t* trows = reinterpret_cast<const uint8_t*>(P.temp + (int64_t)blockIdx.x * CT * P.tempw);
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int r = wid; r < CT; r += CT / 32) {
+        const uint32_t n = s_len[r];
+        const uint8_t* srcr = trows + (int64_t)r * P.tempw * 4;
+        uint8_t* d = dst + s_off[r];
+        for (uint32_t i = lane; i < n; i += 32) d[i] = srcr[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------ finalize
@@ -681,11 +676,13 @@ struct ProfScope {
     }
 };
 
-static size_t enc_ws_layout(int64_t n_tiles, int n_chunks, size_t* off_status, size_t* off_totals, size_t* off_err) {
-    size_t o = 64;                       // ticket
-    *off_status = o; o += (size_t)n_tiles * 8;
-    *off_totals = o; o += (size_t)n_chunks * 8;
-    *off_err = o;    o += (size_t)n_chunks * 4;
+static size_t enc_ws_layout(int64_t n_tiles_alloc, int n_chunks, int tempw, size_t* off_tot, size_t* off_totals,
+                            size_t* off_err, size_t* off_temp) {
+    size_t o = 0;
+    *off_tot = o;    o += (size_t)n_tiles_alloc * 4;  o = (o + 255) & ~(size_t)255;
+    *off_totals = o; o += (size_t)n_chunks * 8;       o = (o + 255) & ~(size_t)255;
+    *off_err = o;    o += (size_t)n_chunks * 4;       o = (o + 255) & ~(size_t)255;
+    *off_temp = o;   o += (size_t)n_tiles_alloc * CT * (size_t)tempw * 4;
     return (o + 255) & ~(size_t)255;
 }
 
@@ -720,8 +717,8 @@ int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t c
     if (L <= 0 || H <= 0 || D <= 0 || chunk_tokens <= 0 || n_chunks <= 0) return -2;
     const int64_t G = (chunk_tokens + kGroup - 1) / kGroup;
     const int64_t n_tiles = (int64_t)n_chunks * G * 2 * L * tiles_per_plane(H * D);
-    size_t a, b, c;
-    return (int64_t)enc_ws_layout(n_tiles, n_chunks, &a, &b, &c);
+    size_t a, b, c, d;
+    return (int64_t)enc_ws_layout(n_tiles, n_chunks, chunk_tokens <= kGroup ? TEMPW_FUSED : TEMPW_SPLIT, &a, &b, &c, &d);
 }
 
 int64_t b200kv_decode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks) {
@@ -756,20 +753,22 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     B2_REQUIRE(out_stride >= lo.off_payload + 16, "out_stride smaller than the fixed container sections");
 
     const int64_t G = lo.ngroups;
-    const int64_t G_last = (last_chunk_tokens + kGroup - 1) / kGroup;
     const int64_t per_group = 2 * (int64_t)P.L * P.tpp;
-    const int64_t n_tiles = ((int64_t)(n_chunks - 1) * G + G_last) * per_group;
-    const int64_t n_tiles_alloc = (int64_t)n_chunks * G * per_group;
-    size_t off_status, off_totals, off_err;
-    const size_t need = enc_ws_layout(n_tiles_alloc, n_chunks, &off_status, &off_totals, &off_err);
+    const int64_t tiles_full = G * per_group;
+    const int64_t n_tiles = (int64_t)n_chunks * tiles_full;     // tiles beyond a ragged last chunk exit at once
+    const bool fused = chunk_tokens <= kGroup;
+    P.tiles_full = (int32_t)tiles_full;
+    P.tempw = fused ? TEMPW_FUSED : TEMPW_SPLIT;
+    size_t off_tot, off_totals, off_err, off_temp;
+    const size_t need = enc_ws_layout(n_tiles, n_chunks, P.tempw, &off_tot, &off_totals, &off_err, &off_temp);
     B2_REQUIRE(workspace != nullptr && workspace_bytes >= (int64_t)need, "workspace too small");
-    B2_REQUIRE(n_tiles < (1ll << 31), "too many tiles in one call");
+    B2_REQUIRE(n_tiles < (1ll << 31) && tiles_full < (1ll << 31), "too many tiles in one call");
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    P.ticket = reinterpret_cast<unsigned int*>(ws);
-    P.status = reinterpret_cast<unsigned long long*>(ws + off_status);
+    P.tile_tot = reinterpret_cast<uint32_t*>(ws + off_tot);
     P.totals = reinterpret_cast<unsigned long long*>(ws + off_totals);
     P.err = reinterpret_cast<unsigned int*>(ws + off_err);
-    B2_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, stream));
+    P.temp = reinterpret_cast<uint32_t*>(ws + off_temp);
+    B2_CHECK_CUDA(cudaMemsetAsync(ws, 0, off_temp, stream));     // counters only; temp rows need no init
 
     // 1) per-(plane, token) absmax -> maxes sections
     const int64_t total_tokens = (int64_t)(n_chunks - 1) * chunk_tokens + last_chunk_tokens;
@@ -784,10 +783,9 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
         else absmax_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
         B2_CHECK_CUDA(cudaGetLastError());
     }
-    // 2) encode
-    const bool fused = chunk_tokens <= kGroup;
-    const size_t smem_fused = (size_t)(((CT * ROWW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + (kGroup + 4) + 2 * CT) * 4;
-    const size_t smem_split = (size_t)(((CT * ROWW_OUT + CT * PAIRW + 3) & ~3) + kGroup + 2 * CT) * 4;
+    // 2) encode (streams -> temp rows, lengths, tile totals)
+    const size_t smem_fused = (size_t)(((CT * SYMW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + 4) * 4;
+    const size_t smem_split = (size_t)(((CT * PAIRW + 3) & ~3) + kGroup + 4) * 4;
     const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
 #define B2_LAUNCH_ENC(FUSED, DT, SMEM)                                                                     \
     do {                                                                                                   \
@@ -811,9 +809,11 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     }
 #undef B2_LAUNCH_ENC
     B2_CHECK_CUDA(cudaGetLastError());
-    // 3) headers + sizes
+    // 3) compaction (collect_bytes) + headers + sizes
     {
         ProfScope prof(kProfFinalize, stream);
+        enc_scan_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(P);
+        compact_kernel<<<(unsigned)n_tiles, CT, 0, stream>>>(P);
         finalize_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P);
     }
     B2_CHECK_CUDA(cudaGetLastError());
