@@ -449,6 +449,11 @@ struct DecState2 {
 // Word source concept: uint32_t next_be() -- next 4 stream bytes as a big-endian word (aligned load + swap).
 template <class Src>
 B2_HD void dec_refill2(DecState2& st, Src& src) {
+#if defined(__CUDA_ARCH__)
+    // warp-uniform guard: at low bit rates most symbol steps need no refill in any lane, and predicated-off
+    // instructions still cost issue slots
+    if (!__any_sync(__activemask(), st.rb < 32u)) return;
+#endif
     if (st.rb < 32u) {
         st.res |= (uint64_t)src.next_be() << (32u - st.rb);
         st.rb += 32u;
@@ -473,8 +478,9 @@ B2_HD void dec_init2(DecState2& st, Src& src, uint32_t skip) {
 //   count = ((value - low + 1) * 2^16 - 1) / span      (one reciprocal instead of a 64-bit division).
 B2_HD uint32_t dec_count_approx(uint32_t off, uint32_t rng) {
 #if defined(__CUDA_ARCH__)
-    const float q = __fdividef(__uint2float_rn(off), __uint2float_rn(rng)) * 65536.0f;
-    const uint32_t c = (uint32_t)__float2int_rz(q);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rn(rng)));      // one MUFU.RCP; rng >= 2^30
+    const uint32_t c = (uint32_t)__float2int_rz(__uint2float_rn(off) * (rc * 65536.0f));
 #else
     const float q = ((float)off / (float)rng) * 65536.0f;
     const uint32_t c = (uint32_t)(int)q;
@@ -505,15 +511,19 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, CdfFn cdf, bool last) {
     uint32_t c0 = cdf(s);
     uint32_t plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
     uint32_t c1 = s == 31u ? 0x10000u : cdf(s + 1u);
-    uint32_t phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);          // 2^32 wraps to 0 (uint32 maths), see below
-    // exactness fix-up (rare, warp-uniformly skipped): phi == 0 with c1 == 65536 means 2^32, i.e. "off < phi" holds
-    while (off < plo && s > 0u) {
-        --s; phi = plo; c0 = cdf(s);
-        plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
-    }
-    while (s < kTop && !(c1 == 0x10000u && phi == 0u) && off >= phi) {
-        ++s; plo = phi; c1 = s == 31u ? 0x10000u : cdf(s + 1u);
-        phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);
+    uint32_t phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);          // 2^32 wraps to 0 (uint32 maths)
+    // exact iff plo <= off < phi.  In wrapping uint32 arithmetic that is (off - plo) < (phi - plo), which also
+    // covers phi == 2^32 (wrapped to 0).  count~ is within +-1 of count, so this almost never fails; the loops
+    // make the result exact whatever the approximation did.
+    if ((uint32_t)(off - plo) >= (uint32_t)(phi - plo)) {
+        while (off < plo && s > 0u) {
+            --s; phi = plo; c0 = cdf(s);
+            plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
+        }
+        while (s < kTop && (uint32_t)(off - plo) >= (uint32_t)(phi - plo)) {
+            ++s; plo = phi; c1 = s == 31u ? 0x10000u : cdf(s + 1u);
+            phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);
+        }
     }
     if (last) return s;
     uint32_t low = st.low + plo;

@@ -186,17 +186,30 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
         uint16_t* hist = crow;
 #pragma unroll
         for (int i = 0; i < kLp; ++i) crow[i] = 0;
+        // pull the whole tile (gt token rows x 256 B) into L2 up front: one prefetch per 128-byte line, spread over
+        // the CTA, so pass 1's loads pay L2 latency instead of a DRAM round trip per batch
+        {
+            const int lines_per_tok = (ncols * 2 + 127) >> 7;
+            const uint16_t* tile0 = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0) * P.sT +
+                                    (int64_t)((ct * CT) / P.D) * P.sH + ((ct * CT) % P.D);
+            if ((ct * CT) / P.D == (ct * CT + ncols - 1) / P.D)    // tile lies within one head row: contiguous per token
+                for (int i = tid; i < gt * lines_per_tok; i += CT) {
+                    const int tok = i / lines_per_tok, ln = i - tok * lines_per_tok;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(tile0 + (int64_t)tok * s1 + ln * 64));
+                }
+        }
         __syncthreads();   // fac ready
         if (active) {
-            // ---- pass 1: 12 tokens (two packed words) per iteration, all loads issued before the first use
+            // ---- pass 1: 24 tokens (four packed words) per iteration, all loads issued before the first use
+            constexpr int NB = 4;
             const uint16_t* p = src;
             int tk = 0, w = 0;
-            for (; tk + 2 * SPW <= gt; tk += 2 * SPW, w += 2, p += 2 * SPW * s1) {
-                uint16_t x[2 * SPW];
+            for (; tk + NB * SPW <= gt; tk += NB * SPW, w += NB, p += NB * SPW * s1) {
+                uint16_t x[NB * SPW];
 #pragma unroll
-                for (int k = 0; k < 2 * SPW; ++k) x[k] = __ldg(p + k * s1);
+                for (int k = 0; k < NB * SPW; ++k) x[k] = __ldg(p + k * s1);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < NB; ++half) {
                     uint32_t word = 0u;
 #pragma unroll
                     for (int k = 0; k < SPW; ++k) {
@@ -416,7 +429,7 @@ __global__ void __launch_bounds__(1024) enc_scan_kernel(EncParams P) {
 // (collect_bytes, cachegen_encoder.py:225-238): one warp per stream, byte-granular coalesced copies
 __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
     __shared__ uint32_t s_warp[CT / 32];
-    __shared__ uint32_t s_off[CT], s_len[CT];
+    __shared__ uint32_t s_off[CT];
     const int tid = threadIdx.x;
     TileId id;
     if (!decode_tile(P, blockIdx.x, &id)) return;
@@ -428,22 +441,25 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
     const uint32_t len = c < P.C ? (uint32_t)lengths[c] : 0u;
     uint32_t tile_total;
     s_off[tid] = block_excl_scan(len, s_warp, &tile_total);
-    s_len[tid] = len;
-    __syncthreads();
     const uint64_t base = P.tile_tot[(int64_t)id.j * P.tiles_full + id.tile_in_chunk];
     const int64_t room = P.out_stride - lo.off_payload;
     if ((int64_t)(base + tile_total) > room) {          // never write past the slot the caller gave us
         if (tid == 0) atomicOr(&P.err[id.j], 4u);
         return;
     }
-    uint8_t* dst = cont + lo.off_payload + base;
-    const uint8_t* trows = reinterpret_cast<const uint8_t*>(P.temp + (int64_t)blockIdx.x * CT * P.tempw);
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int r = wid; r < CT; r += CT / 32) {
-        const uint32_t n = s_len[r];
-        const uint8_t* srcr = trows + (int64_t)r * P.tempw * 4;
-        uint8_t* d = dst + s_off[r];
-        for (uint32_t i = lane; i < n; i += 32) d[i] = srcr[i];
+    // one thread per stream: all CT rows move in parallel (word loads from the temp row, byte stores because the
+    // destination has arbitrary alignment; L2 merges them into full sectors)
+    if (len) {
+        uint8_t* d = cont + lo.off_payload + base + s_off[tid];
+        const uint32_t* srcw = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
+        const uint32_t nw = (len + 3u) >> 2;
+        for (uint32_t w = 0; w < nw; ++w) {
+            const uint32_t v = __ldg(srcw + w);
+            const uint32_t nb = min(4u, len - 4u * w);
+#pragma unroll
+            for (uint32_t b = 0; b < 4u; ++b)
+                if (b < nb) d[4u * w + b] = (uint8_t)(v >> (8u * b));
+        }
     }
 }
 
