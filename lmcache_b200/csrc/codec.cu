@@ -426,10 +426,12 @@ __global__ void __launch_bounds__(1024) enc_scan_kernel(EncParams P) {
 }
 
 // move each tile's streams from its temp rows to their final, contiguous place in the payload
-// (collect_bytes, cachegen_encoder.py:225-238): one warp per stream, byte-granular coalesced copies
+// (collect_bytes, cachegen_encoder.py:225-238).  Each thread copies its own stream into a shared-memory image of the
+// tile's byte range (placed at the destination's 16-byte phase), then the CTA writes that range with 16-byte vector
+// stores: the payload is written as full sectors no matter how short the individual streams are.
 __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
+    extern __shared__ __align__(16) uint8_t stage[];      // 16 + CT * tempw * 4 bytes
     __shared__ uint32_t s_warp[CT / 32];
-    __shared__ uint32_t s_off[CT];
     const int tid = threadIdx.x;
     TileId id;
     if (!decode_tile(P, blockIdx.x, &id)) return;
@@ -438,19 +440,19 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
     uint8_t* cont = P.out + (int64_t)id.j * P.out_stride;
     const Layout lo = make_layout(P.L, P.C, id.t);
     const int32_t* lengths = reinterpret_cast<const int32_t*>(cont + lo.off_lengths) + ((int64_t)id.g * NL + id.nl) * P.C;
-    const uint32_t len = c < P.C ? (uint32_t)lengths[c] : 0u;
+    const uint32_t len = c < P.C ? min((uint32_t)lengths[c], (uint32_t)P.tempw * 4u) : 0u;
     uint32_t tile_total;
-    s_off[tid] = block_excl_scan(len, s_warp, &tile_total);
+    const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
     const uint64_t base = P.tile_tot[(int64_t)id.j * P.tiles_full + id.tile_in_chunk];
     const int64_t room = P.out_stride - lo.off_payload;
     if ((int64_t)(base + tile_total) > room) {          // never write past the slot the caller gave us
         if (tid == 0) atomicOr(&P.err[id.j], 4u);
         return;
     }
-    // one thread per stream: all CT rows move in parallel (word loads from the temp row, byte stores because the
-    // destination has arbitrary alignment; L2 merges them into full sectors)
+    uint8_t* dst = cont + lo.off_payload + base;
+    const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
     if (len) {
-        uint8_t* d = cont + lo.off_payload + base + s_off[tid];
+        uint8_t* d = stage + phase + my_off;
         const uint32_t* srcw = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
         const uint32_t nw = (len + 3u) >> 2;
         for (uint32_t w = 0; w < nw; ++w) {
@@ -461,6 +463,15 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
                 if (b < nb) d[4u * w + b] = (uint8_t)(v >> (8u * b));
         }
     }
+    __syncthreads();
+    // [phase, phase + tile_total) of `stage` -> dst - phase + same offsets; vector body, byte head / tail
+    const uint32_t lo_b = phase, hi_b = phase + tile_total;
+    const uint32_t body0 = min(hi_b, (lo_b + 15u) & ~15u), body1 = max(body0, hi_b & ~15u);
+    uint8_t* dbase = dst - phase;
+    for (uint32_t i = lo_b + tid; i < body0; i += CT) dbase[i] = stage[i];
+    for (uint32_t i = body0 + 16u * tid; i < body1; i += 16u * CT)
+        *reinterpret_cast<uint4*>(dbase + i) = *reinterpret_cast<const uint4*>(stage + i);
+    for (uint32_t i = body1 + tid; i < hi_b; i += CT) dbase[i] = stage[i];
 }
 
 // ------------------------------------------------------------------------------------------ finalize
@@ -828,8 +839,10 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     // 3) compaction (collect_bytes) + headers + sizes
     {
         ProfScope prof(kProfFinalize, stream);
+        B2_CHECK_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((size_t)CT * TEMPW_SPLIT * 4 + 32)));
         enc_scan_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(P);
-        compact_kernel<<<(unsigned)n_tiles, CT, 0, stream>>>(P);
+        compact_kernel<<<(unsigned)n_tiles, CT, (size_t)CT * P.tempw * 4 + 32, stream>>>(P);
         finalize_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P);
     }
     B2_CHECK_CUDA(cudaGetLastError());
