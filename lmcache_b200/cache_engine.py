@@ -148,11 +148,17 @@ class LMCacheEngine:
         n_chunks = 0
         if start_chunk_idx < len(chunk_hashes):
             view = KvView.from_tuple(self._as_cuda_kv(kv_tensors_raw), fmt)
-            chunks = self._pack_chunks(view, start_chunk_idx * self.chunk_size, fmt)
-            end_make_chunks = time.perf_counter()
-            n_chunks = self.engine_.batched_put(
-                ((self._make_key(h, fmt), c) for h, c in zip(chunk_hashes[start_chunk_idx:], chunks)),
-                blocking=blocking)
+            self._geom = (view.L, view.H, view.D, view.dtype)
+            keys = [self._make_key(h, fmt) for h in chunk_hashes[start_chunk_idx:]]
+            if self._fast_path():
+                # B200-native path: the backend consumes the caller's 2L tensors directly (batched encode / one gather)
+                end_make_chunks = time.perf_counter()
+                n_chunks = self.engine_.put_kv_chunks(keys, view, start_chunk_idx * self.chunk_size, self.chunk_size,
+                                                      blocking=blocking)
+            else:
+                chunks = self._pack_chunks(view, start_chunk_idx * self.chunk_size, fmt)
+                end_make_chunks = time.perf_counter()
+                n_chunks = self.engine_.batched_put(zip(keys, chunks), blocking=blocking)
         else:
             end_make_chunks = time.perf_counter()
         end_time = time.perf_counter()
@@ -178,6 +184,8 @@ class LMCacheEngine:
         if fmt not in ("vllm", "huggingface"):
             raise ValueError(f"Invalid format: {fmt}")
         chunk_hashes = self._prefix_hash(tokens, num_skip_chunk)
+        if self._fast_path() and len(chunk_hashes) > 0:
+            return self._retrieve_into_blob(tokens, chunk_hashes, num_skip_tok, num_skip_chunk, ret_mask, fmt, st)
         retrieved: List[torch.Tensor] = []
         for chunk in self.engine_.batched_get(self._make_key(h, fmt) for h in chunk_hashes):
             if chunk is None:
@@ -206,6 +214,53 @@ class LMCacheEngine:
         ret = self._blob_to_tuple_kv(blob)
         retrieved_token_count = total
         logger.info(f"Retrieved {len(retrieved)} chunks ({retrieved_token_count} tokens in total) -- "
+                    f"elapsed time {time.perf_counter() - st}")
+        ret_mask[num_skip_tok + retrieved_token_count:] = False
+        return ret, ret_mask
+
+    # ------------------------------------------------------------------ B200-native fast paths
+    def _fast_path(self) -> bool:
+        f = getattr(self.engine_, "supports_kv_view", None)
+        return bool(f and f())
+
+    def _kv_geometry(self):
+        """(L, H, D, dtype) of this engine's chunks, learnt from the first store / a probe get."""
+        return getattr(self, "_geom", None)
+
+    def _retrieve_into_blob(self, tokens, chunk_hashes, num_skip_tok, num_skip_chunk, ret_mask, fmt, st):
+        """retrieve() without per-chunk tensors or torch.cat: the backend decodes / uploads every hit chunk straight
+        into one preallocated blob; the suffix-mask trim of the first chunk is a view offset, not a copy."""
+        keys = [self._make_key(h, fmt) for h in chunk_hashes]
+        geom = self._kv_geometry()
+        if geom is None:
+            # shapes unknown (nothing stored through this engine yet): learn them from the first chunk
+            first = self.engine_.get(keys[0])
+            if first is None:
+                logger.info("Retrieved 0 chunks")
+                ret_mask[:] = False
+                return (), ret_mask
+            L, H, D = (first.shape[0], first.shape[3], first.shape[4]) if fmt == "vllm" else \
+                (first.shape[0], first.shape[2], first.shape[4])
+            self._geom = geom = (L, H, D, first.dtype)
+        L, H, D, dtype = geom
+        od = getattr(getattr(self.engine_, "deserializer", None), "out_dtype", None)
+        if od is not None:
+            dtype = od()
+        n_tok_max = len(tokens) - num_skip_chunk * self.chunk_size
+        shape = (L, 2, n_tok_max, H, D) if fmt == "vllm" else (L, 2, H, n_tok_max, D)
+        device = torch.device("cuda", torch.cuda.current_device())
+        blob = torch.empty(shape, dtype=dtype, device=device)
+        n = self.engine_.get_kv_into(keys, KvView.from_blob(blob, fmt), 0, self.chunk_size)
+        if n == 0:
+            logger.info("Retrieved 0 chunks")
+            ret_mask[:] = False
+            return (), ret_mask
+        tdim = 2 if fmt == "vllm" else 3
+        got = min(n * self.chunk_size, n_tok_max)              # the last hit chunk may be the ragged tail
+        extra = num_skip_tok - num_skip_chunk * self.chunk_size
+        ret = self._blob_to_tuple_kv(blob.narrow(tdim, extra, got - extra))
+        retrieved_token_count = got - extra
+        logger.info(f"Retrieved {n} chunks ({retrieved_token_count} tokens in total) -- "
                     f"elapsed time {time.perf_counter() - st}")
         ret_mask[num_skip_tok + retrieved_token_count:] = False
         return ret, ret_mask

@@ -60,12 +60,15 @@ class KvView:
     """A KV source / destination for the native library: either one strided blob tensor or the engine's
     tuple of 2L per-layer tensors (no stack / permute / contiguous copies).  Keeps the tensors alive."""
 
-    def __init__(self, desc: N.KvDesc, keep, ntokens: int, device: torch.device, dtype: torch.dtype):
+    def __init__(self, desc: N.KvDesc, keep, ntokens: int, device: torch.device, dtype: torch.dtype,
+                 fmt: str = "vllm", blob: Optional[torch.Tensor] = None):
         self.desc = desc
         self._keep = keep
         self.ntokens = ntokens
         self.device = device
         self.dtype = dtype
+        self.fmt = fmt
+        self.blob = blob      # the single blob tensor behind this view, when there is one
 
     @property
     def L(self): return self.desc.L
@@ -103,7 +106,7 @@ class KvView:
         d.sL, d.sKV, d.sT, d.sH = sL, sKV, sT, sH
         d.L, d.H, d.D = L, H, D
         d.dtype = KvView._code(blob.dtype)
-        return KvView(d, blob, T, blob.device, blob.dtype)
+        return KvView(d, blob, T, blob.device, blob.dtype, fmt, blob)
 
     @staticmethod
     def from_tuple(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], fmt: str) -> "KvView":
@@ -141,7 +144,7 @@ class KvView:
         d.sT, d.sH = sT, sH
         d.L, d.H, d.D = L, H, D
         d.dtype = KvView._code(ref.dtype)
-        return KvView(d, (keep, ptrs), T, ref.device, ref.dtype)
+        return KvView(d, (keep, ptrs), T, ref.device, ref.dtype, fmt)
 
 
 def parse_header(buf) -> N.Header:
@@ -344,13 +347,16 @@ class CacheGenCodec:
             raise ValueError("containers of one decode call must share max_dtype")
         ntoks = [int(h.ntokens) for h in heads]
         tmax = max(ntoks)
+        for tok, nt in zip(dst_tok, ntoks):
+            if tok < 0 or tok + nt > dst.ntokens:
+                raise ValueError(f"container of {nt} tokens at offset {tok} does not fit a {dst.ntokens}-token destination")
         with self._dec_lock, torch.cuda.device(dst.device):
             tstream = stream if stream is not None else torch.cuda.current_stream()
             sp = tstream.cuda_stream
             need_in = sum(((int(h.total_bytes) + 15) & ~15) + 16 for h in heads) + 16
             self._order_decode(tstream, need_in, lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n))
             if n == 1 and isinstance(containers[0], torch.Tensor) and containers[0].is_cuda \
-                    and containers[0].data_ptr() % 16 == 0:
+                    and containers[0].data_ptr() % 16 == 0 and containers[0].numel() >= int(heads[0].total_bytes) + 16:
                 keep_dev = containers[0]
                 self.decode_raw(keep_dev.data_ptr(), [0], ntoks, dst, dst_tok, max_dtype, tstream, _locked=True)
                 return

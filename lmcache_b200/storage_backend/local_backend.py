@@ -109,6 +109,94 @@ class LMCLocalBackend(LMCBackendInterface):
             return out
         return val.to(self.dst_device)
 
+    # ------------------------------------------------------------------ engine fast paths
+    def supports_kv_view(self) -> bool:
+        return True
+
+    def put_kv_chunks(self, keys, view, tok_begin: int, chunk_size: int, blocking: bool = True) -> int:
+        """Store tokens [tok_begin, T) of `view` as len(keys) chunk blobs: ONE gather kernel (b200kv_pack_chunks)
+        builds every chunk blob; for the host tier ONE device->host DMA moves them all into a page-locked slab."""
+        fmt_hf = getattr(view, "fmt", "vllm") == "huggingface"
+        n_tok = view.ntokens - tok_begin
+        n_chunks = len(keys)
+        assert n_chunks == (n_tok + chunk_size - 1) // chunk_size
+        last = n_tok - (n_chunks - 1) * chunk_size
+        per_tok = 2 * view.L * view.H * view.D
+        stride = per_tok * chunk_size
+        dev = torch.empty(n_chunks * stride, dtype=view.dtype, device=view.device)
+        with torch.cuda.device(view.device):
+            cur = torch.cuda.current_stream()
+            N.check(N.lib().b200kv_pack_chunks(ctypes.byref(view.desc), tok_begin, n_chunks, chunk_size, last,
+                                               1 if fmt_hf else 0, ctypes.c_void_p(dev.data_ptr()),
+                                               stride * dev.element_size(), cur.cuda_stream), "pack_chunks")
+
+            def shape(t):
+                return (view.L, 2, view.H, t, view.D) if fmt_hf else (view.L, 2, t, view.H, view.D)
+
+            if self.device == "cuda":
+                vals = [dev[j * stride: j * stride + per_tok * (chunk_size if j < n_chunks - 1 else last)]
+                        .view(shape(chunk_size if j < n_chunks - 1 else last)) for j in range(n_chunks)]
+            else:
+                host = torch.empty(n_chunks * stride, dtype=view.dtype, pin_memory=True)
+                side = self._side_stream(view.device)
+                side.wait_stream(cur)
+                _copy_async(host, dev, side)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                vals = []
+                for j in range(n_chunks):
+                    t = chunk_size if j < n_chunks - 1 else last
+                    vals.append(_HostEntry(host[j * stride: j * stride + per_tok * t].view(shape(t)), ev, dev))
+                if blocking:
+                    ev.synchronize()
+                    for v in vals:
+                        v.event, v.src = None, None
+        with self.update_lock:
+            for key, v in zip(keys, vals):
+                self.dict[key] = v
+        return n_chunks
+
+    def get_kv_into(self, keys, dst, dst_tok0: int, chunk_size: int) -> int:
+        """Copy consecutive chunks (until the first miss) straight into the destination blob view `dst` at token
+        offsets dst_tok0 + i * chunk_size: strided 2-D copies (host tier: async uploads), no intermediate chunk tensors,
+        no torch.cat."""
+        fmt_hf = getattr(dst, "fmt", "vllm") == "huggingface"
+        blob = dst.blob
+        n = 0
+        with torch.cuda.device(blob.device):
+            stream = torch.cuda.current_stream()
+            for i, key in enumerate(keys):
+                val = self.dict.get(key, None)
+                if val is None:
+                    break
+                src = val.host if isinstance(val, _HostEntry) else val
+                if isinstance(val, _HostEntry):
+                    val.wait()
+                elif not src.is_cuda:
+                    src = src.cuda()
+                t = src.shape[3] if fmt_hf else src.shape[2]
+                tok = dst_tok0 + i * chunk_size
+                if tok + t > dst.ntokens or src.dtype != blob.dtype:
+                    break
+                es = blob.element_size()
+                if fmt_hf:      # rows = (l, kv, h): t*D contiguous elements each
+                    rows, row_bytes = blob.shape[0] * 2 * blob.shape[2], t * blob.shape[4] * es
+                    dst_pitch = blob.shape[3] * blob.shape[4] * es
+                    dptr = blob.data_ptr() + tok * blob.shape[4] * es
+                else:           # rows = (l, kv): t*H*D contiguous elements each
+                    rows, row_bytes = blob.shape[0] * 2, t * blob.shape[3] * blob.shape[4] * es
+                    dst_pitch = blob.shape[2] * blob.shape[3] * blob.shape[4] * es
+                    dptr = blob.data_ptr() + tok * blob.shape[3] * blob.shape[4] * es
+                N.check(N.lib().b200kv_copy2d_async(ctypes.c_void_p(dptr), dst_pitch, ctypes.c_void_p(src.data_ptr()),
+                                                    row_bytes, row_bytes, rows, stream.cuda_stream), "copy2d")
+                if isinstance(val, _HostEntry):
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    self._inflight = [(e, h) for e, h in self._inflight if not e.query()]
+                    self._inflight.append((ev, val.host))
+                n += 1
+        return n
+
     def close(self):
         for val in list(self.dict.values()):
             if isinstance(val, _HostEntry):

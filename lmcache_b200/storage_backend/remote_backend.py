@@ -49,11 +49,15 @@ class LMCRemoteBackend(LMCBackendInterface):
             if isinstance(item, RemoteBackendEndSignal):
                 self.put_queue.task_done()
                 break
-            key, value = item
             try:
-                self.put_blocking(key, value)
+                if item[0] == "view":
+                    _, keys, view, tok_begin, chunk_size = item
+                    self._put_view_blocking(keys, view, tok_begin, chunk_size)
+                else:
+                    key, value = item
+                    self.put_blocking(key, value)
             except Exception as e:   # a failed background put is a cache miss later, not a crash
-                logger.error(f"background put of {key.chunk_hash[:8]} failed: {e}")
+                logger.error(f"background put failed: {e}")
             finally:
                 self.put_queue.task_done()
 
@@ -95,6 +99,44 @@ class LMCRemoteBackend(LMCBackendInterface):
         if bs is None or len(bs) == 0:
             return None
         return self.deserializer.from_bytes(bs).to(self.dst_device)
+
+    # ------------------------------------------------------------------ engine fast paths (no per-chunk blobs)
+    def supports_kv_view(self) -> bool:
+        """True when the serde plugin can encode / decode straight from / into the engine's KV tensors."""
+        return hasattr(self.serializer, "view_to_bytes_batch") and hasattr(self.deserializer, "decode_into")
+
+    def _put_view_blocking(self, keys, view, tok_begin: int, chunk_size: int) -> None:
+        n_tokens = view.ntokens - tok_begin
+        blobs = self.serializer.view_to_bytes_batch(view, chunk_size, tok_begin, n_tokens)
+        assert len(blobs) == len(keys)
+        for key, bs in zip(keys, blobs):
+            self.connection.set(self._combine_key(key), bs)
+            self.existing_keys.add(key)
+
+    def put_kv_chunks(self, keys: List[CacheEngineKey], view, tok_begin: int, chunk_size: int,
+                      blocking: bool = True) -> int:
+        """Store tokens [tok_begin, T) of `view` as len(keys) chunks: one batched encode (all chunks in one kernel
+        launch sequence), then one set() per chunk.  Replaces the engine's blob pack + per-chunk to_bytes."""
+        if blocking:
+            self._put_view_blocking(keys, view, tok_begin, chunk_size)
+        else:
+            self.put_queue.put(("view", list(keys), view, tok_begin, chunk_size))
+        return len(keys)
+
+    def get_kv_into(self, keys: List[CacheEngineKey], dst, dst_tok0: int, chunk_size: int) -> int:
+        """Fetch consecutive chunks until the first miss and decode them with ONE batched launch straight into `dst`
+        (chunk i lands at token dst_tok0 + i * chunk_size).  Returns (number of chunks, tokens written)."""
+        blobs = []
+        for key in keys:
+            if not self.contains(key):
+                break
+            bs = self.connection.get(self._combine_key(key))
+            if bs is None or len(bs) == 0:
+                break
+            blobs.append(bs)
+        if blobs:
+            self.deserializer.decode_into(blobs, dst, [dst_tok0 + i * chunk_size for i in range(len(blobs))])
+        return len(blobs)
 
     def close(self):
         if self.put_thread is not None and self.put_thread.is_alive():

@@ -40,6 +40,14 @@ class CacheGenDeserializer(Deserializer):
         return out
 
     @_lmcache_nvtx_annotate
+    def decode_into(self, containers: Sequence, dst: KvView, dst_tok: Sequence[int]) -> None:
+        """Engine fast path: decode containers straight into a destination view at the given token offsets."""
+        self.codec.decode(list(containers), dst, list(dst_tok))
+
+    def out_dtype(self) -> torch.dtype:
+        return self._out_dtype()
+
+    @_lmcache_nvtx_annotate
     def from_bytes_batch(self, containers: Sequence, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Decode consecutive chunks into ONE blob (the retrieve-side torch.cat disappears):
         container j lands at token offset sum(ntokens[:j])."""

@@ -48,6 +48,12 @@ class CacheGenSerializer(Serializer):
     def kv_to_bytes_batch(self, kv: Sequence, chunk_size: Optional[int] = None, tok_begin: int = 0,
                           n_tokens: Optional[int] = None) -> List[bytes]:
         """Same, straight from the engine's tuple of per-layer (K, V) tensors (no blob is ever built)."""
-        view = KvView.from_tuple(kv, self.fmt)
+        return self.view_to_bytes_batch(KvView.from_tuple(kv, self.fmt), chunk_size, tok_begin, n_tokens)
+
+    @_lmcache_nvtx_annotate
+    def view_to_bytes_batch(self, view: KvView, chunk_size: Optional[int] = None, tok_begin: int = 0,
+                            n_tokens: Optional[int] = None) -> List[bytes]:
+        """Engine fast path: encode tokens [tok_begin, tok_begin + n_tokens) of a KvView, one container per chunk,
+        with one launch sequence and one device->host copy pass."""
         n = view.ntokens - tok_begin if n_tokens is None else n_tokens
         return self.codec.encode_to_host(view, tok_begin, n, chunk_size or self.chunk_size)
