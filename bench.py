@@ -236,11 +236,9 @@ def main():
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = world * raw_bytes / (ms_step * 1e-3) / 1e9
+    from lmcache_b200.dist_util import aggregate_gbps, max_over_ranks
+    ms_step = max_over_ranks(ms_total, dev) / args.steps          # device time, max over ranks
+    value = aggregate_gbps(raw_bytes, ms_step, world)              # weak scaling: every rank codes its own block
 
     # ---- per-kernel live timing (events around each launch inside the library), separate passes
     lib.b200kv_profile_enable(1)
@@ -403,11 +401,8 @@ def run_e2e(args, codec, kv, out, out_view, staging, stride, dev, world, barrier
     ev1.record(cur)
     barrier()
     wall = (time.perf_counter() - t0) / steps
-    t = torch.tensor([wall], device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sec = float(t.item())
+    from lmcache_b200.dist_util import max_over_ranks
+    sec = max_over_ranks(wall, dev)
     host_raw.close(); host_cont.close(); host_digest.close()
     return {"value": round(world * raw_bytes / sec / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": round(sec * 1e3, 2), "steps": steps,

@@ -177,10 +177,22 @@ def test_retrieve_device(backend, src_device, autorelease):
         assert k.device == torch.device("cuda:0") and v.device == torch.device("cuda:0")
 
 
+@pytest.fixture(params=["fast", "generic"])
+def engine_path(request, monkeypatch):
+    """Run engine tests through both code paths: the B200-native fast path (backend consumes the caller's KV tensors /
+    fills one blob) and the generic per-chunk plugin path every third-party backend would take."""
+    if request.param == "generic":
+        from lmcache_b200.storage_backend.local_backend import LMCLocalBackend
+        from lmcache_b200.storage_backend.remote_backend import LMCRemoteBackend
+        monkeypatch.setattr(LMCLocalBackend, "supports_kv_view", lambda self: False)
+        monkeypatch.setattr(LMCRemoteBackend, "supports_kv_view", lambda self: False)
+    return request.param
+
+
 @pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
 @pytest.mark.parametrize("backend", ["cuda", "cpu"])
 @pytest.mark.parametrize("blocking", [True, False])
-def test_same_retrieve_store(fmt, backend, blocking, autorelease):
+def test_same_retrieve_store(fmt, backend, blocking, autorelease, engine_path):
     from lmcache_b200.cache_engine import LMCacheEngine
     from lmcache_b200.config import LMCacheEngineConfig
     device = "cpu" if backend == "cpu" else "cuda"
@@ -199,7 +211,7 @@ def test_same_retrieve_store(fmt, backend, blocking, autorelease):
 @pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
 @pytest.mark.parametrize("chunk_size", [128, 256])
 @pytest.mark.parametrize("backend", ["cuda", "cpu"])
-def test_retrieve_prefix(fmt, chunk_size, backend, autorelease):
+def test_retrieve_prefix(fmt, chunk_size, backend, autorelease, engine_path):
     from lmcache_b200.cache_engine import LMCacheEngine
     from lmcache_b200.config import LMCacheEngineConfig
     num_tokens, new_num_tokens = 2000, 1000
@@ -217,7 +229,7 @@ def test_retrieve_prefix(fmt, chunk_size, backend, autorelease):
 
 @pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
 @pytest.mark.parametrize("chunk_size", [128, 256])
-def test_mixed_retrieve(fmt, chunk_size, autorelease):
+def test_mixed_retrieve(fmt, chunk_size, autorelease, engine_path):
     from lmcache_b200.cache_engine import LMCacheEngine
     from lmcache_b200.config import LMCacheEngineConfig
     num_tokens, new_num_tokens = 2000, 1000
@@ -244,7 +256,7 @@ def test_mixed_retrieve(fmt, chunk_size, autorelease):
     check_kv_cache_equal(retrieved, final_kv, num_tokens + new_num_tokens, fmt)
 
 
-def test_golden_engine_semantics(autorelease):
+def test_golden_engine_semantics(autorelease, engine_path):
     """The scalars recorded from the reference engine in this container (tests/golden/golden_engine.json)."""
     from lmcache_b200.cache_engine import LMCacheEngine
     from lmcache_b200.config import LMCacheEngineConfig
@@ -341,7 +353,7 @@ def test_remote_torch_serde_lossless(fmt, lmserver, autorelease):
 
 @pytest.mark.parametrize("fmt", ["vllm", "huggingface"])
 @pytest.mark.parametrize("pipelined", [False, True])
-def test_remote_cachegen_matches_reference_chain(fmt, pipelined, lmserver, autorelease):
+def test_remote_cachegen_matches_reference_chain(fmt, pipelined, lmserver, autorelease, engine_path):
     import ref_torch
     from lmcache_b200.cache_engine import LMCacheEngine
     from lmcache_b200.config import LMCacheEngineConfig
@@ -351,6 +363,7 @@ def test_remote_cachegen_matches_reference_chain(fmt, pipelined, lmserver, autor
     kv = generate_kv_cache(T, fmt, "cuda", 32, 8, 128)
     cfg = LMCacheEngineConfig(256, None, lmserver, "cachegen", pipelined, False)
     engine = autorelease(LMCacheEngine(cfg, dumb_metadata(fmt, model)))
+    assert engine._fast_path() == (engine_path == "fast")
     engine.store(tokens, kv, blocking=not pipelined)
     if pipelined:
         engine.engine_.put_queue.join()     # non-blocking store: wait for the put worker to drain
@@ -365,3 +378,15 @@ def test_remote_cachegen_matches_reference_chain(fmt, pipelined, lmserver, autor
     got = torch.stack([torch.stack(p) for p in r])
     assert got.shape == want.shape and got.dtype == want.dtype
     assert torch.equal(got.view(torch.int16), want.contiguous().view(torch.int16))
+    # a second, fresh engine ("another vLLM instance") sharing the server: full hit, and a suffix-mask retrieve
+    engine2 = autorelease(LMCacheEngine(cfg, dumb_metadata(fmt, model)))
+    r2, m2 = engine2.retrieve(tokens)
+    assert torch.sum(m2) == T
+    assert torch.equal(torch.stack([torch.stack(p) for p in r2]).view(torch.int16), want.contiguous().view(torch.int16))
+    mask = torch.ones(T, dtype=torch.bool)
+    mask[:300] = False
+    r3, m3 = engine2.retrieve(tokens, mask)
+    assert torch.sum(m3) == T - 300 and int(m3.nonzero()[0]) == 300
+    tdim = 2 if fmt == "vllm" else 3
+    assert torch.equal(torch.stack([torch.stack(p) for p in r3]).view(torch.int16),
+                       want.narrow(tdim, 300, T - 300).contiguous().view(torch.int16))
