@@ -73,6 +73,12 @@ def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321):
 
     from oracle import oracle as O
     O.build()
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    cores = O.set_threads(ncpu)          # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
+    torch.set_num_threads(ncpu)
     kv = synth_kv_torch(n_chunks * chunk, "cpu", seed)
     bits = kv.view(torch.int16).numpy().view(np.uint16).reshape(L, 2, n_chunks * chunk, C)
     kb, vb = O.make_bins(MODEL)
@@ -88,7 +94,7 @@ def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321):
             times.append(dt)
     sec = sum(times) / len(times)
     raw = n_chunks * chunk * L * 2 * C * 2
-    return raw / sec / 1e9, sec, os.cpu_count()
+    return raw / sec / 1e9, sec, cores
 
 
 def run_reference_arm(args):

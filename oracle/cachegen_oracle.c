@@ -23,6 +23,7 @@
  * (cachegen_encoder.py:57-59); an FMA flips symbols.
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -419,6 +420,12 @@ int oracle_sha256_chain(const uint8_t* tokens, int64_t n_tokens, int elem_size, 
         plen = 64;
     }
     return n;
+}
+
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs of bench.py ask for all host threads explicitly. */
+int oracle_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
 }
 
 int oracle_version(void) { return 1; }

@@ -55,8 +55,15 @@ def lib() -> ctypes.CDLL:
         L.oracle_dequantize.restype = None
         L.oracle_sha256_chain.argtypes = [vp, i64, i32, i32, vp]
         L.oracle_sha256_chain.restype = i32
+        L.oracle_set_threads.argtypes = [i32]
+        L.oracle_set_threads.restype = i32
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> int:
+    """Use n OpenMP threads (torchrun forces OMP_NUM_THREADS=1); returns the thread count in effect."""
+    return int(lib().oracle_set_threads(int(n)))
 
 
 def _p(a: np.ndarray) -> ctypes.c_void_p:
