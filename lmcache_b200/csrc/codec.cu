@@ -35,7 +35,6 @@ struct EncParams {
     int32_t L, H, D, C, dtype;
     int32_t n_chunks, chunk_tokens, last_chunk_tokens, tpp;   // tpp = tiles per plane
     int32_t tiles_full, tempw;                                 // tiles per full chunk; words per temp row
-    int32_t chunk0, launch_chunks;                             // this launch covers chunks [chunk0, chunk0 + launch_chunks)
     uint8_t* out;
     int64_t out_stride;
     uint64_t* sizes_out;
@@ -60,7 +59,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_
     const int64_t nrows = (int64_t)2 * P.L * total_tokens;
     if (warp >= nrows) return;
     const int nl = (int)(warp / total_tokens);
-    const int64_t T = warp % total_tokens + (int64_t)P.chunk0 * P.chunk_tokens;     // token index within the call
+    const int64_t T = warp % total_tokens;
     const uint16_t* row = P.pt.p[nl] + (P.tok_begin + T) * P.sT;
     uint32_t m = 0;
     if (VEC) {
@@ -117,15 +116,13 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 
 // tile -> (chunk j, group g, plane nl, channel tile ct); tiles of a chunk are ordered (g, nl, ct), which is the
 // order of the streams in the container payload.  Returns false for tiles beyond the (ragged) last chunk.
-struct TileId { int j, g, nl, ct, t, tok0, gt, tile_in_chunk; int64_t gtile; };
+struct TileId { int j, g, nl, ct, t, tok0, gt, tile_in_chunk; };
 __device__ __forceinline__ bool decode_tile(const EncParams& P, uint32_t tile, TileId* id) {
     const uint32_t per_group = 2u * P.L * P.tpp;
-    const uint32_t jl = tile / (uint32_t)P.tiles_full;
-    const uint32_t rem = tile - jl * (uint32_t)P.tiles_full;
-    const uint32_t j = jl + (uint32_t)P.chunk0;
+    const uint32_t j = tile / (uint32_t)P.tiles_full;
+    const uint32_t rem = tile - j * (uint32_t)P.tiles_full;
     id->j = (int)j;
     id->tile_in_chunk = (int)rem;
-    id->gtile = (int64_t)j * P.tiles_full + rem;             // tile index within the whole call (temp rows, tile_tot)
     id->t = chunk_tokens_of(P, (int)j);
     id->g = (int)(rem / per_group);
     if (id->g * kGroup >= id->t) return false;
@@ -178,7 +175,7 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0) * P.sT +
                           (int64_t)h * P.sH + (active ? c - h * P.D : 0);
     const int64_t s1 = P.sT;
-    uint32_t* trow = P.temp + (id.gtile * CT + tid) * P.tempw;
+    uint32_t* trow = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
     const uint32_t cap = (uint32_t)P.tempw;
     uint32_t len = 0u;
 
@@ -324,7 +321,7 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     }
     uint32_t tile_total;
     (void)block_excl_scan(len, s_warp, &tile_total);
-    if (tid == 0) P.tile_tot[id.gtile] = tile_total;
+    if (tid == 0) P.tile_tot[(int64_t)j * P.tiles_full + id.tile_in_chunk] = tile_total;
 }
 
 // ------------------------------------------------------------------------------------------ cdf (chunks > 256 tokens)
@@ -336,9 +333,8 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
     const int tid = threadIdx.x;
     const int NL = 2 * P.L;
     const uint32_t per_chunk = (uint32_t)NL * P.tpp;
-    const uint32_t jl = blockIdx.x / per_chunk;
-    const uint32_t rem = blockIdx.x - jl * per_chunk;
-    const uint32_t j = jl + (uint32_t)P.chunk0;
+    const uint32_t j = blockIdx.x / per_chunk;
+    const uint32_t rem = blockIdx.x - j * per_chunk;
     const int nl = (int)(rem / P.tpp);
     const int ct = (int)(rem - (uint32_t)nl * P.tpp);
     const int t = chunk_tokens_of(P, (int)j);
@@ -392,7 +388,7 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
 __global__ void __launch_bounds__(1024) enc_scan_kernel(EncParams P) {
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_carry;
-    const int j = P.chunk0 + blockIdx.x;
+    const int j = blockIdx.x;
     const int t = chunk_tokens_of(P, j);
     const int ntiles = ((t + kGroup - 1) / kGroup) * 2 * P.L * P.tpp;
     uint32_t* tb = P.tile_tot + (int64_t)j * P.tiles_full;
@@ -447,7 +443,7 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
     const uint32_t len = c < P.C ? min((uint32_t)lengths[c], (uint32_t)P.tempw * 4u) : 0u;
     uint32_t tile_total;
     const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
-    const uint64_t base = P.tile_tot[id.gtile];
+    const uint64_t base = P.tile_tot[(int64_t)id.j * P.tiles_full + id.tile_in_chunk];
     const int64_t room = P.out_stride - lo.off_payload;
     if ((int64_t)(base + tile_total) > room) {          // never write past the slot the caller gave us
         if (tid == 0) atomicOr(&P.err[id.j], 4u);
@@ -457,7 +453,7 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
     if (len) {
         uint8_t* d = stage + phase + my_off;
-        const uint32_t* srcw = P.temp + (id.gtile * CT + tid) * P.tempw;
+        const uint32_t* srcw = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
         const uint32_t nw = (len + 3u) >> 2;
         for (uint32_t w = 0; w < nw; ++w) {
             const uint32_t v = __ldg(srcw + w);
@@ -682,49 +678,30 @@ int make_plane_table(const b200kv_kv_desc* kv, const float* key_bins, const floa
 
 static int tiles_per_plane(int C) { return (C + CT - 1) / CT; }
 
-// ---- optional per-kernel timing (bench.py's roofline leg): events around every launch of the last encode / decode
-// call, summed per slot (a call may launch a slot several times, once per chunk group)
+// ---- optional per-kernel timing (bench.py's roofline leg): events around each launch of the last call
 enum { kProfAbsmax = 0, kProfCdf, kProfEncode, kProfFinalize, kProfTileSum, kProfTileScan, kProfDecode, kProfCount };
-constexpr int kProfMaxPairs = 64;
 static bool g_prof_on = false;
-static cudaEvent_t g_prof_ev[kProfCount][kProfMaxPairs][2];
-static int g_prof_n[kProfCount];
+static cudaEvent_t g_prof_ev[kProfCount][2];
+static bool g_prof_have[kProfCount];
 static bool g_prof_init = false;
 
-static void prof_reset(int first, int last) {
-    for (int i = first; i <= last; ++i) g_prof_n[i] = 0;
-}
-
 struct ProfScope {
-    int slot, idx;
+    int slot;
     cudaStream_t stream;
-    ProfScope(int slot_, cudaStream_t s) : slot(slot_), idx(-1), stream(s) {
+    ProfScope(int slot_, cudaStream_t s) : slot(slot_), stream(s) {
         if (!g_prof_on) return;
         if (!g_prof_init) {
-            for (int i = 0; i < kProfCount; ++i)
-                for (int k = 0; k < kProfMaxPairs; ++k) { cudaEventCreate(&g_prof_ev[i][k][0]); cudaEventCreate(&g_prof_ev[i][k][1]); }
+            for (int i = 0; i < kProfCount; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); }
             g_prof_init = true;
         }
-        if (g_prof_n[slot] >= kProfMaxPairs) return;
-        idx = g_prof_n[slot]++;
-        cudaEventRecord(g_prof_ev[slot][idx][0], stream);
+        cudaEventRecord(g_prof_ev[slot][0], stream);
     }
     ~ProfScope() {
-        if (idx >= 0) cudaEventRecord(g_prof_ev[slot][idx][1], stream);
+        if (!g_prof_on) return;
+        cudaEventRecord(g_prof_ev[slot][1], stream);
+        g_prof_have[slot] = true;
     }
 };
-
-// library-owned side stream per device: absmax of chunk group k+1 and compaction of group k-1 run on it while the
-// issue-bound encode kernel of group k owns the caller's stream
-static cudaStream_t g_side_stream[64];
-static int side_stream(cudaStream_t* out) {
-    int dev = 0;
-    B2_CHECK_CUDA(cudaGetDevice(&dev));
-    B2_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
-    if (!g_side_stream[dev]) B2_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side_stream[dev], cudaStreamNonBlocking));
-    *out = g_side_stream[dev];
-    return 0;
-}
 
 static size_t enc_ws_layout(int64_t n_tiles_alloc, int n_chunks, int tempw, size_t* off_tot, size_t* off_totals,
                             size_t* off_err, size_t* off_temp) {
@@ -808,8 +785,6 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     const int64_t n_tiles = (int64_t)n_chunks * tiles_full;     // tiles beyond a ragged last chunk exit at once
     const bool fused = chunk_tokens <= kGroup;
     P.tiles_full = (int32_t)tiles_full;
-    P.chunk0 = 0;
-    P.launch_chunks = n_chunks;
     P.tempw = fused ? TEMPW_FUSED : TEMPW_SPLIT;
     size_t off_tot, off_totals, off_err, off_temp;
     const size_t need = enc_ws_layout(n_tiles, n_chunks, P.tempw, &off_tot, &off_totals, &off_err, &off_temp);
@@ -821,128 +796,53 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     P.err = reinterpret_cast<unsigned int*>(ws + off_err);
     P.temp = reinterpret_cast<uint32_t*>(ws + off_temp);
     B2_CHECK_CUDA(cudaMemsetAsync(ws, 0, off_temp, stream));     // counters only; temp rows need no init
-    if (g_prof_on) prof_reset(kProfAbsmax, kProfFinalize);
 
-    bool vec = (kv->D % 8 == 0) && (kv->sT % 8 == 0) && (kv->sH % 8 == 0);
-    for (int nl = 0; nl < 2 * P.L && vec; ++nl) vec = (reinterpret_cast<uintptr_t>(P.pt.p[nl]) & 15) == 0;
+    // 1) per-(plane, token) absmax -> maxes sections
+    const int64_t total_tokens = (int64_t)(n_chunks - 1) * chunk_tokens + last_chunk_tokens;
+    {
+        bool vec = (kv->D % 8 == 0) && (kv->sT % 8 == 0) && (kv->sH % 8 == 0);
+        for (int nl = 0; nl < 2 * P.L && vec; ++nl) vec = (reinterpret_cast<uintptr_t>(P.pt.p[nl]) & 15) == 0;
+        const int64_t rows = 2 * (int64_t)P.L * total_tokens;
+        const int64_t blocks = (rows + 7) / 8;
+        B2_REQUIRE(blocks < (1ll << 31), "too many rows in one call");
+        ProfScope prof(kProfAbsmax, stream);
+        if (vec) absmax_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        else absmax_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        B2_CHECK_CUDA(cudaGetLastError());
+    }
+    // 2) encode (streams -> temp rows, lengths, tile totals)
     const size_t smem_fused = (size_t)(((CT * SYMW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + 4) * 4;
     const size_t smem_split = (size_t)(((CT * PAIRW + 3) & ~3) + kGroup + 4) * 4;
     const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
-    const size_t smem_compact = (size_t)CT * P.tempw * 4 + 32;
+#define B2_LAUNCH_ENC(FUSED, DT, SMEM)                                                                     \
+    do {                                                                                                   \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<FUSED, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)(SMEM)));                                                  \
+        encode_kernel<FUSED, DT><<<(unsigned)n_tiles, CT, (SMEM), stream>>>(P);                            \
+    } while (0)
     if (fused) {
-        if (P.dtype == B200KV_DT_BF16)
-            B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
-        else
-            B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
+        ProfScope prof(kProfEncode, stream);
+        if (P.dtype == B200KV_DT_BF16) B2_LAUNCH_ENC(true, 0, smem_fused); else B2_LAUNCH_ENC(true, 1, smem_fused);
     } else {
-        if (P.dtype == B200KV_DT_BF16)
-            B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_split));
-        else
-            B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_split));
-    }
-    B2_CHECK_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)((size_t)CT * TEMPW_SPLIT * 4 + 32)));
-
-    // Chunk groups.  Per group: absmax -> encode -> scan + compact.  With several groups the memory-bound absmax of
-    // group k+1 and the latency-bound compaction of group k-1 run on a side stream underneath the issue-bound encode
-    // kernel of group k; with one group everything stays on the caller's stream.
-    const int n_groups = n_chunks >= 8 ? 4 : 1;
-    const int per = (n_chunks + n_groups - 1) / n_groups;
-    cudaStream_t side = stream;
-    cudaEvent_t ev_entry = nullptr, ev_abs[4] = {nullptr, nullptr, nullptr, nullptr}, ev_enc[4] = {nullptr, nullptr, nullptr, nullptr},
-                ev_side_done = nullptr;
-    auto new_event = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
-    if (n_groups > 1) {
-        if (int rc = side_stream(&side)) return rc;
-        B2_CHECK_CUDA(new_event(&ev_entry));
-        B2_CHECK_CUDA(cudaEventRecord(ev_entry, stream));            // everything queued on the caller's stream so far
-        B2_CHECK_CUDA(cudaStreamWaitEvent(side, ev_entry, 0));       // (KV producers, the memset above) comes first
-        for (int k = 0; k < n_groups; ++k) { B2_CHECK_CUDA(new_event(&ev_abs[k])); B2_CHECK_CUDA(new_event(&ev_enc[k])); }
-        B2_CHECK_CUDA(new_event(&ev_side_done));
-    }
-    auto group_params = [&](int k) {
-        EncParams Q = P;
-        Q.chunk0 = k * per;
-        Q.launch_chunks = (k == n_groups - 1) ? n_chunks - Q.chunk0 : per;
-        return Q;
-    };
-    auto launch_absmax = [&](int k, cudaStream_t st) -> int {
-        EncParams Q = group_params(k);
-        const int64_t ntok = (int64_t)(Q.launch_chunks - 1) * chunk_tokens +
-                             ((Q.chunk0 + Q.launch_chunks == n_chunks) ? last_chunk_tokens : chunk_tokens);
-        const int64_t blocks = (2 * (int64_t)P.L * ntok + 7) / 8;
-        B2_REQUIRE(blocks < (1ll << 31), "too many rows in one call");
-        ProfScope prof(kProfAbsmax, st);
-        if (vec) absmax_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(Q, ntok);
-        else absmax_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(Q, ntok);
-        B2_CHECK_CUDA(cudaGetLastError());
-        return 0;
-    };
-    auto launch_encode = [&](int k, cudaStream_t st) -> int {
-        EncParams Q = group_params(k);
-        const unsigned tiles = (unsigned)((int64_t)Q.launch_chunks * tiles_full);
-        if (!fused) {
-            ProfScope prof(kProfCdf, st);
-            const unsigned cdf_blocks = (unsigned)((int64_t)Q.launch_chunks * per_group);
-            if (P.dtype == B200KV_DT_BF16) cdf_kernel<0><<<cdf_blocks, CT, smem_cdf, st>>>(Q);
-            else cdf_kernel<1><<<cdf_blocks, CT, smem_cdf, st>>>(Q);
-            B2_CHECK_CUDA(cudaGetLastError());
-        }
-        ProfScope prof(kProfEncode, st);
-        if (fused) {
-            if (P.dtype == B200KV_DT_BF16) encode_kernel<true, 0><<<tiles, CT, smem_fused, st>>>(Q);
-            else encode_kernel<true, 1><<<tiles, CT, smem_fused, st>>>(Q);
-        } else {
-            if (P.dtype == B200KV_DT_BF16) encode_kernel<false, 0><<<tiles, CT, smem_split, st>>>(Q);
-            else encode_kernel<false, 1><<<tiles, CT, smem_split, st>>>(Q);
+        const unsigned cdf_blocks = (unsigned)((int64_t)n_chunks * per_group);
+        {
+            ProfScope prof(kProfCdf, stream);
+            if (P.dtype == B200KV_DT_BF16) cdf_kernel<0><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+            else cdf_kernel<1><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
         }
         B2_CHECK_CUDA(cudaGetLastError());
-        return 0;
-    };
-    auto launch_compact = [&](int k, cudaStream_t st) -> int {
-        EncParams Q = group_params(k);
-        ProfScope prof(kProfFinalize, st);
-        enc_scan_kernel<<<(unsigned)Q.launch_chunks, 1024, 0, st>>>(Q);
-        compact_kernel<<<(unsigned)((int64_t)Q.launch_chunks * tiles_full), CT, smem_compact, st>>>(Q);
-        B2_CHECK_CUDA(cudaGetLastError());
-        return 0;
-    };
-
-    int rc = 0;
-    if (n_groups == 1) {
-        if ((rc = launch_absmax(0, stream)) || (rc = launch_encode(0, stream)) || (rc = launch_compact(0, stream))) return rc;
-    } else {
-        // side stream: abs(0) abs(1) | per k: [wait enc(k)] compact(k), abs(k+2)
-        for (int k = 0; k < 2 && k < n_groups && !rc; ++k) {
-            rc = launch_absmax(k, side);
-            if (!rc && cudaEventRecord(ev_abs[k], side) != cudaSuccess) rc = -1;
-        }
-        for (int k = 0; k < n_groups && !rc; ++k) {
-            if (cudaStreamWaitEvent(stream, ev_abs[k], 0) != cudaSuccess) { rc = -1; break; }
-            if ((rc = launch_encode(k, stream))) break;
-            if (cudaEventRecord(ev_enc[k], stream) != cudaSuccess) { rc = -1; break; }
-            if (cudaStreamWaitEvent(side, ev_enc[k], 0) != cudaSuccess) { rc = -1; break; }
-            if ((rc = launch_compact(k, side))) break;
-            if (k + 2 < n_groups) {
-                if ((rc = launch_absmax(k + 2, side))) break;
-                if (cudaEventRecord(ev_abs[k + 2], side) != cudaSuccess) { rc = -1; break; }
-            }
-        }
-        if (!rc) {
-            if (cudaEventRecord(ev_side_done, side) != cudaSuccess || cudaStreamWaitEvent(stream, ev_side_done, 0) != cudaSuccess) rc = -1;
-        }
-        // events may be destroyed while pending: the runtime releases them once they complete
-        cudaEventDestroy(ev_entry);
-        for (int k = 0; k < n_groups; ++k) { cudaEventDestroy(ev_abs[k]); cudaEventDestroy(ev_enc[k]); }
-        cudaEventDestroy(ev_side_done);
-        if (rc) {
-            if (rc == -1) set_error(std::string("stream/event choreography failed: ") + cudaGetErrorString(cudaGetLastError()));
-            return rc;
-        }
+        ProfScope prof(kProfEncode, stream);
+        if (P.dtype == B200KV_DT_BF16) B2_LAUNCH_ENC(false, 0, smem_split); else B2_LAUNCH_ENC(false, 1, smem_split);
     }
-    // headers + sizes (after every group's compaction)
+#undef B2_LAUNCH_ENC
+    B2_CHECK_CUDA(cudaGetLastError());
+    // 3) compaction (collect_bytes) + headers + sizes
     {
         ProfScope prof(kProfFinalize, stream);
+        B2_CHECK_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((size_t)CT * TEMPW_SPLIT * 4 + 32)));
+        enc_scan_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(P);
+        compact_kernel<<<(unsigned)n_tiles, CT, (size_t)CT * P.tempw * 4 + 32, stream>>>(P);
         finalize_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P);
     }
     B2_CHECK_CUDA(cudaGetLastError());
@@ -994,7 +894,6 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     P.chunks = reinterpret_cast<const DecChunk*>(ws);
     P.tile_base = reinterpret_cast<unsigned long long*>(ws + off_tb);
 
-    if (g_prof_on) prof_reset(kProfTileSum, kProfDecode);
     dim3 gsum((unsigned)((tiles_max + 3) / 4), (unsigned)n_chunks);
     {
         ProfScope prof(kProfTileSum, stream);
@@ -1023,7 +922,7 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
 
 int b200kv_profile_enable(int32_t on) {
     g_prof_on = on != 0;
-    prof_reset(0, kProfCount - 1);
+    for (int i = 0; i < kProfCount; ++i) g_prof_have[i] = false;
     return 0;
 }
 
@@ -1031,15 +930,10 @@ int b200kv_profile_last(float* ms, int32_t n) {
     B2_REQUIRE(ms != nullptr && n >= kProfCount, "need room for 7 floats");
     for (int i = 0; i < kProfCount; ++i) {
         ms[i] = -1.0f;
-        if (!g_prof_on || g_prof_n[i] == 0) continue;
-        float sum = 0.0f;
-        for (int k = 0; k < g_prof_n[i]; ++k) {
-            float t = 0.0f;
-            B2_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[i][k][1]));
-            B2_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_ev[i][k][0], g_prof_ev[i][k][1]));
-            sum += t;
+        if (g_prof_on && g_prof_have[i]) {
+            B2_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[i][1]));
+            B2_CHECK_CUDA(cudaEventElapsedTime(&ms[i], g_prof_ev[i][0], g_prof_ev[i][1]));
         }
-        ms[i] = sum;
     }
     return kProfCount;
 }
