@@ -474,6 +474,14 @@ B2_HD void dec_init2(DecState2& st, Src& src, uint32_t skip) {
     dec_refill2(st, src);
 }
 
+B2_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
 // Approximate count ~ floor((value - low) * 2^16 / span), within +-1 of the reference's exact
 //   count = ((value - low + 1) * 2^16 - 1) / span      (one reciprocal instead of a 64-bit division).
 B2_HD uint32_t dec_count_approx(uint32_t off, uint32_t rng) {
@@ -488,42 +496,70 @@ B2_HD uint32_t dec_count_approx(uint32_t off, uint32_t rng) {
     return c < 65535u ? c : 65535u;
 }
 
-// Decode one symbol.  cdf(i) returns the uint16 CDF entry i of this stream.  NSTEPS = 5 searches symbols
-// 0..31, NSTEPS = 4 symbols 0..15 (planes with <= 16 bins only ever code symbols 0..14).
+// The decoder reads the stream's CDF as a table of 33 words  e[i] = cdf[i] << 16  (e[32] = 0xFFFFFFFF):
+//   * compares in the count domain become  e[i] <= (count << 16 | 0xFFFF);
+//   * (span * cdf[i]) >> 16  ==  umulhi(span, e[i])  for span < 2^32: one IMAD.HI, no 64-bit arithmetic.
+B2_HD uint32_t dec_table_entry(uint32_t i, uint32_t cdf16) { return i < 32u ? (cdf16 << 16) : 0xFFFFFFFFu; }
+
+// exact interval products for symbol s from the pre-shifted table, valid for every state (incl. span = 2^32)
+B2_HD void dec_exact_products(const uint32_t* e, uint32_t r, uint32_t s, uint32_t* plo, uint32_t* phi) {
+    const uint32_t c0 = e[s] >> 16;
+    const uint32_t c1 = s >= 31u ? 0x10000u : (e[s + 1u] >> 16);
+    *plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
+    *phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);          // 2^32 wraps to 0 (the reference's uint32 maths)
+}
+
+#if defined(__CUDACC__)
+// one lower-bound step on a 32-bit shared-memory address: a += 4*STEP iff table[a/4 + STEP] <= key
+template <int STEP>
+__device__ __forceinline__ void dec_search_steps(uint32_t& a, uint32_t key) {
+    uint32_t ev;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(ev) : "r"(a), "n"(STEP * 4));
+    a = ev <= key ? a + STEP * 4 : a;
+    if constexpr (STEP > 1) dec_search_steps<STEP / 2>(a, key);
+}
+#endif
+
+// Decode one symbol.  NSTEPS = 5 searches symbols 0..31, NSTEPS = 4 symbols 0..15 (planes with <= 16 bins only ever
+// code symbols 0..14).
 //  1. s~ = max{ s : cdf[s] <= count~ } by a fixed-depth, branch-free lower-bound search in the count domain
-//     (compares only -- the 64-bit multiplies of a product-domain search made the FMA pipe the bottleneck).
-//  2. the exact interval products plo = (span*cdf[s])>>16, phi = (span*cdf[s+1])>>16 are needed for the state
-//     update anyway; the symbol is exact iff plo <= off < phi, which is the reference's decision rule
-//     (cdf[s] <= count  <=>  (span*cdf[s])>>16 <= off).  count~ is within +-1 of count, so at most one step of
-//     correction is ever needed; the loops below make the result exact whatever the approximation did.
-template <int NSTEPS, class Src, class CdfFn>
-B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, CdfFn cdf, bool last) {
+//     (per step: one LDS off a running pointer, one compare, one predicated add).
+//  2. plo = umulhi(span, e[s]), phi = umulhi(span, e[s+1]) -- needed for the state update anyway.  The symbol is exact
+//     iff plo <= off < phi (the reference's rule cdf[s] <= count  <=>  (span*cdf[s])>>16 <= off), checked in wrapping
+//     uint32 arithmetic as (off - plo) < (phi - plo).
+//  3. count~ is within +-1 of count, so the check almost never fails; when it does (or when span = 2^32, where umulhi
+//     cannot be used, or s = 31 whose upper bound is 2^16) a slow path recomputes the products with 64-bit arithmetic
+//     and walks to the exact symbol.  The result is exact whatever the approximation did.
+template <int NSTEPS, class Src>
+B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last) {
     const uint32_t r = st.rng;
     const uint32_t off = st.value - st.low;
-    const uint32_t cnt = dec_count_approx(off, r);
+    const uint32_t cnt16 = (dec_count_approx(off, r) << 16) | 0xFFFFu;
     constexpr uint32_t kTop = (1u << NSTEPS) - 1u;               // highest searchable symbol
-    uint32_t s = 0u;
+    const uint32_t span = r + 1u;                                // 0 when the interval is the whole 32-bit range
+#if defined(__CUDA_ARCH__)
+    // the table lives in shared memory: walk it with a 32-bit shared address so that every step is
+    // LDS [a + imm] / ISETP / select, and the symbol index falls out of the address
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(e);
+    uint32_t a = a0;
+    dec_search_steps<(1 << (NSTEPS - 1))>(a, cnt16);
+    uint32_t s = (a - a0) >> 2;
+    uint32_t e0, e1;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e0) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(e1) : "r"(a));
+#else
+    const uint32_t* a = e;
 #pragma unroll
-    for (int step = 1 << (NSTEPS - 1); step > 0; step >>= 1) {
-        const uint32_t cand = s + (uint32_t)step;
-        s = cdf(cand) <= cnt ? cand : s;
-    }
-    uint32_t c0 = cdf(s);
-    uint32_t plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
-    uint32_t c1 = s == 31u ? 0x10000u : cdf(s + 1u);
-    uint32_t phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);          // 2^32 wraps to 0 (uint32 maths)
-    // exact iff plo <= off < phi.  In wrapping uint32 arithmetic that is (off - plo) < (phi - plo), which also
-    // covers phi == 2^32 (wrapped to 0).  count~ is within +-1 of count, so this almost never fails; the loops
-    // make the result exact whatever the approximation did.
-    if ((uint32_t)(off - plo) >= (uint32_t)(phi - plo)) {
-        while (off < plo && s > 0u) {
-            --s; phi = plo; c0 = cdf(s);
-            plo = (uint32_t)(((uint64_t)r * c0 + c0) >> 16);
-        }
-        while (s < kTop && (uint32_t)(off - plo) >= (uint32_t)(phi - plo)) {
-            ++s; plo = phi; c1 = s == 31u ? 0x10000u : cdf(s + 1u);
-            phi = (uint32_t)(((uint64_t)r * c1 + c1) >> 16);
-        }
+    for (int step = 1 << (NSTEPS - 1); step > 0; step >>= 1) a = a[step] <= cnt16 ? a + step : a;
+    uint32_t s = (uint32_t)(a - e);
+    const uint32_t e0 = a[0], e1 = a[1];
+#endif
+    uint32_t plo = umulhi32(span, e0);
+    uint32_t phi = umulhi32(span, e1);
+    if ((uint32_t)(off - plo) >= (uint32_t)(phi - plo) || (NSTEPS == 5 && s == 31u)) {
+        dec_exact_products(e, r, s, &plo, &phi);
+        while (off < plo && s > 0u) { --s; dec_exact_products(e, r, s, &plo, &phi); }
+        while (s < kTop && (uint32_t)(off - plo) >= (uint32_t)(phi - plo)) { ++s; dec_exact_products(e, r, s, &plo, &phi); }
     }
     if (last) return s;
     uint32_t low = st.low + plo;

@@ -584,22 +584,23 @@ __device__ __forceinline__ uint16_t out_half(float v, int dt) {
     return dt ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
-// per-thread decode loop: one stream, gt symbols, straight to the destination layout
+// per-thread decode loop: one stream, gt symbols, straight to the destination layout.
+// dst is addressed as base + 32-bit element offset (one IMAD.WIDE per store instead of 64-bit pointer bookkeeping).
 template <int OUT_DT, int NSTEPS>
-__device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint16_t* crow, const float* lut,
-                                              const float* mx, uint16_t* dst, int64_t sT, int gt) {
+__device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint32_t* erow, const float* lut,
+                                              const float* mx, uint16_t* dst, uint32_t sT, int gt) {
     const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(my_bytes) & 3u);
     WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip), 0u};
     src.prime();
     DecState2 st;
     dec_init2(st, src, skip);
-    auto cdf = [&](uint32_t k) -> uint32_t { return crow[k]; };
-    for (int i = 0; i < gt - 1; ++i, dst += sT) {
-        const uint32_t s = dec_symbol2<NSTEPS>(st, src, cdf, false);
-        *dst = out_half(dequant_value(lut[s], mx[i]), OUT_DT);
+    uint32_t o = 0u;
+    for (int i = 0; i < gt - 1; ++i, o += sT) {
+        const uint32_t s = dec_symbol2<NSTEPS>(st, src, erow, false);
+        dst[o] = out_half(dequant_value(lut[s], mx[i]), OUT_DT);
     }
-    const uint32_t s = dec_symbol2<NSTEPS>(st, src, cdf, true);
-    *dst = out_half(dequant_value(lut[s], mx[gt - 1]), OUT_DT);
+    const uint32_t s = dec_symbol2<NSTEPS>(st, src, erow, true);
+    dst[o] = out_half(dequant_value(lut[s], mx[gt - 1]), OUT_DT);
 }
 
 // One tile = CT streams of one (chunk, group, plane).  Only the CDF rows (66 B per stream, contiguous in the
@@ -609,8 +610,8 @@ __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uin
 template <int OUT_DT>
 __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint16_t* cdf_s = reinterpret_cast<uint16_t*>(smem);                             // CT * kLp (rows of 33, contiguous)
-    float* mx = reinterpret_cast<float*>(smem + ((CT * kLp * 2 + 15) / 16) * 4);     // kGroup
+    uint32_t* tab = smem;                                                            // CT * 33 words: cdf << 16 (rows of 33, odd)
+    float* mx = reinterpret_cast<float*>(smem + CT * kLp);                           // kGroup
     float* lut = mx + kGroup;                                                        // 32
     __shared__ uint32_t s_warp[CT / 32];
 
@@ -640,7 +641,10 @@ __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
 
     // stage CDF rows (one contiguous run of ncols * 33 halfwords), row maxima, LUT
     const uint16_t* cdf_src = reinterpret_cast<const uint16_t*>(dc.base + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
-    for (int e = tid; e < ncols * kLp; e += CT) cdf_s[e] = __ldg(cdf_src + e);
+    for (int e = tid; e < ncols * kLp; e += CT) {
+        const uint32_t i = (uint32_t)e % (uint32_t)kLp;
+        tab[e] = dec_table_entry(i, __ldg(cdf_src + e));
+    }
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(dc.base + lo.off_maxes) + (int64_t)nl * dc.t + tok0;
     for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
     const float cq = P.pt.maxq[nl];
@@ -648,11 +652,12 @@ __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     __syncthreads();
 
     if (!active) return;
-    const uint16_t* crow = cdf_s + tid * kLp;
+    const uint32_t* erow = tab + tid * kLp;
     const int h = c / P.D;
     uint16_t* dst = const_cast<uint16_t*>(P.pt.p[nl]) + (dc.dst_tok + tok0) * P.sT + (int64_t)h * P.sH + (c - h * P.D);
-    if (cq <= 7.0f) decode_stream<OUT_DT, 4>(my_bytes, crow, lut, mx, dst, P.sT, gt);   // <= 16 bins: symbols 0..14
-    else decode_stream<OUT_DT, 5>(my_bytes, crow, lut, mx, dst, P.sT, gt);
+    // a group spans <= 256 token rows: 255 * sT must fit the 32-bit element offset used inside the loop
+    if (cq <= 7.0f) decode_stream<OUT_DT, 4>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt);   // <= 16 bins: symbols 0..14
+    else decode_stream<OUT_DT, 5>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -859,6 +864,7 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     if (int rc = make_plane_table(dst, key_bins, value_bins, &P.pt)) return rc;
     B2_REQUIRE(containers && offsets && ntokens && dst_tok && n_chunks > 0, "bad chunk arrays");
     B2_REQUIRE(max_dtype == B200KV_DT_BF16 || max_dtype == B200KV_DT_FP16, "bad max_dtype");
+    B2_REQUIRE(dst->sT > 0 && dst->sT < (1ll << 23), "destination token stride out of range");
     P.sT = dst->sT; P.sH = dst->sH;
     P.L = dst->L; P.H = dst->H; P.D = dst->D; P.C = dst->H * dst->D;
     P.out_dtype = dst->dtype; P.max_dtype = max_dtype; P.n_chunks = n_chunks;
@@ -906,7 +912,7 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     }
     B2_CHECK_CUDA(cudaGetLastError());
 
-    const size_t smem = (size_t)((CT * kLp * 2 + 15) / 16) * 16 + (size_t)(kGroup + 32) * 4;
+    const size_t smem = (size_t)(CT * kLp + kGroup + 32) * 4;
     dim3 grid((unsigned)tiles_max, (unsigned)n_chunks);
     ProfScope prof(kProfDecode, stream);
     if (P.out_dtype == B200KV_DT_BF16) {

@@ -91,9 +91,10 @@ struct WordSrc {   // aligned big-endian word reader over a byte buffer that may
 void sim_decode_stream2(const uint16_t* cdf, const uint8_t* in, int64_t n, int g, uint8_t* out, int64_t out_stride, int skip, int nsteps) {
     WordSrc src{nullptr, -(int64_t)skip, in, n};
     DecState2 st; dec_init2(st, src, (uint32_t)skip);
-    auto c = [&](uint32_t k) { return (uint32_t)cdf[k]; };
+    uint32_t e[kLp];
+    for (uint32_t i = 0; i < (uint32_t)kLp; ++i) e[i] = dec_table_entry(i, cdf[i]);
     for (int i = 0; i < g; ++i)
-        out[i * out_stride] = (uint8_t)(nsteps == 4 ? dec_symbol2<4>(st, src, c, i == g - 1) : dec_symbol2<5>(st, src, c, i == g - 1));
+        out[i * out_stride] = (uint8_t)(nsteps == 4 ? dec_symbol2<4>(st, src, e, i == g - 1) : dec_symbol2<5>(st, src, e, i == g - 1));
 }
 
 void sim_cdf(const uint32_t* counts, int t, uint16_t* cdf) {
