@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Secondary measurements on the B200 box (not the headline bench): SHA-256 prefix-hash kernel, the host mover
+(LMCLocalBackend cpu tier through the engine, BASELINE configs[2] shape scaled to fit a quick run), and the
+engine-level store/retrieve through the serde plugin boundary (lm:// + cachegen).  Prints one JSON object.
+
+    python profiles/extra_bench.py > gpurun_out/extra.json
+"""
+import hashlib
+import json
+import os
+import socket
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import __graft_entry__ as ge  # noqa: E402
+
+ge.build_cuda()
+from lmcache_b200.cache_engine import LMCacheEngine, sha256_prefix_chain  # noqa: E402
+from lmcache_b200.config import LMCacheEngineConfig, LMCacheEngineMetadata  # noqa: E402
+
+torch.cuda.set_device(0)
+out = {}
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), sum(ts) / len(ts)
+
+
+# ---------------- hash chain (a1)
+g = torch.Generator().manual_seed(5)
+for label, n, seqs in [("8192_tokens_1_chain", 8192, None), ("65536_tokens_1_chain", 65536, None),
+                       ("16x4096_tokens_16_chains", 16 * 4096, [i * 4096 for i in range(17)])]:
+    toks = torch.randint(0, 32000, (n,), generator=g, dtype=torch.int64)
+    dtoks = toks.cuda()
+    best, mean = timeit(lambda: sha256_prefix_chain(dtoks, 256, seqs))
+
+    def cpu_ref():
+        offs = seqs or [0, n]
+        outp = []
+        for i in range(len(offs) - 1):
+            pre = ""
+            for a in range(offs[i], offs[i + 1], 256):
+                pre = hashlib.sha256(pre.encode("ascii") + toks[a:min(a + 256, offs[i + 1])].numpy().tobytes()).hexdigest()
+                outp.append(pre)
+        return outp
+    t0 = time.perf_counter()
+    want = cpu_ref()
+    tcpu = time.perf_counter() - t0
+    assert sha256_prefix_chain(dtoks, 256, seqs) == want
+    out["hash_" + label] = {"gpu_us_best": round(best * 1e6, 1), "gpu_us_mean": round(mean * 1e6, 1),
+                            "cpu_hashlib_us": round(tcpu * 1e6, 1), "chunks": len(want)}
+
+# ---------------- host mover through the engine (local cpu tier), 8192 tokens x 32L x 32H x 128D = 4 GiB
+L, H, D, T = 32, 32, 128, 8192
+kv = tuple((torch.randn(T, H, D, device="cuda").to(torch.bfloat16), torch.randn(T, H, D, device="cuda").to(torch.bfloat16))
+           for _ in range(L))
+raw = 2 * L * T * H * D * 2
+toks = torch.randint(0, 32000, (T,), generator=g, dtype=torch.int64).cuda()
+for backend in ("cpu", "cuda"):
+    meta = LMCacheEngineMetadata("test_model", 1, 0, "vllm", "bfloat16")
+    eng = LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=256, backend=backend), meta)
+    t0 = time.perf_counter()
+    eng.store(toks, kv, skip_existing=False)
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t0
+    st_best, _ = timeit(lambda: eng.store(toks, kv, skip_existing=False), n=3, warm=1)
+    rt_best, _ = timeit(lambda: eng.retrieve(toks), n=3, warm=1)
+    r, m = eng.retrieve(toks)
+    assert int(m.sum()) == T and torch.equal(r[3][1], kv[3][1])
+    out[f"engine_local_{backend}"] = {"store_GBps": round(raw / st_best / 1e9, 1), "retrieve_GBps": round(raw / rt_best / 1e9, 1),
+                                      "first_store_s": round(t_first, 3), "raw_bytes": raw}
+    eng.close()
+    del eng
+
+# ---------------- engine over lm:// + cachegen (serde plugin boundary), 2048 tokens
+s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+env = dict(os.environ, PYTHONPATH=ROOT)
+srv = subprocess.Popen([sys.executable, "-m", "lmcache_b200.server", "127.0.0.1", str(port)], env=env)
+for _ in range(100):
+    try:
+        socket.create_connection(("127.0.0.1", port), timeout=0.2).close(); break
+    except OSError:
+        time.sleep(0.1)
+try:
+    T2 = 2048
+    kv2 = tuple((k[:T2].contiguous(), v[:T2].contiguous()) for k, v in kv)
+    toks2 = toks[:T2]
+    raw2 = 2 * L * T2 * H * D * 2
+    for fast in (True, False):
+        meta = LMCacheEngineMetadata("lmsys/longchat-7b-16k", 1, 0 if fast else 1, "vllm", "bfloat16")
+        eng = LMCacheEngine(LMCacheEngineConfig(256, None, f"lm://127.0.0.1:{port}", "cachegen", False, False), meta)
+        if not fast:
+            eng.engine_.supports_kv_view = lambda: False
+        st_best, _ = timeit(lambda: eng.store(toks2, kv2, skip_existing=False), n=3, warm=1)
+        rt_best, _ = timeit(lambda: eng.retrieve(toks2), n=3, warm=1)
+        out["engine_lm_cachegen_" + ("fast_path" if fast else "generic_path")] = {
+            "store_GBps": round(raw2 / st_best / 1e9, 2), "retrieve_GBps": round(raw2 / rt_best / 1e9, 2), "raw_bytes": raw2,
+            "note": "python socket + in-process python server dominate; GB/s of raw KV"}
+        eng.close()
+finally:
+    srv.terminate(); srv.wait()
+
+print(json.dumps(out, indent=1))
