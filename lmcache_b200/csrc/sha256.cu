@@ -2,15 +2,19 @@
 //
 // Replaces LMCacheEngine._hash / _chunk_tokens / _prefix_hash (lmcache/cache_engine.py:58-96):
 //     h_i = sha256( ascii_hex(h_{i-1}) || bytes(tokens[i*cs:(i+1)*cs]) ).hexdigest(),   h_{-1} = ""
-// which costs the reference one tokens.cpu() device->host sync per chunk.  Here the whole chain runs in one
-// launch on the caller's stream and only the 32-byte digests cross to the host (one copy, no per-chunk sync).
+// which costs the reference one tokens.cpu() device->host sync per chunk.  Here the whole chain runs on the
+// caller's stream and only the 32-byte digests cross to the host (one copy, no per-chunk sync).
 //
-// A SHA-256 chain is serial by construction (Merkle-Damgard: every 64-byte block needs the previous
-// state, and chunk i's first block is the previous digest), so one chain is latency-bound.  The kernel
-// therefore splits the work per chain across one warp: all 32 lanes expand message schedules
-// (W[16..63] + K, the state-independent ~45% of the work) for 32 blocks at a time into shared memory, then
-// lane 0 runs the 64 serial rounds per block.  Independent sequences (n_seq chains: batched requests,
-// RAG chunk mixes) run on different warps/SMs concurrently.
+// A SHA-256 chain is serial by construction (Merkle-Damgard: every 64-byte block needs the previous state, and
+// chunk i's first block is the previous digest), so one chain is latency-bound: 64 rounds x ~4 dependent
+// operations per block.  The work is therefore split by what depends on the chain:
+//   1. sha256_expand_kernel -- every block that holds only token bytes / padding is state-independent.  The hex
+//      prefix is exactly 64 bytes = one block, so the token bytes of a chunk always start on a block boundary and
+//      all blocks after the prefix block qualify.  One thread per block expands the message schedule and stores
+//      (W + K)[0..63] (256 B per block) in a scratch buffer.  Fully parallel, ~45 % of the total work.
+//   2. sha256_chain_kernel -- one thread per sequence walks its chunks: expands the one prefix block itself, then
+//      streams the precomputed (W + K) blocks through 64 fully unrolled rounds with register renaming.
+//      Independent sequences (batched requests, RAG chunk mixes) occupy the other lanes / warps.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,115 +34,151 @@ __constant__ uint32_t kK[64] = {
 
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
-// Message byte `i` of the chunk message = prefix (64 hex chars, or empty for the first chunk) || token bytes ||
-// 0x80 || zeros || 64-bit big-endian bit length.
-struct ChunkMsg {
-    const uint8_t* tok;     // token bytes of this chunk
-    uint32_t ntok_bytes;
-    uint32_t plen;          // 0 or 64
-    const uint8_t* prefix;  // 64 hex chars in shared memory
-    uint32_t total;         // plen + ntok_bytes
-    uint32_t nblocks;       // padded block count
-    __device__ __forceinline__ uint32_t byte_at(uint32_t i) const {
-        if (i < plen) return prefix[i];
-        if (i < total) return tok[i - plen];
-        if (i == total) return 0x80u;
-        const uint32_t end = nblocks * 64u;
-        if (i >= end - 8u) {
-            const uint64_t bits = (uint64_t)total * 8ull;
-            return (uint32_t)(bits >> (8u * (end - 1u - i))) & 0xffu;
-        }
-        return 0u;
-    }
+struct ShaParams {
+    const uint8_t* tokens;
+    const int64_t* seq_offsets;   // device, n_seq + 1 token indices
+    const int64_t* seq_block0;    // device, n_seq + 1: first scratch block of each sequence
+    const int64_t* seq_chunk0;    // device, n_seq + 1: first digest slot of each sequence
+    uint32_t* scratch;            // [n_blocks][64]  (W + K)
+    uint8_t* digests;
+    int64_t n_blocks;
+    int32_t n_seq, elem_size, chunk_size;
+    int32_t blocks_per_full_chunk;   // ceil((chunk_size * elem_size + 9) / 64): tail blocks (tokens + padding) of a full chunk
 };
 
-constexpr int kWarpsPerCta = 4;
+// expand 16 message words into (W + K)[64]
+__device__ __forceinline__ void expand_store(uint32_t (&w)[64], uint32_t* dst) {
+#pragma unroll
+    for (int i = 16; i < 64; ++i) {
+        const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        const uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        uint4 v = make_uint4(w[i] + kK[i], w[i + 1] + kK[i + 1], w[i + 2] + kK[i + 2], w[i + 3] + kK[i + 3]);
+        *reinterpret_cast<uint4*>(dst + i) = v;
+    }
+}
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) sha256_chain_kernel(const uint8_t* tokens, int elem_size,
-                                                                         const int64_t* seq_offsets, int n_seq,
-                                                                         int chunk_size, uint8_t* digests) {
-    __shared__ uint32_t s_wk[kWarpsPerCta][64][32];   // (W + K)[round][block] for 32 blocks per warp (32 KiB total)
-    __shared__ uint8_t s_prefix[kWarpsPerCta][64];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int seq = blockIdx.x * kWarpsPerCta + wid;
-    if (seq >= n_seq) return;
-    const int64_t t0 = seq_offsets[seq], t1 = seq_offsets[seq + 1];
-    // digest slot of this sequence = sum of chunk counts of the previous ones
-    int64_t slot = 0;
-    for (int s = 0; s < seq; ++s) slot += (seq_offsets[s + 1] - seq_offsets[s] + chunk_size - 1) / chunk_size;
-    uint32_t (*wk)[32] = s_wk[wid];
-    uint8_t* prefix = s_prefix[wid];
+// One thread per state-independent block.  Block b of sequence s: chunk ci = b / bpc (all chunks of a sequence but
+// the last are full), k = block index inside the chunk's token+padding tail.
+__global__ void __launch_bounds__(128) sha256_expand_kernel(ShaParams P) {
+    const int64_t gb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gb >= P.n_blocks) return;
+    // find the sequence (few sequences: linear / binary search over seq_block0)
+    int lo = 0, hi = P.n_seq;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (P.seq_block0[mid] <= gb) lo = mid; else hi = mid;
+    }
+    const int s = lo;
+    const int64_t b = gb - P.seq_block0[s];
+    const int64_t t0 = P.seq_offsets[s], t1 = P.seq_offsets[s + 1];
+    const int64_t ci = b / P.blocks_per_full_chunk;
+    const int64_t k = b - ci * P.blocks_per_full_chunk;
+    const int64_t tb = t0 + ci * P.chunk_size;
+    const int64_t cnt = (t1 - tb) < P.chunk_size ? (t1 - tb) : P.chunk_size;
+    const uint32_t nbytes = (uint32_t)(cnt * P.elem_size);            // token bytes of this chunk
+    const uint32_t plen = ci == 0 ? 0u : 64u;
+    const uint64_t bits = (uint64_t)(plen + nbytes) * 8ull;
+    const uint32_t ntail = (nbytes + 9u + 63u) / 64u;                  // blocks in this chunk's tail
+    if (cnt <= 0 || (uint32_t)k >= ntail) return;                      // slack slot of a ragged last chunk
+    const uint8_t* tok = P.tokens + tb * P.elem_size;
+    const bool word_ok = (reinterpret_cast<uintptr_t>(tok) & 3u) == 0u;
+    uint32_t w[64];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t o = (uint32_t)k * 64u + 4u * i;                 // byte offset inside the tail
+        if (word_ok && o + 4u <= nbytes) {
+            w[i] = __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(tok + o)), 0u, 0x0123);
+        } else {
+            uint32_t v = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t p = o + q;
+                uint32_t byte = 0u;
+                if (p < nbytes) byte = tok[p];
+                else if (p == nbytes) byte = 0x80u;
+                else if (p >= ntail * 64u - 8u) byte = (uint32_t)(bits >> (8u * (ntail * 64u - 1u - p))) & 0xffu;
+                v = (v << 8) | byte;
+            }
+            w[i] = v;
+        }
+    }
+    expand_store(w, P.scratch + gb * 64);
+}
 
+// 64 rounds over precomputed (W + K); state in registers, variables renamed instead of rotated
+#define B2_SHA_ROUND(a, b, c, d, e, f, g, h, wk)                                              \
+    {                                                                                          \
+        const uint32_t t1_ = (h) + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + (((e) & (f)) ^ (~(e) & (g))) + (wk); \
+        const uint32_t t2_ = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + (((a) & (b)) ^ ((a) & (c)) ^ ((b) & (c))); \
+        (d) += t1_;                                                                            \
+        (h) = t1_ + t2_;                                                                       \
+    }
+
+__device__ __forceinline__ void compress_wk(uint32_t (&st)[8], const uint4* wk4) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const uint4 x = wk4[i], y = wk4[i + 1];
+        B2_SHA_ROUND(a, b, c, d, e, f, g, h, x.x)
+        B2_SHA_ROUND(h, a, b, c, d, e, f, g, x.y)
+        B2_SHA_ROUND(g, h, a, b, c, d, e, f, x.z)
+        B2_SHA_ROUND(f, g, h, a, b, c, d, e, x.w)
+        B2_SHA_ROUND(e, f, g, h, a, b, c, d, y.x)
+        B2_SHA_ROUND(d, e, f, g, h, a, b, c, y.y)
+        B2_SHA_ROUND(c, d, e, f, g, h, a, b, y.z)
+        B2_SHA_ROUND(b, c, d, e, f, g, h, a, y.w)
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// One thread per sequence (chain).
+__global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_seq) return;
+    const int64_t t0 = P.seq_offsets[s], t1 = P.seq_offsets[s + 1];
+    int64_t slot = P.seq_chunk0[s];
+    int64_t gb = P.seq_block0[s];
+    uint32_t dig[8];
     bool first = true;
-    for (int64_t tb = t0; tb < t1; tb += chunk_size, ++slot) {
-        const int64_t cnt = (t1 - tb) < chunk_size ? (t1 - tb) : chunk_size;
-        ChunkMsg msg;
-        msg.tok = tokens + tb * elem_size;
-        msg.ntok_bytes = (uint32_t)(cnt * elem_size);
-        msg.plen = first ? 0u : 64u;
-        msg.prefix = prefix;
-        msg.total = msg.plen + msg.ntok_bytes;
-        msg.nblocks = (msg.total + 9u + 63u) / 64u;
-        const bool word_ok = (reinterpret_cast<uintptr_t>(msg.tok) & 3u) == 0u;
-
+    for (int64_t tb = t0; tb < t1; tb += P.chunk_size, ++slot) {
+        const int64_t cnt = (t1 - tb) < P.chunk_size ? (t1 - tb) : P.chunk_size;
+        const uint32_t ntail = ((uint32_t)(cnt * P.elem_size) + 9u + 63u) / 64u;
         uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
                           0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
-        for (uint32_t b0 = 0; b0 < msg.nblocks; b0 += 32u) {
-            const uint32_t nb = min(32u, msg.nblocks - b0);
-            // ---- parallel: lane L expands block b0 + L
-            if ((uint32_t)lane < nb) {
-                uint32_t w[64];
-                const uint32_t base = (b0 + lane) * 64u;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t o = base + 4u * i;
-                    if (word_ok && o >= msg.plen && o + 4u <= msg.total)   // whole word inside the token bytes
-                        w[i] = __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(msg.tok + (o - msg.plen))), 0u, 0x0123);
-                    else
-                        w[i] = (msg.byte_at(o) << 24) | (msg.byte_at(o + 1) << 16) | (msg.byte_at(o + 2) << 8) |
-                               msg.byte_at(o + 3);
-                }
-#pragma unroll
-                for (int i = 16; i < 64; ++i) {
-                    const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
-                    const uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
-                    w[i] = w[i - 16] + s0 + w[i - 7] + s1;
-                }
-#pragma unroll
-                for (int i = 0; i < 64; ++i) wk[i][lane] = w[i] + kK[i];   // conflict-free: lanes -> banks
-            }
-            __syncwarp();
-            // ---- serial: lane 0 runs the compression rounds
-            if (lane == 0) {
-                for (uint32_t b = 0; b < nb; ++b) {
-                    uint32_t a = st[0], bb = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-#pragma unroll 16
-                    for (int i = 0; i < 64; ++i) {
-                        const uint32_t t1_ = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + wk[i][b];
-                        const uint32_t t2_ = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & bb) ^ (a & c) ^ (bb & c));
-                        h = g; g = f; f = e; e = d + t1_; d = c; c = bb; bb = a; a = t1_ + t2_;
-                    }
-                    st[0] += a; st[1] += bb; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
-                }
-            }
-            __syncwarp();
-        }
-        // ---- publish digest; hex of it is the next chunk's prefix
-        if (lane == 0) {
-            uint8_t* out = digests + slot * 32;
+        if (!first) {
+            // prefix block: the 64 hex characters of the previous digest, 8 per state word
+            uint32_t w[64];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t byte = (st[i] >> (24 - 8 * k)) & 0xffu;
-                    out[4 * i + k] = (uint8_t)byte;
-                    const uint32_t hi = byte >> 4, lo = byte & 15u;
-                    prefix[8 * i + 2 * k] = (uint8_t)(hi < 10u ? '0' + hi : 'a' + hi - 10u);
-                    prefix[8 * i + 2 * k + 1] = (uint8_t)(lo < 10u ? '0' + lo : 'a' + lo - 10u);
+                for (int hw = 0; hw < 2; ++hw) {
+                    uint32_t v = 0u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t nib = (dig[i] >> (28 - 4 * (4 * hw + q))) & 15u;
+                        v = (v << 8) | (nib < 10u ? 0x30u + nib : 0x57u + nib);      // '0'..'9', 'a'..'f'
+                    }
+                    w[2 * i + hw] = v;
                 }
             }
+            __align__(16) uint32_t wk[64];
+            expand_store(w, wk);
+            compress_wk(st, reinterpret_cast<const uint4*>(wk));
         }
-        __syncwarp();
+        const uint4* wk4 = reinterpret_cast<const uint4*>(P.scratch + gb * 64);
+        for (uint32_t k = 0; k < ntail; ++k, wk4 += 16) compress_wk(st, wk4);
+        gb += P.blocks_per_full_chunk;      // scratch blocks are laid out at a fixed stride per chunk
+        uint8_t* out = P.digests + slot * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dig[i] = st[i];
+            out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
+            out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+        }
         first = false;
     }
 }
@@ -154,24 +194,59 @@ extern "C" int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const 
     B2_REQUIRE(elem_size == 1 || elem_size == 2 || elem_size == 4 || elem_size == 8, "elem_size must be 1/2/4/8");
     B2_REQUIRE(chunk_size > 0, "chunk_size must be positive");
     B2_REQUIRE((int64_t)chunk_size * elem_size < (1ll << 28), "chunk too large");
+    const int64_t bpc = ((int64_t)chunk_size * elem_size + 9 + 63) / 64;
+    // host tables: per sequence, first scratch block and first digest slot (chunks at a fixed block stride)
+    int64_t* tab = static_cast<int64_t*>(malloc(sizeof(int64_t) * 3 * (size_t)(n_seq + 1)));
+    B2_REQUIRE(tab != nullptr, "out of host memory");
+    int64_t* h_off = tab;
+    int64_t* h_blk = tab + (n_seq + 1);
+    int64_t* h_chk = tab + 2 * (n_seq + 1);
     int64_t nchunks = 0;
-    for (int s = 0; s < n_seq; ++s) {
-        B2_REQUIRE(seq_offsets[s + 1] >= seq_offsets[s], "seq_offsets must be non-decreasing");
-        nchunks += (seq_offsets[s + 1] - seq_offsets[s] + chunk_size - 1) / chunk_size;
+    for (int s = 0; s <= n_seq; ++s) {
+        h_off[s] = seq_offsets[s];
+        h_blk[s] = nchunks * bpc;
+        h_chk[s] = nchunks;
+        if (s < n_seq) {
+            if (seq_offsets[s + 1] < seq_offsets[s]) {
+                free(tab);
+                B2_REQUIRE(false, "seq_offsets must be non-decreasing");
+            }
+            nchunks += (seq_offsets[s + 1] - seq_offsets[s] + chunk_size - 1) / chunk_size;
+        }
     }
-    if (nchunks == 0) return 0;
-    B2_REQUIRE(tokens != nullptr && digests != nullptr, "NULL tokens / digests");
-    // sequence table -> device (small; staged by the driver before return)
-    int64_t* d_off = nullptr;
-    B2_CHECK_CUDA(cudaMallocAsync(&d_off, sizeof(int64_t) * (size_t)(n_seq + 1), stream));
-    cudaError_t e = cudaMemcpyAsync(d_off, seq_offsets, sizeof(int64_t) * (size_t)(n_seq + 1), cudaMemcpyHostToDevice, stream);
+    if (nchunks == 0) { free(tab); return 0; }
+    if (tokens == nullptr || digests == nullptr) {
+        free(tab);
+        B2_REQUIRE(false, "NULL tokens / digests");
+    }
+    const int64_t n_blocks = nchunks * bpc;
+    const size_t tab_bytes = sizeof(int64_t) * 3 * (size_t)(n_seq + 1);
+    const size_t tab_pad = (tab_bytes + 255) & ~(size_t)255;
+    uint8_t* dmem = nullptr;
+    cudaError_t e = cudaMallocAsync(&dmem, tab_pad + (size_t)n_blocks * 256, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dmem, tab, tab_bytes, cudaMemcpyHostToDevice, stream);   // staged before return
+    free(tab);
+    if (e != cudaSuccess) {
+        if (dmem) cudaFreeAsync(dmem, stream);
+        B2_CHECK_CUDA(e);
+    }
+    ShaParams P;
+    P.tokens = static_cast<const uint8_t*>(tokens);
+    P.seq_offsets = reinterpret_cast<const int64_t*>(dmem);
+    P.seq_block0 = P.seq_offsets + (n_seq + 1);
+    P.seq_chunk0 = P.seq_offsets + 2 * (n_seq + 1);
+    P.scratch = reinterpret_cast<uint32_t*>(dmem + tab_pad);
+    P.digests = static_cast<uint8_t*>(digests);
+    P.n_blocks = n_blocks;
+    P.n_seq = n_seq; P.elem_size = elem_size; P.chunk_size = chunk_size;
+    P.blocks_per_full_chunk = (int32_t)bpc;
+    sha256_expand_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, stream>>>(P);
+    e = cudaGetLastError();
     if (e == cudaSuccess) {
-        const int blocks = (n_seq + kWarpsPerCta - 1) / kWarpsPerCta;
-        sha256_chain_kernel<<<blocks, 32 * kWarpsPerCta, 0, stream>>>(static_cast<const uint8_t*>(tokens), elem_size, d_off,
-                                                                        n_seq, chunk_size, static_cast<uint8_t*>(digests));
+        sha256_chain_kernel<<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
         e = cudaGetLastError();
     }
-    cudaFreeAsync(d_off, stream);
+    cudaFreeAsync(dmem, stream);
     B2_CHECK_CUDA(e);
     return 0;
 }

@@ -64,6 +64,10 @@ for label, n, seqs in [("8192_tokens_1_chain", 8192, None), ("65536_tokens_1_cha
     out["hash_" + label] = {"gpu_us_best": round(best * 1e6, 1), "gpu_us_mean": round(mean * 1e6, 1),
                             "cpu_hashlib_us": round(tcpu * 1e6, 1), "chunks": len(want)}
 
+if os.environ.get('EXTRA_ONLY') == 'hash':
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
+
 # ---------------- host mover through the engine (local cpu tier), 8192 tokens x 32L x 32H x 128D = 4 GiB
 L, H, D, T = 32, 32, 128, 8192
 kv = tuple((torch.randn(T, H, D, device="cuda").to(torch.bfloat16), torch.randn(T, H, D, device="cuda").to(torch.bfloat16))
