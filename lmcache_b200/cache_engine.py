@@ -12,6 +12,7 @@ miss ends the match, everything after the first missing chunk is (re)stored (:18
 from __future__ import annotations
 
 import ctypes
+import threading
 import time
 from typing import Dict, Iterable, List, Optional, Tuple, Union
 
@@ -25,6 +26,18 @@ from lmcache_b200.storage_backend import CreateStorageBackend
 from lmcache_b200.utils import CacheEngineKey, KVCache, _lmcache_nvtx_annotate
 
 logger = init_logger(__name__)
+
+
+_digest_lock = threading.Lock()
+_digest_buf: Optional[PinnedBuffer] = None
+
+
+def _digest_buffer(nbytes: int) -> PinnedBuffer:
+    """Process-wide page-locked landing area for digests (cudaHostAlloc costs far more than a hash launch)."""
+    global _digest_buf
+    if _digest_buf is None or _digest_buf.nbytes < nbytes:
+        _digest_buf = PinnedBuffer(max(1 << 16, 2 * nbytes))
+    return _digest_buf
 
 
 def sha256_prefix_chain(tokens: torch.Tensor, chunk_size: int, seq_offsets: Optional[List[int]] = None) -> List[str]:
@@ -43,8 +56,8 @@ def sha256_prefix_chain(tokens: torch.Tensor, chunk_size: int, seq_offsets: Opti
         return []
     dev_tokens = tokens if tokens.is_cuda else tokens.to("cuda", non_blocking=False)
     dev_tokens = dev_tokens.contiguous()
-    out = PinnedBuffer(32 * nchunks)   # the kernel writes digests straight into mapped host memory
-    try:
+    with _digest_lock:
+        out = _digest_buffer(32 * nchunks)   # the kernel writes digests straight into mapped host memory
         with torch.cuda.device(dev_tokens.device):
             sp = torch.cuda.current_stream().cuda_stream
             N.check(N.lib().b200kv_sha256_chain(ctypes.c_void_p(dev_tokens.data_ptr()), dev_tokens.element_size(),
@@ -52,8 +65,6 @@ def sha256_prefix_chain(tokens: torch.Tensor, chunk_size: int, seq_offsets: Opti
                                                 sp), "sha256_chain")
             N.check(N.lib().b200kv_stream_sync(sp), "stream_sync")
         raw = bytes(out.view(0, 32 * nchunks))
-    finally:
-        out.close()
     return [raw[32 * i: 32 * i + 32].hex() for i in range(nchunks)]
 
 

@@ -118,11 +118,12 @@ __global__ void __launch_bounds__(128) sha256_expand_kernel(ShaParams P) {
         (h) = t1_ + t2_;                                                                       \
     }
 
-__device__ __forceinline__ void compress_wk(uint32_t (&st)[8], const uint4* wk4) {
+// 64 rounds over a block's (W + K) held in registers
+__device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q)[16]) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-        const uint4 x = wk4[i], y = wk4[i + 1];
+        const uint4 x = q[i], y = q[i + 1];
         B2_SHA_ROUND(a, b, c, d, e, f, g, h, x.x)
         B2_SHA_ROUND(h, a, b, c, d, e, f, g, x.y)
         B2_SHA_ROUND(g, h, a, b, c, d, e, f, x.z)
@@ -133,6 +134,11 @@ __device__ __forceinline__ void compress_wk(uint32_t (&st)[8], const uint4* wk4)
         B2_SHA_ROUND(b, c, d, e, f, g, h, a, y.w)
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+__device__ __forceinline__ void load_block(uint4 (&q)[16], const uint4* p) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = __ldg(p + i);
 }
 
 // One thread per sequence (chain).
@@ -165,12 +171,30 @@ __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
                     w[2 * i + hw] = v;
                 }
             }
-            __align__(16) uint32_t wk[64];
-            expand_store(w, wk);
-            compress_wk(st, reinterpret_cast<const uint4*>(wk));
+            // expand in registers: (W + K) as 16 uint4
+#pragma unroll
+            for (int i = 16; i < 64; ++i) {
+                const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+                const uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+                w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+            }
+            uint4 q[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                q[i] = make_uint4(w[4 * i] + kK[4 * i], w[4 * i + 1] + kK[4 * i + 1], w[4 * i + 2] + kK[4 * i + 2],
+                                  w[4 * i + 3] + kK[4 * i + 3]);
+            compress_regs(st, q);
         }
+        // stream the precomputed blocks: the next block's 16 loads are in flight while this block's rounds run
         const uint4* wk4 = reinterpret_cast<const uint4*>(P.scratch + gb * 64);
-        for (uint32_t k = 0; k < ntail; ++k, wk4 += 16) compress_wk(st, wk4);
+        uint4 cur[16], nxt[16];
+        load_block(cur, wk4);
+        for (uint32_t k = 0; k < ntail; ++k) {
+            if (k + 1 < ntail) load_block(nxt, wk4 + 16 * (k + 1));
+            compress_regs(st, cur);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+        }
         gb += P.blocks_per_full_chunk;      // scratch blocks are laid out at a fixed stride per chunk
         uint8_t* out = P.digests + slot * 32;
 #pragma unroll
