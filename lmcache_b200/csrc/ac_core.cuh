@@ -436,27 +436,26 @@ B2_HD uint32_t dec_symbol(DecState& st, Src& src, CdfFn cdf, bool last) {
 }
 
 // ---- production decoder step: same symbols as dec_symbol, organised for SIMT execution.
+//  * state is (low, rng, off) with off = value - low.  Both E1/E2 and E3 renormalisation steps then act on off as a
+//    plain left shift that pulls in stream bits (the E3 "value -= 2^30" cancels against low's cleared MSB), so the
+//    decoder never materialises `value` and needs no MSB flip.
+//  * stream bits come from a two-word window (cur : nxt) with a bit position pos < 32: the next k <= 18 bits are
+//    funnel_l(t, x, k) with t = funnel_l(nxt, cur, pos); a refill is `cur = nxt; nxt = next word; pos -= 32`.
 //  * symbol search: fixed-depth and branch-free (warp lanes never diverge; a data-dependent walk was measured
 //    2x slower because a warp pays for its longest lane), see dec_symbol2.
-//  * renormalisation consumes n + m <= 18 bits per symbol from a 64-bit left-aligned reservoir that is kept
-//    at >= 32 valid bits by one predicated aligned-word refill per symbol.
 struct DecState2 {
-    uint32_t low, rng, value;
-    uint64_t res;      // left-aligned bit reservoir
-    uint32_t rb;       // valid bits in res (>= 32 at the start of every symbol)
+    uint32_t low, rng, off;
+    uint32_t cur, nxt;     // stream words (big-endian bit order), nxt is the look-ahead
+    uint32_t pos;          // bits of `cur` already consumed (< 32 between symbols)
 };
 
 // Word source concept: uint32_t next_be() -- next 4 stream bytes as a big-endian word (aligned load + swap).
 template <class Src>
 B2_HD void dec_refill2(DecState2& st, Src& src) {
-#if defined(__CUDA_ARCH__)
-    // warp-uniform guard: at low bit rates most symbol steps need no refill in any lane, and predicated-off
-    // instructions still cost issue slots
-    if (!__any_sync(__activemask(), st.rb < 32u)) return;
-#endif
-    if (st.rb < 32u) {
-        st.res |= (uint64_t)src.next_be() << (32u - st.rb);
-        st.rb += 32u;
+    if (st.pos >= 32u) {
+        st.cur = st.nxt;
+        st.nxt = src.next_be();
+        st.pos -= 32u;
     }
 }
 
@@ -464,13 +463,11 @@ B2_HD void dec_refill2(DecState2& st, Src& src) {
 template <class Src>
 B2_HD void dec_init2(DecState2& st, Src& src, uint32_t skip) {
     st.low = 0u; st.rng = 0xFFFFFFFFu;
-    const uint32_t w0 = src.next_be();
-    st.res = (uint64_t)w0 << (32u + 8u * skip);
-    st.rb = 32u - 8u * skip;
-    dec_refill2(st, src);
-    st.value = (uint32_t)(st.res >> 32);
-    st.res <<= 32;
-    st.rb -= 32u;
+    st.cur = src.next_be();
+    st.nxt = src.next_be();
+    st.pos = 8u * skip;
+    st.off = funnel_l(st.nxt, st.cur, st.pos);        // first 32 stream bits (value, low = 0)
+    st.pos += 32u;
     dec_refill2(st, src);
 }
 
@@ -533,7 +530,7 @@ __device__ __forceinline__ void dec_search_steps(uint32_t& a, uint32_t key) {
 template <int NSTEPS, class Src>
 B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last) {
     const uint32_t r = st.rng;
-    const uint32_t off = st.value - st.low;
+    const uint32_t off = st.off;
     const uint32_t cnt16 = (dec_count_approx(off, r) << 16) | 0xFFFFu;
     constexpr uint32_t kTop = (1u << NSTEPS) - 1u;               // highest searchable symbol
     const uint32_t span = r + 1u;                                // 0 when the interval is the whole 32-bit range
@@ -569,9 +566,9 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
     high = shl_fill1(high, n);
     const uint32_t m = e3_count(low, high);
     const uint32_t k = n + m;                                    // <= 18 for 16-bit CDFs
-    st.value = funnel_l((uint32_t)(st.res >> 32), st.value, k) ^ (m ? 0x80000000u : 0u);
-    st.res <<= k;
-    st.rb -= k;
+    const uint32_t t = funnel_l(st.nxt, st.cur, st.pos);         // the next 32 unread stream bits
+    st.off = funnel_l(t, off - plo, k);                          // ((off - plo) << k) | next k bits
+    st.pos += k;
     st.low = (low << m) & 0x7FFFFFFFu;
     st.rng = (shl_fill1(high, m) | 0x80000000u) - st.low;
     dec_refill2(st, src);
