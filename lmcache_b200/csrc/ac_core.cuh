@@ -278,18 +278,59 @@ B2_HD void enc_symbol(EncState& st, uint32_t c_lo, uint32_t width, Sink& sink) {
 }
 
 // ---- production encoder step: same bitstream as enc_symbol, organised for SIMT execution.
-// State keeps `rng = high - low` instead of high; emission is predicated instead of branched:
-//   n leading agreed bits + p pending bits form ONE (n+p)-bit value  V = top + ((2^p - 1) << (n-1))
-// (b0 followed by p copies of !b0 followed by the other n-1 bits, written as a carry), appended to a 64-bit
-// accumulator; at most one 32-bit word leaves the accumulator per symbol.  Only p + n > 32 (a pending run
-// longer than a word) takes a real branch.
+// The reference coder delays "pending" (E3) bits until the next agreed bit tells whether they are 01..1 or 10..0.
+// That is carry resolution in disguise, so the production coder tracks the ABSOLUTE low instead:
+//   x   = window of the absolute low = reference `low` with its MSB flipped while E3 bits are pending
+//   rng = reference high - low
+// With h = x + (phi - 1) (wrapping), x ^ h equals low ^ high and the E3 pattern below the MSB is unchanged, so the
+// shift counts n (E1/E2) and m (E3) come out exactly as in the reference, and EVERY shift -- E1, E2 or E3 -- simply
+// moves the MSB of x into the output: out = (out << k) | (x >> (32 - k)), x <<= k, k = n + m.  A pending run that
+// resolves to 10..0 shows up as a carry out of x + plo, which is added to the output accumulator (the run 01..1 is
+// sitting there and ripples).  No pending counter, no masks, no data-dependent emission branch; termination is
+// x + 2^30 with the same carry rule, then the top two bits.
+// The accumulator `lo` holds nb < 32 unflushed bits, right aligned, zero above -- except a carry that rippled
+// through all nb of them, which then sits at bit nb and, at the next flush, lands one position above the 32-bit
+// word being written: the (rare) signal to increment the words already in the row.
 struct EncState2 {
-    uint32_t low, rng, pending;
-    uint64_t acc;
-    uint32_t nb;     // valid bits in acc, < 32 between calls
+    uint32_t x, rng;
+    uint32_t lo;     // unflushed output bits
+    uint32_t nb;     // number of them, < 32 between calls
     uint32_t w;      // words written to the row so far
-    B2_HD void init() { low = 0u; rng = 0xFFFFFFFFu; pending = 0u; acc = 0ull; nb = 0u; w = 0u; }
+    B2_HD void init() { x = 0u; rng = 0xFFFFFFFFu; lo = 0u; nb = 0u; w = 0u; }
 };
+
+// add `over` to the big-endian number formed by row words [0, w): the carry left the accumulator
+B2_HD void enc_ripple(uint32_t* row, uint32_t w, uint32_t capm1, uint32_t over) {
+    while (over != 0u && w != 0u) {
+        --w;
+        uint32_t* q = row + (w < capm1 ? w : capm1);
+        const uint32_t v = bswap32(*q) + over;
+        *q = bswap32(v);
+        over = v < over ? 1u : 0u;
+    }
+}
+
+// append the top k bits of x (0 <= k <= 31) to the accumulator; flush one word when 32 are available
+B2_HD void enc_append(EncState2& st, uint32_t x, uint32_t k, uint32_t* row, uint32_t capm1) {
+    const uint32_t hi = funnel_l(st.lo, 0u, k);                 // bits pushed above 32 (incl. a rippled carry)
+    const uint32_t lo = funnel_l(x, st.lo, k);
+    const uint32_t nb = st.nb + k;
+    const uint32_t nb2 = nb & 31u;                              // nb < 64: subtract 32 iff flushing
+    const uint32_t word = bswap32(funnel_r(lo, hi, nb2));       // meaningful only when flushing
+    uint32_t* dst = row + (st.w < capm1 ? st.w : capm1);
+#if defined(__CUDA_ARCH__)
+    // one predicated store: in a warp some lane flushes on nearly every symbol, so a branch here would run for all
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %0, 32;\n\t@p st.global.u32 [%1], %2;\n\t}"
+                 :: "r"(nb), "l"(dst), "r"(word) : "memory");
+#else
+    if (nb >= 32u) *dst = word;
+#endif
+    const bool flush = nb >= 32u;
+    if (flush && (hi >> nb2) != 0u) enc_ripple(row, st.w, capm1, hi >> nb2);     // rare
+    st.lo = lo & ~((flush ? 0xFFFFFFFFu : 0u) << nb2);          // flushed bits leave; otherwise keep all (carry bit too)
+    st.w += nb >> 5;
+    st.nb = nb2;
+}
 
 // row: word-addressed output row with capacity `cap` words (stores are clamped to the last word so a
 // violated size bound can never write outside the row; the bound itself is proven in DESIGN.md 3.2)
@@ -298,65 +339,28 @@ B2_HD void enc_symbol2(EncState2& st, uint32_t c_lo, uint32_t width, uint32_t* r
     const uint32_t c_hi = c_lo + width;
     const uint32_t plo = (uint32_t)(((uint64_t)r * c_lo + c_lo) >> 16);
     const uint32_t phi = (uint32_t)(((uint64_t)r * c_hi + c_hi) >> 16);   // wraps to 0 when it is 2^32
-    uint32_t low = st.low + plo;
-    uint32_t high = st.low + phi - 1u;
-    const uint32_t n = clz32((low ^ high) | 1u);
-    const uint32_t top = funnel_l(low, 0u, n);                 // n leading bits of low (0 when n == 0)
-    low <<= n;
-    high = shl_fill1(high, n);
-    const uint32_t m = e3_count(low, high);
-    uint32_t p = st.pending;
-    uint32_t v, k;
-    if (p + n > 32u && n != 0u) {                               // rare, warp-uniformly not taken: long pending run
-        const uint32_t b0 = top >> (n - 1u);
-        const uint32_t fill = b0 ? 0u : 0xFFFFFFFFu;
-        st.acc = (st.acc << 1) | b0; st.nb += 1u;
-        if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
-        while (p) {
-            const uint32_t kk = p < 32u ? p : 32u;
-            st.acc = (st.acc << kk) | (kk == 32u ? fill : (fill & ((1u << kk) - 1u)));
-            st.nb += kk;
-            if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
-            p -= kk;
-        }
-        v = top & ((1u << (n - 1u)) - 1u);
-        k = n - 1u;
-    } else {
-        // predicated: mask = all ones iff bits are emitted
-        const uint32_t mask = n != 0u ? 0xFFFFFFFFu : 0u;
-        v = (top + ((((1u << (p & 31u)) - 1u) << ((n - 1u) & 31u)))) & mask;
-        k = (n + p) & mask;
-        p &= ~mask;
-    }
-    st.pending = p + m;
-    st.low = (low << m) & 0x7FFFFFFFu;
-    st.rng = (shl_fill1(high, m) | 0x80000000u) - st.low;
-    st.acc = (st.acc << k) | (uint64_t)v;
-    const uint32_t nb = st.nb + k;
-    const bool flush = nb >= 32u;
-    const uint32_t nb2 = nb & 31u;                              // nb < 64: subtract 32 iff flushing
-    const uint32_t word = bswap32((uint32_t)(st.acc >> nb2));   // meaningful only when flushing
-    if (flush) row[st.w < cap ? st.w : cap - 1u] = word;        // single predicated store
-    st.w += flush ? 1u : 0u;
-    st.nb = nb2;
+    const uint32_t x = st.x + plo;
+    const uint32_t h = st.x + phi - 1u;
+    st.lo += x < plo ? 1u : 0u;                                 // carry: the pending run resolves to 10..0
+    const uint32_t n = clz32((x ^ h) | 1u);
+    const uint32_t m = e3_count(x << n, h << n);
+    const uint32_t k = n + m;                                   // <= 18: the coded interval is >= 2^14 wide
+    st.x = x << k;
+    st.rng = shl_fill1(h, k) - st.x;
+    enc_append(st, x, k, row, cap - 1u);
 }
 
-// terminate: final bit + pending, zero pad; returns the stream's byte length
+// terminate: the reference's final bit + pending run = the top two bits of x + 2^30 (with carry), zero padded to a
+// byte; returns the stream's byte length
 B2_HD uint32_t enc_finish2(EncState2& st, uint32_t* row, uint32_t cap) {
-    uint32_t p = st.pending + 1u;
-    const uint32_t bit = st.low < 0x40000000u ? 0u : 1u;
-    const uint32_t fill = bit ? 0u : 0xFFFFFFFFu;
-    st.acc = (st.acc << 1) | bit; st.nb += 1u;
-    if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
-    while (p) {
-        const uint32_t kk = p < 32u ? p : 32u;
-        st.acc = (st.acc << kk) | (kk == 32u ? fill : (fill & ((1u << kk) - 1u)));
-        st.nb += kk;
-        if (st.nb >= 32u) { st.nb -= 32u; row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc >> st.nb)); st.w++; }
-        p -= kk;
-    }
+    const uint32_t capm1 = cap - 1u;
+    const uint32_t x = st.x + 0x40000000u;
+    st.lo += x < 0x40000000u ? 1u : 0u;
+    enc_append(st, x, 2u, row, capm1);
+    const uint32_t over = st.lo >> st.nb;                       // a carry that rippled through the whole tail
+    if (over) { enc_ripple(row, st.w, capm1, over); st.lo &= ~(0xFFFFFFFFu << st.nb); }
     const uint32_t full = st.w;
-    if (st.nb) { row[st.w < cap ? st.w : cap - 1u] = bswap32((uint32_t)(st.acc << (32u - st.nb))); st.w++; }
+    if (st.nb) { row[st.w < capm1 ? st.w : capm1] = bswap32(st.lo << (32u - st.nb)); st.w++; }
     return 4u * full + ((st.nb + 7u) >> 3);
 }
 

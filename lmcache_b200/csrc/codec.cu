@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
                           (int64_t)h * P.sH + (active ? c - h * P.D : 0);
     const int64_t s1 = P.sT;
     uint32_t* trow = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
-    const uint32_t cap = (uint32_t)P.tempw;
+    uint32_t cap = (uint32_t)P.tempw;
+    // keep the row pointer and the capacity as plain register values: otherwise every flush re-derives the address
+    // from (tile, tid, tempw, base) with six extra instructions
+    asm volatile("" : "+l"(trow), "+r"(cap));
     uint32_t len = 0u;
 
     if (FUSED) {

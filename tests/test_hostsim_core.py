@@ -134,6 +134,28 @@ def test_production_coder_long_pending_run(sim):
         _check_v2(sim, cdf3.view(np.int16), sym3, 0, 256)
 
 
+def test_production_coder_random_carry_stress(sim):
+    """random few-symbol CDFs whose boundaries sit on / next to the midpoint and quarter points: the pending run
+    (= carry ripple in the production coder) crosses flushed 32-bit words in both directions"""
+    rng = np.random.default_rng(2024)
+    anchors = np.array([16384, 32768, 49152, 8192, 24576, 40960, 57344])
+    for case in range(120):
+        nsym = int(rng.integers(2, 6))
+        cuts = np.unique(np.clip(rng.choice(anchors, nsym - 1) + rng.integers(-2, 3, nsym - 1), 1, 65000))
+        nsym = len(cuts) + 1
+        cdf = np.zeros((1, 1, 33), np.uint16)
+        cdf[0, 0, 1:nsym] = cuts
+        cdf[0, 0, nsym:32] = 65100 + np.arange(32 - nsym)          # unused symbols keep width 1
+        g = int(rng.integers(1, 257))
+        if case % 3 == 0:       # long runs of one symbol, occasionally broken
+            sym = np.full(g, rng.integers(0, nsym), np.int64)
+            brk = rng.random(g) < 0.03
+            sym[brk] = rng.integers(0, nsym, brk.sum())
+        else:
+            sym = rng.integers(0, nsym, g)
+        _check_v2(sim, cdf.view(np.int16), sym.astype(np.int8).reshape(1, g, 1), 0, g)
+
+
 def test_coder_foreign_cdf_expensive_symbols(sim):
     """Group coded with a CDF that is NOT its own histogram (chunk > 256 tokens): symbols may cost up to 16
     bits and pending runs get long; encoder and decoder must still match the bit-by-bit oracle."""
