@@ -145,7 +145,7 @@ __device__ __forceinline__ bool decode_tile(const EncParams& P, uint32_t tile, T
 // the container; the tile's byte total goes to tile_tot.  Compaction into the contiguous payload (collect_bytes in the
 // reference) is done by scan_kernel + compact_kernel afterwards, so no CTA ever waits on another one.
 template <bool FUSED, int DT>
-__global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
+__global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     // FUSED : symbol rows u32[CT][SYMW] | cdf rows u16[CT][33] (also the histogram) | fac[256] (later fl32(n/t)[257])
     // !FUSED: pair rows u32[CT][33]                                                 | fac[256]
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + id.tok0;
     const float maxq = P.pt.maxq[nl];
     for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[i], DT));
+    if (FUSED) for (int i = gt + tid; i < kGroup + 8; i += CT) fac[i] = 0.0f;      // padded slots of the last batch
 
     const int h = active ? c / P.D : 0;
     const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0) * P.sT +
@@ -203,35 +204,51 @@ __global__ void __launch_bounds__(CT) encode_kernel(EncParams P) {
         }
         __syncthreads();   // fac ready
         if (active) {
-            // ---- pass 1: 24 tokens (four packed words) per iteration, all loads issued before the first use
-            constexpr int NB = 4;
-            const uint16_t* p = src;
-            int tk = 0, w = 0;
-            for (; tk + NB * SPW <= gt; tk += NB * SPW, w += NB, p += NB * SPW * s1) {
-                uint16_t x[NB * SPW];
+            // ---- pass 1: batches of 12 tokens (two packed words), register double-buffered: the loads of batch b+1
+            // are in flight while batch b is quantised, so a warp never sits out a full L2 round trip per batch.
+            // Slots past the group's end (last word / last batch) read as x = 0 with factor 0 and are quantised like
+            // the rest; their known symbol is taken out of the histogram afterwards, and pass 2 never reads them.
+            constexpr int NB = 2, BT = NB * SPW;
+            const int nbatch = (gt + BT - 1) / BT;
+            uint16_t xa[BT], xb[BT];
+            auto load = [&](uint16_t (&x)[BT], int b) {
+                const int tk = b * BT;
+                const uint16_t* p = src + (int64_t)tk * s1;
+                if (tk + BT <= gt) {
 #pragma unroll
-                for (int k = 0; k < NB * SPW; ++k) x[k] = __ldg(p + k * s1);
+                    for (int k = 0; k < BT; ++k) x[k] = __ldg(p + k * s1);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < BT; ++k) x[k] = tk + k < gt ? __ldg(p + k * s1) : (uint16_t)0;
+                }
+            };
+            auto quantise = [&](const uint16_t (&x)[BT], int b) {
+                const int tk = b * BT;
 #pragma unroll
                 for (int half = 0; half < NB; ++half) {
-                    uint32_t word = 0u;
+                    if (tk + half * SPW < gt) {
+                        uint32_t word = 0u;
 #pragma unroll
-                    for (int k = 0; k < SPW; ++k) {
-                        const uint32_t q = quant_symbol(half_to_float(x[half * SPW + k], DT), fac[tk + half * SPW + k], maxq);
-                        hist[q] += 1;                                   // symbols are <= 30 by construction
-                        word |= q << (5 * k);
+                        for (int k = 0; k < SPW; ++k) {
+                            const uint32_t q = quant_symbol(half_to_float(x[half * SPW + k], DT), fac[tk + half * SPW + k], maxq);
+                            hist[q] += 1;                               // symbols are <= 30 by construction
+                            word |= q << (5 * k);
+                        }
+                        myrow[b * NB + half] = word;
                     }
-                    myrow[w + half] = word;
+                }
+            };
+            load(xa, 0);
+            for (int b = 0; b < nbatch; b += 2) {
+                if (b + 1 < nbatch) load(xb, b + 1);
+                quantise(xa, b);
+                if (b + 1 < nbatch) {
+                    if (b + 2 < nbatch) load(xa, b + 2);
+                    quantise(xb, b + 1);
                 }
             }
-            for (; tk < gt; tk += SPW, ++w, p += SPW * s1) {              // ragged tail: up to SPW tokens per word
-                uint32_t word = 0u;
-                for (int k = 0; k < SPW && tk + k < gt; ++k) {
-                    const uint32_t q = quant_symbol(half_to_float(__ldg(p + k * s1), DT), fac[tk + k], maxq);
-                    hist[q] += 1;
-                    word |= q << (5 * k);
-                }
-                myrow[w] = word;
-            }
+            const int pad = (gt + SPW - 1) / SPW * SPW - gt;            // padded slots in the last word
+            if (pad) hist[quant_symbol(0.0f, 0.0f, maxq)] -= (uint16_t)pad;
         }
         __syncthreads();   // every thread is done with fac: reuse it as the fl32(n / t) table
         {
@@ -819,7 +836,7 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
         B2_CHECK_CUDA(cudaGetLastError());
     }
     // 2) encode (streams -> temp rows, lengths, tile totals)
-    const size_t smem_fused = (size_t)(((CT * SYMW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + 4) * 4;
+    const size_t smem_fused = (size_t)(((CT * SYMW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + 8) * 4;
     const size_t smem_split = (size_t)(((CT * PAIRW + 3) & ~3) + kGroup + 4) * 4;
     const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
 #define B2_LAUNCH_ENC(FUSED, DT, SMEM)                                                                     \
