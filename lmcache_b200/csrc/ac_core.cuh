@@ -80,6 +80,17 @@ B2_HD uint32_t bswap32(uint32_t v) {
 #endif
 }
 
+// position of the leading one (FLO / bfind); 0xFFFFFFFF for x == 0
+B2_HD uint32_t bfind32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return x ? 31u - (uint32_t)__builtin_clz(x) : 0xFFFFFFFFu;
+#endif
+}
+
 // (x << n) | ones(n), 0 <= n <= 31 : one funnel shift with an all-ones low word
 B2_HD uint32_t shl_fill1(uint32_t x, uint32_t n) { return funnel_l(0xFFFFFFFFu, x, n); }
 
@@ -299,13 +310,13 @@ struct EncState2 {
     B2_HD void init() { x = 0u; rng = 0xFFFFFFFFu; lo = 0u; nb = 0u; w = 0u; }
 };
 
-// add `over` to the big-endian number formed by row words [0, w): the carry left the accumulator
+// add `over` to the number formed by row words [0, w) (word 0 most significant): the carry left the accumulator
 B2_HD void enc_ripple(uint32_t* row, uint32_t w, uint32_t capm1, uint32_t over) {
     while (over != 0u && w != 0u) {
         --w;
         uint32_t* q = row + (w < capm1 ? w : capm1);
-        const uint32_t v = bswap32(*q) + over;
-        *q = bswap32(v);
+        const uint32_t v = *q + over;
+        *q = v;
         over = v < over ? 1u : 0u;
     }
 }
@@ -316,7 +327,7 @@ B2_HD void enc_append(EncState2& st, uint32_t x, uint32_t k, uint32_t* row, uint
     const uint32_t lo = funnel_l(x, st.lo, k);
     const uint32_t nb = st.nb + k;
     const uint32_t nb2 = nb & 31u;                              // nb < 64: subtract 32 iff flushing
-    const uint32_t word = bswap32(funnel_r(lo, hi, nb2));       // meaningful only when flushing
+    const uint32_t word = funnel_r(lo, hi, nb2);                // meaningful only when flushing
     uint32_t* dst = row + (st.w < capm1 ? st.w : capm1);
 #if defined(__CUDA_ARCH__)
     // one predicated store: in a warp some lane flushes on nearly every symbol, so a branch here would run for all
@@ -325,26 +336,38 @@ B2_HD void enc_append(EncState2& st, uint32_t x, uint32_t k, uint32_t* row, uint
 #else
     if (nb >= 32u) *dst = word;
 #endif
-    const bool flush = nb >= 32u;
-    if (flush && (hi >> nb2) != 0u) enc_ripple(row, st.w, capm1, hi >> nb2);     // rare
-    st.lo = lo & ~((flush ? 0xFFFFFFFFu : 0u) << nb2);          // flushed bits leave; otherwise keep all (carry bit too)
+    // hi != 0 only when flushing (nb < 32 keeps every accumulator bit, the carry bit included, inside lo); a bit
+    // above the 32-bit word just written is a carry that rippled through all unflushed bits
+    const uint32_t over = hi >> nb2;
+    if (over != 0u) enc_ripple(row, st.w, capm1, over);          // rare
+    st.lo = lo & ~((nb >= 32u ? 0xFFFFFFFFu : 0u) << nb2);       // flushed bits leave; otherwise keep all (carry bit too)
     st.w += nb >> 5;
     st.nb = nb2;
 }
 
 // row: word-addressed output row with capacity `cap` words (stores are clamped to the last word so a
-// violated size bound can never write outside the row; the bound itself is proven in DESIGN.md 3.2)
+// violated size bound can never write outside the row; the bound itself is proven in DESIGN.md 3.2).
+// Row words hold the stream MSB-first in NATIVE order (stream byte 4w+b = bits 31-8b.. of word w): whoever moves the
+// row to its final place writes the bytes out (compact_kernel), so the coder spends no byte swap per symbol.
 B2_HD void enc_symbol2(EncState2& st, uint32_t c_lo, uint32_t width, uint32_t* row, uint32_t cap) {
     const uint32_t r = st.rng;
     const uint32_t c_hi = c_lo + width;
     const uint32_t plo = (uint32_t)(((uint64_t)r * c_lo + c_lo) >> 16);
     const uint32_t phi = (uint32_t)(((uint64_t)r * c_hi + c_hi) >> 16);   // wraps to 0 when it is 2^32
-    const uint32_t x = st.x + plo;
     const uint32_t h = st.x + phi - 1u;
-    st.lo += x < plo ? 1u : 0u;                                 // carry: the pending run resolves to 10..0
-    const uint32_t n = clz32((x ^ h) | 1u);
-    const uint32_t m = e3_count(x << n, h << n);
-    const uint32_t k = n + m;                                   // <= 18: the coded interval is >= 2^14 wide
+    uint32_t x;
+#if defined(__CUDA_ARCH__)
+    // carry out of x + plo: the pending run resolves to 10..0 -- add it to the accumulator
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(x), "=r"(st.lo) : "r"(st.x), "r"(plo), "r"(st.lo));
+#else
+    x = st.x + plo;
+    st.lo += x < plo ? 1u : 0u;
+#endif
+    // k = n + m in one go: p = position of the first differing bit (n = 31 - p agreed bits above it); below it the
+    // E3 run continues while x has 1 and h has 0, so k = 30 - (position of the first bit below p with ~x | h)
+    const uint32_t p = bfind32((x ^ h) | 1u);
+    const uint32_t f = ((~x) | h) & ~(0xFFFFFFFFu << p);
+    const uint32_t k = 30u - bfind32(f);                         // <= 18: the coded interval is >= 2^14 wide
     st.x = x << k;
     st.rng = shl_fill1(h, k) - st.x;
     enc_append(st, x, k, row, cap - 1u);
@@ -360,7 +383,7 @@ B2_HD uint32_t enc_finish2(EncState2& st, uint32_t* row, uint32_t cap) {
     const uint32_t over = st.lo >> st.nb;                       // a carry that rippled through the whole tail
     if (over) { enc_ripple(row, st.w, capm1, over); st.lo &= ~(0xFFFFFFFFu << st.nb); }
     const uint32_t full = st.w;
-    if (st.nb) { row[st.w < capm1 ? st.w : capm1] = bswap32(st.lo << (32u - st.nb)); st.w++; }
+    if (st.nb) { row[st.w < capm1 ? st.w : capm1] = st.lo << (32u - st.nb); st.w++; }
     return 4u * full + ((st.nb + 7u) >> 3);
 }
 

@@ -224,15 +224,19 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
             };
             auto quantise = [&](const uint16_t (&x)[BT], int b) {
                 const int tk = b * BT;
+                // all symbols of the batch first (independent chains), then the histogram read-modify-writes: those
+                // may alias each other, so interleaving them with the arithmetic would serialise the whole batch
+                uint32_t q[BT];
+#pragma unroll
+                for (int k = 0; k < BT; ++k) q[k] = quant_symbol(half_to_float(x[k], DT), fac[tk + k], maxq);
 #pragma unroll
                 for (int half = 0; half < NB; ++half) {
                     if (tk + half * SPW < gt) {
                         uint32_t word = 0u;
 #pragma unroll
                         for (int k = 0; k < SPW; ++k) {
-                            const uint32_t q = quant_symbol(half_to_float(x[half * SPW + k], DT), fac[tk + half * SPW + k], maxq);
-                            hist[q] += 1;                               // symbols are <= 30 by construction
-                            word |= q << (5 * k);
+                            hist[q[half * SPW + k]] += 1;               // symbols are <= 30 by construction
+                            word |= q[half * SPW + k] << (5 * k);
                         }
                         myrow[b * NB + half] = word;
                     }
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
             const uint32_t nb = min(4u, len - 4u * w);
 #pragma unroll
             for (uint32_t b = 0; b < 4u; ++b)
-                if (b < nb) d[4u * w + b] = (uint8_t)(v >> (8u * b));
+                if (b < nb) d[4u * w + b] = (uint8_t)(v >> (24u - 8u * b));      // rows are MSB-first native words
         }
     }
     __syncthreads();

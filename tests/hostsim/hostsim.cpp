@@ -70,7 +70,8 @@ int64_t sim_encode_stream2(const uint16_t* cdf, const int8_t* sym, int64_t sym_s
         enc_symbol2(st, c_lo, c_hi - c_lo, row.data(), capw);
     }
     uint32_t n = enc_finish2(st, row.data(), capw);
-    if ((int64_t)n <= cap) memcpy(out, row.data(), n);
+    if ((int64_t)n <= cap)
+        for (uint32_t i = 0; i < n; ++i) out[i] = (uint8_t)(row[i >> 2] >> (24u - 8u * (i & 3u)));   // MSB-first words
     return n;
 }
 
