@@ -471,7 +471,7 @@ B2_HD uint32_t dec_symbol(DecState& st, Src& src, CdfFn cdf, bool last) {
 //  * symbol search: fixed-depth and branch-free (warp lanes never diverge; a data-dependent walk was measured
 //    2x slower because a warp pays for its longest lane), see dec_symbol2.
 struct DecState2 {
-    uint32_t low, rng, off;
+    uint32_t x, span, off; // x: window of the absolute low (enc_symbol2); span = high - low + 1 (0 means 2^32)
     uint32_t cur, nxt;     // stream words (big-endian bit order), nxt is the look-ahead
     uint32_t pos;          // bits of `cur` already consumed (< 32 between symbols)
 };
@@ -489,7 +489,7 @@ B2_HD void dec_refill2(DecState2& st, Src& src) {
 // `skip` = number of leading bytes of the first aligned word that belong to the previous stream (0..3)
 template <class Src>
 B2_HD void dec_init2(DecState2& st, Src& src, uint32_t skip) {
-    st.low = 0u; st.rng = 0xFFFFFFFFu;
+    st.x = 0u; st.span = 0u;
     st.cur = src.next_be();
     st.nxt = src.next_be();
     st.pos = 8u * skip;
@@ -508,13 +508,14 @@ B2_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 
 // Approximate count ~ floor((value - low) * 2^16 / span), within +-1 of the reference's exact
 //   count = ((value - low + 1) * 2^16 - 1) / span      (one reciprocal instead of a 64-bit division).
+// `rng` is the span as a uint32 (0 stands for 2^32: the guess is then arbitrary and the exactness check repairs it).
 B2_HD uint32_t dec_count_approx(uint32_t off, uint32_t rng) {
 #if defined(__CUDA_ARCH__)
     float rc;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rn(rng)));      // one MUFU.RCP; rng >= 2^30
     const uint32_t c = (uint32_t)__float2int_rz(__uint2float_rn(off) * (rc * 65536.0f));
 #else
-    const float q = ((float)off / (float)rng) * 65536.0f;
+    const float q = rng ? ((float)off / (float)rng) * 65536.0f : 0.0f;      // rng == 0 stands for 2^32: any guess does
     const uint32_t c = (uint32_t)(int)q;
 #endif
     return c < 65535u ? c : 65535u;
@@ -556,11 +557,11 @@ __device__ __forceinline__ void dec_search_steps(uint32_t& a, uint32_t key) {
 //     and walks to the exact symbol.  The result is exact whatever the approximation did.
 template <int NSTEPS, class Src>
 B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last) {
-    const uint32_t r = st.rng;
+    const uint32_t span = st.span;                               // 0 when the interval is the whole 32-bit range
+    const uint32_t r = span - 1u;
     const uint32_t off = st.off;
-    const uint32_t cnt16 = (dec_count_approx(off, r) << 16) | 0xFFFFu;
+    const uint32_t cnt16 = (dec_count_approx(off, span) << 16) | 0xFFFFu;
     constexpr uint32_t kTop = (1u << NSTEPS) - 1u;               // highest searchable symbol
-    const uint32_t span = r + 1u;                                // 0 when the interval is the whole 32-bit range
 #if defined(__CUDA_ARCH__)
     // the table lives in shared memory: walk it with a 32-bit shared address so that every step is
     // LDS [a + imm] / ISETP / select, and the symbol index falls out of the address
@@ -586,18 +587,17 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
         while (s < kTop && (uint32_t)(off - plo) >= (uint32_t)(phi - plo)) { ++s; dec_exact_products(e, r, s, &plo, &phi); }
     }
     if (last) return s;
-    uint32_t low = st.low + plo;
-    uint32_t high = st.low + phi - 1u;
-    const uint32_t n = clz32((low ^ high) | 1u);
-    low <<= n;
-    high = shl_fill1(high, n);
-    const uint32_t m = e3_count(low, high);
-    const uint32_t k = n + m;                                    // <= 18 for 16-bit CDFs
+    // renormalisation exactly as in enc_symbol2: all k = n + m shifts (E1/E2/E3) at once, on the absolute-low window
+    const uint32_t x = st.x + plo;
+    const uint32_t h = st.x + phi - 1u;
+    const uint32_t p = bfind32((x ^ h) | 1u);
+    const uint32_t f = ((~x) | h) & ~(0xFFFFFFFFu << p);
+    const uint32_t k = 30u - bfind32(f);                         // <= 18 for 16-bit CDFs
     const uint32_t t = funnel_l(st.nxt, st.cur, st.pos);         // the next 32 unread stream bits
     st.off = funnel_l(t, off - plo, k);                          // ((off - plo) << k) | next k bits
     st.pos += k;
-    st.low = (low << m) & 0x7FFFFFFFu;
-    st.rng = (shl_fill1(high, m) | 0x80000000u) - st.low;
+    st.x = x << k;
+    st.span = (phi - plo) << k;                                  // (high - low + 1) << k; 2^32 wraps to 0
     dec_refill2(st, src);
     return s;
 }

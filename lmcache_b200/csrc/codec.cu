@@ -593,12 +593,14 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(DecParams P) {
 // load for word i+1 is issued when word i is consumed, so its L2/L1 latency overlaps ~8+ symbols of decoding.
 // Each lane walks its own stream; a 32-byte sector serves 8 consecutive refills from L1.
 struct WordSrc {
-    const uint32_t* p;
+    const uint32_t* base;
+    uint32_t idx;        // next word to load: a 32-bit index keeps the refill to one IMAD.WIDE + one add
     uint32_t ahead;
-    __device__ __forceinline__ void prime() { ahead = __ldg(p++); }
+    __device__ __forceinline__ void prime() { ahead = __ldg(base + idx); ++idx; }
     __device__ __forceinline__ uint32_t next_be() {
         const uint32_t w = ahead;
-        ahead = __ldg(p++);
+        ahead = __ldg(base + idx);
+        ++idx;
         return __byte_perm(w, 0u, 0x0123);
     }
 };
@@ -609,22 +611,21 @@ __device__ __forceinline__ uint16_t out_half(float v, int dt) {
 }
 
 // per-thread decode loop: one stream, gt symbols, straight to the destination layout.
-// dst is addressed as base + 32-bit element offset (one IMAD.WIDE per store instead of 64-bit pointer bookkeeping).
 template <int OUT_DT, int NSTEPS>
 __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint32_t* erow, const float* lut,
                                               const float* mx, uint16_t* dst, uint32_t sT, int gt) {
     const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(my_bytes) & 3u);
-    WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip), 0u};
+    WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip), 0u, 0u};
     src.prime();
     DecState2 st;
     dec_init2(st, src, skip);
-    uint32_t o = 0u;
-    for (int i = 0; i < gt - 1; ++i, o += sT) {
+    uint16_t* d = dst;                                      // running pointer: one 64-bit add per token
+    for (int i = 0; i < gt - 1; ++i, d += sT) {
         const uint32_t s = dec_symbol2<NSTEPS>(st, src, erow, false);
-        dst[o] = out_half(dequant_value(lut[s], mx[i]), OUT_DT);
+        *d = out_half(dequant_value(lut[s], mx[i]), OUT_DT);
     }
     const uint32_t s = dec_symbol2<NSTEPS>(st, src, erow, true);
-    dst[o] = out_half(dequant_value(lut[s], mx[gt - 1]), OUT_DT);
+    *d = out_half(dequant_value(lut[s], mx[gt - 1]), OUT_DT);
 }
 
 // One tile = CT streams of one (chunk, group, plane).  Only the CDF rows (66 B per stream, contiguous in the
