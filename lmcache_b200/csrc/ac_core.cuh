@@ -506,19 +506,21 @@ B2_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-// Approximate count ~ floor((value - low) * 2^16 / span), within +-1 of the reference's exact
-//   count = ((value - low + 1) * 2^16 - 1) / span      (one reciprocal instead of a 64-bit division).
-// `rng` is the span as a uint32 (0 stands for 2^32: the guess is then arbitrary and the exactness check repairs it).
-B2_HD uint32_t dec_count_approx(uint32_t off, uint32_t rng) {
+// Search key ~ floor((value - low) * 2^32 / span): its top 16 bits are the reference's count
+//   count = ((value - low + 1) * 2^16 - 1) / span
+// to within +-1 (one MUFU.RCP instead of a 64-bit division; the low bits only break ties), so  e[i] <= key  with
+// e[i] = cdf[i] << 16 is the count-domain compare cdf[i] <= count.  F2I.U32 saturates, NaN gives 0.
+// `span` is a uint32 (0 stands for 2^32: the guess is then arbitrary and the exactness check repairs it).
+B2_HD uint32_t dec_key_approx(uint32_t off, uint32_t span) {
 #if defined(__CUDA_ARCH__)
     float rc;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rn(rng)));      // one MUFU.RCP; rng >= 2^30
-    const uint32_t c = (uint32_t)__float2int_rz(__uint2float_rn(off) * (rc * 65536.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rn(span)));     // one MUFU.RCP; span > 2^30
+    return __float2uint_rz(__uint2float_rn(off) * (rc * 4294967296.0f));
 #else
-    const float q = rng ? ((float)off / (float)rng) * 65536.0f : 0.0f;      // rng == 0 stands for 2^32: any guess does
-    const uint32_t c = (uint32_t)(int)q;
+    if (span == 0u) return 0u;
+    const float q = ((float)off / (float)span) * 4294967296.0f;
+    return q >= 4294967040.0f ? 0xFFFFFFFFu : (uint32_t)q;
 #endif
-    return c < 65535u ? c : 65535u;
 }
 
 // The decoder reads the stream's CDF as a table of 33 words  e[i] = cdf[i] << 16  (e[32] = 0xFFFFFFFF):
@@ -560,7 +562,7 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
     const uint32_t span = st.span;                               // 0 when the interval is the whole 32-bit range
     const uint32_t r = span - 1u;
     const uint32_t off = st.off;
-    const uint32_t cnt16 = (dec_count_approx(off, span) << 16) | 0xFFFFu;
+    const uint32_t cnt16 = dec_key_approx(off, span);
     constexpr uint32_t kTop = (1u << NSTEPS) - 1u;               // highest searchable symbol
 #if defined(__CUDA_ARCH__)
     // the table lives in shared memory: walk it with a 32-bit shared address so that every step is
