@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tokens", type=int, default=8192)
     ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--heads", type=int, default=32, help="KV heads (32 = BASELINE configs[1]; 8 = GQA shapes, side measurement)")
     ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -179,6 +180,8 @@ def parity_spot_check(kv, out, cs):
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse_args()
+    global H, C
+    H, C = args.heads, args.heads * D
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -309,13 +312,13 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32->u8 (bf16 KV)",
             "data": "synthetic",
             "config": {"workload": f"CacheGen encode+decode, {L}L/{H}H/{D}D {T}-token bf16 KV block per GPU, "
-                                   f"chunk_size {cs} -> {n_chunks} chunks (BASELINE configs[1])",
+                                   f"chunk_size {cs} -> {n_chunks} chunks" + (" (BASELINE configs[1])" if H == 32 else " (side measurement, not the BASELINE shape)"),
                        "raw_bytes_per_gpu": raw_bytes, "container_bytes": container_bytes,
                        "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
                        "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity},
             "encode_GBps": round(raw_bytes / (sum(kern_ms.get(k, 0) for k in ("absmax", "cdf", "encode", "compact")) * 1e-3) / 1e9, 1),
             "decode_GBps": round(raw_bytes / (sum(kern_ms.get(k, 0) for k in ("tile_sum", "tile_scan", "decode")) * 1e-3) / 1e9, 1),
-            "gpu_launches": 8 * args.steps,
+            "gpu_launches": (3 + sum(1 for k in kern_ms if k != "compact")) * args.steps,   # compact slot = scan + compact + finalize
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

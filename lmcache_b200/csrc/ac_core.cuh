@@ -547,8 +547,9 @@ __device__ __forceinline__ void dec_search_steps(uint32_t& a, uint32_t key) {
 }
 #endif
 
-// Decode one symbol.  NSTEPS = 5 searches symbols 0..31, NSTEPS = 4 symbols 0..15 (planes with <= 16 bins only ever
-// code symbols 0..14).
+// Decode one symbol; returns 4 * symbol (the byte offset of its entry in a 32-bit table, which is what the table
+// walk produces and what the caller's dequantisation LUT wants).  NSTEPS = 5 searches symbols 0..31, NSTEPS = 4
+// symbols 0..15 (planes with <= 16 bins only ever code symbols 0..14).
 //  1. s~ = max{ s : cdf[s] <= count~ } by a fixed-depth, branch-free lower-bound search in the count domain
 //     (per step: one LDS off a running pointer, one compare, one predicated add).
 //  2. plo = umulhi(span, e[s]), phi = umulhi(span, e[s+1]) -- needed for the state update anyway.  The symbol is exact
@@ -570,7 +571,7 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(e);
     uint32_t a = a0;
     dec_search_steps<(1 << (NSTEPS - 1))>(a, cnt16);
-    uint32_t s = (a - a0) >> 2;
+    uint32_t s4 = a - a0;                                        // 4 * symbol: the table walk yields a byte offset
     uint32_t e0, e1;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e0) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(e1) : "r"(a));
@@ -578,17 +579,19 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
     const uint32_t* a = e;
 #pragma unroll
     for (int step = 1 << (NSTEPS - 1); step > 0; step >>= 1) a = a[step] <= cnt16 ? a + step : a;
-    uint32_t s = (uint32_t)(a - e);
+    uint32_t s4 = 4u * (uint32_t)(a - e);
     const uint32_t e0 = a[0], e1 = a[1];
 #endif
     uint32_t plo = umulhi32(span, e0);
     uint32_t phi = umulhi32(span, e1);
-    if ((uint32_t)(off - plo) >= (uint32_t)(phi - plo) || (NSTEPS == 5 && s == 31u)) {
+    if ((uint32_t)(off - plo) >= (uint32_t)(phi - plo) || (NSTEPS == 5 && s4 == 124u)) {
+        uint32_t s = s4 >> 2;
         dec_exact_products(e, r, s, &plo, &phi);
         while (off < plo && s > 0u) { --s; dec_exact_products(e, r, s, &plo, &phi); }
         while (s < kTop && (uint32_t)(off - plo) >= (uint32_t)(phi - plo)) { ++s; dec_exact_products(e, r, s, &plo, &phi); }
+        s4 = 4u * s;
     }
-    if (last) return s;
+    if (last) return s4;
     // renormalisation exactly as in enc_symbol2: all k = n + m shifts (E1/E2/E3) at once, on the absolute-low window
     const uint32_t x = st.x + plo;
     const uint32_t h = st.x + phi - 1u;
@@ -601,7 +604,7 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
     st.x = x << k;
     st.span = (phi - plo) << k;                                  // (high - low + 1) << k; 2^32 wraps to 0
     dec_refill2(st, src);
-    return s;
+    return s4;
 }
 
 // ---------------------------------------------------------------- container layout (host + device)

@@ -169,13 +169,13 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
     const Layout lo = make_layout(P.L, P.C, t);
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + id.tok0;
     const float maxq = P.pt.maxq[nl];
+    const int64_t s1 = P.sT;
     for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[i], DT));
     if (FUSED) for (int i = gt + tid; i < kGroup + 8; i += CT) fac[i] = 0.0f;      // padded slots of the last batch
 
     const int h = active ? c / P.D : 0;
     const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0) * P.sT +
                           (int64_t)h * P.sH + (active ? c - h * P.D : 0);
-    const int64_t s1 = P.sT;
     uint32_t* trow = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
     uint32_t cap = (uint32_t)P.tempw;
     // keep the row pointer and the capacity as plain register values: otherwise every flush re-derives the address
@@ -478,13 +478,31 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
     if (len) {
         uint8_t* d = stage + phase + my_off;
         const uint32_t* srcw = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
-        const uint32_t nw = (len + 3u) >> 2;
-        for (uint32_t w = 0; w < nw; ++w) {
-            const uint32_t v = __ldg(srcw + w);
+        auto put_word = [&](uint32_t w, uint32_t v) {        // rows are MSB-first native words
             const uint32_t nb = min(4u, len - 4u * w);
 #pragma unroll
             for (uint32_t b = 0; b < 4u; ++b)
-                if (b < nb) d[4u * w + b] = (uint8_t)(v >> (24u - 8u * b));      // rows are MSB-first native words
+                if (b < nb) d[4u * w + b] = (uint8_t)(v >> (24u - 8u * b));
+        };
+        if (P.tempw == TEMPW_FUSED) {
+            // 160-byte rows, 16-byte aligned: all of the row's 16-byte loads are issued before the first use
+            // (a word-at-a-time loop left one load in flight per thread and the kernel waiting on L2/DRAM latency)
+            constexpr int NV = TEMPW_FUSED / 4;
+            uint4 v[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+                if (16u * q < len) v[q] = __ldg(reinterpret_cast<const uint4*>(srcw) + q);
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+                if (16u * q < len) {
+                    put_word(4u * q, v[q].x);
+                    if (16u * q + 4u < len) put_word(4u * q + 1u, v[q].y);
+                    if (16u * q + 8u < len) put_word(4u * q + 2u, v[q].z);
+                    if (16u * q + 12u < len) put_word(4u * q + 3u, v[q].w);
+                }
+        } else {
+            const uint32_t nw = (len + 3u) >> 2;
+            for (uint32_t w = 0; w < nw; ++w) put_word(w, __ldg(srcw + w));
         }
     }
     __syncthreads();
@@ -620,12 +638,11 @@ __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uin
     DecState2 st;
     dec_init2(st, src, skip);
     uint16_t* d = dst;                                      // running pointer: one 64-bit add per token
-    for (int i = 0; i < gt - 1; ++i, d += sT) {
-        const uint32_t s = dec_symbol2<NSTEPS>(st, src, erow, false);
-        *d = out_half(dequant_value(lut[s], mx[i]), OUT_DT);
-    }
-    const uint32_t s = dec_symbol2<NSTEPS>(st, src, erow, true);
-    *d = out_half(dequant_value(lut[s], mx[gt - 1]), OUT_DT);
+    // dec_symbol2 returns 4 * symbol = the byte offset into the fp32 LUT
+    auto lut_at = [&](uint32_t s4) { return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lut) + s4); };
+    for (int i = 0; i < gt - 1; ++i, d += sT)
+        *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]), OUT_DT);
+    *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]), OUT_DT);
 }
 
 // One tile = CT streams of one (chunk, group, plane).  Only the CDF rows (66 B per stream, contiguous in the
@@ -829,6 +846,7 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
 
     // 1) per-(plane, token) absmax -> maxes sections
     const int64_t total_tokens = (int64_t)(n_chunks - 1) * chunk_tokens + last_chunk_tokens;
+    for (int i = 0; i <= kProfFinalize; ++i) g_prof_have[i] = false;
     {
         bool vec = (kv->D % 8 == 0) && (kv->sT % 8 == 0) && (kv->sH % 8 == 0);
         for (int nl = 0; nl < 2 * P.L && vec; ++nl) vec = (reinterpret_cast<uintptr_t>(P.pt.p[nl]) & 15) == 0;

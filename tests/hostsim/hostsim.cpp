@@ -95,7 +95,7 @@ void sim_decode_stream2(const uint16_t* cdf, const uint8_t* in, int64_t n, int g
     uint32_t e[kLp];
     for (uint32_t i = 0; i < (uint32_t)kLp; ++i) e[i] = dec_table_entry(i, cdf[i]);
     for (int i = 0; i < g; ++i)
-        out[i * out_stride] = (uint8_t)(nsteps == 4 ? dec_symbol2<4>(st, src, e, i == g - 1) : dec_symbol2<5>(st, src, e, i == g - 1));
+        out[i * out_stride] = (uint8_t)((nsteps == 4 ? dec_symbol2<4>(st, src, e, i == g - 1) : dec_symbol2<5>(st, src, e, i == g - 1)) >> 2);   // returns 4 * symbol
 }
 
 void sim_cdf(const uint32_t* counts, int t, uint16_t* cdf) {
