@@ -305,44 +305,59 @@ B2_HD void enc_symbol(EncState& st, uint32_t c_lo, uint32_t width, Sink& sink) {
 struct EncState2 {
     uint32_t x, rng;
     uint32_t lo;     // unflushed output bits
-    uint32_t nb;     // number of them, < 32 between calls
+    uint32_t m;      // (number of them) - 32, i.e. -32..-1 between calls: "a word is full" is just m >= 0
     uint32_t w;      // words written to the row so far
-    B2_HD void init() { x = 0u; rng = 0xFFFFFFFFu; lo = 0u; nb = 0u; w = 0u; }
+    B2_HD void init() { x = 0u; rng = 0xFFFFFFFFu; lo = 0u; m = 0xFFFFFFE0u; w = 0u; }
+    B2_HD uint32_t nbits() const { return m & 31u; }
 };
 
-// add `over` to the number formed by row words [0, w) (word 0 most significant): the carry left the accumulator
+// (x << n) with n taken as an unsigned 32-bit count: 0 for n >= 32 (PTX shl clamps; C++ would be undefined)
+B2_HD uint32_t shl_clamp(uint32_t x, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+#else
+    return n >= 32u ? 0u : x << n;
+#endif
+}
+
+// add `over` to the number formed by row words [0, w) (word 0 most significant): the carry left the accumulator.
+// Only called with w >= 1 (a carry can only ripple into words that exist).
 B2_HD void enc_ripple(uint32_t* row, uint32_t w, uint32_t capm1, uint32_t over) {
-    while (over != 0u && w != 0u) {
+    do {
         --w;
         uint32_t* q = row + (w < capm1 ? w : capm1);
         const uint32_t v = *q + over;
         *q = v;
         over = v < over ? 1u : 0u;
-    }
+    } while (over != 0u && w != 0u);
 }
 
 // append the top k bits of x (0 <= k <= 31) to the accumulator; flush one word when 32 are available
 B2_HD void enc_append(EncState2& st, uint32_t x, uint32_t k, uint32_t* row, uint32_t capm1) {
     const uint32_t hi = funnel_l(st.lo, 0u, k);                 // bits pushed above 32 (incl. a rippled carry)
     const uint32_t lo = funnel_l(x, st.lo, k);
-    const uint32_t nb = st.nb + k;
-    const uint32_t nb2 = nb & 31u;                              // nb < 64: subtract 32 iff flushing
-    const uint32_t word = funnel_r(lo, hi, nb2);                // meaningful only when flushing
+    const uint32_t m = st.m + k;                                // >= 0 (as int32) iff 32 bits are ready; then m = bits left
+    const uint32_t word = funnel_r(lo, hi, m & 31u);            // meaningful only when flushing (funnel shifts wrap)
     uint32_t* dst = row + (st.w < capm1 ? st.w : capm1);
+    const bool flush = (int32_t)m >= 0;
 #if defined(__CUDA_ARCH__)
     // one predicated store: in a warp some lane flushes on nearly every symbol, so a branch here would run for all
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %0, 32;\n\t@p st.global.u32 [%1], %2;\n\t}"
-                 :: "r"(nb), "l"(dst), "r"(word) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}"
+                 :: "r"(m), "l"(dst), "r"(word) : "memory");
 #else
-    if (nb >= 32u) *dst = word;
+    if (flush) *dst = word;
 #endif
-    // hi != 0 only when flushing (nb < 32 keeps every accumulator bit, the carry bit included, inside lo); a bit
+    // hi != 0 only when flushing (otherwise every accumulator bit, the carry bit included, stays inside lo); a bit
     // above the 32-bit word just written is a carry that rippled through all unflushed bits
-    const uint32_t over = hi >> nb2;
+    const uint32_t over = funnel_r(hi, 0u, m & 31u);
     if (over != 0u) enc_ripple(row, st.w, capm1, over);          // rare
-    st.lo = lo & ~((nb >= 32u ? 0xFFFFFFFFu : 0u) << nb2);       // flushed bits leave; otherwise keep all (carry bit too)
-    st.w += nb >> 5;
-    st.nb = nb2;
+    // flushed bits leave: keep the low m bits.  Without a flush m is "negative" = a huge unsigned count, the clamped
+    // shift yields 0 and every bit stays (carry bit too)
+    st.lo = lo & ~shl_clamp(0xFFFFFFFFu, m);
+    st.w += flush ? 1u : 0u;
+    st.m = m | 0xFFFFFFE0u;                                     // (m mod 32) - 32
 }
 
 // row: word-addressed output row with capacity `cap` words (stores are clamped to the last word so a
@@ -380,11 +395,12 @@ B2_HD uint32_t enc_finish2(EncState2& st, uint32_t* row, uint32_t cap) {
     const uint32_t x = st.x + 0x40000000u;
     st.lo += x < 0x40000000u ? 1u : 0u;
     enc_append(st, x, 2u, row, capm1);
-    const uint32_t over = st.lo >> st.nb;                       // a carry that rippled through the whole tail
-    if (over) { enc_ripple(row, st.w, capm1, over); st.lo &= ~(0xFFFFFFFFu << st.nb); }
+    const uint32_t nb = st.nbits();
+    const uint32_t over = st.lo >> nb;                          // a carry that rippled through the whole tail
+    if (over) { if (st.w) enc_ripple(row, st.w, capm1, over); st.lo &= ~(0xFFFFFFFFu << nb); }
     const uint32_t full = st.w;
-    if (st.nb) { row[st.w < capm1 ? st.w : capm1] = st.lo << (32u - st.nb); st.w++; }
-    return 4u * full + ((st.nb + 7u) >> 3);
+    if (nb) { row[st.w < capm1 ? st.w : capm1] = st.lo << (32u - nb); st.w++; }
+    return 4u * full + ((nb + 7u) >> 3);
 }
 
 // terminate the stream; returns the number of trailing bits (0..31) still in st.acc (left to the caller
