@@ -18,6 +18,11 @@ KEYS = [
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    # the coder kernels are bounded by the ALU pipe (one warp instruction per 2 cycles per SMSP) and by issue slots
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
 ]
 STALLS = ["long_scoreboard", "short_scoreboard", "wait", "not_selected", "barrier", "math_pipe_throttle",
           "branch_resolving", "mio_throttle", "lg_throttle", "no_instruction", "dispatch_stall", "sleeping"]
