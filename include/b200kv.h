@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define B200KV_VERSION 1
+#define B200KV_VERSION 2           /* ABI version; 2: b200kv_kv_desc.slot_map */
+#define B200KV_CONTAINER_VERSION 1 /* "B2KV" wire container version (b200kv_header.version) */
 #define B200KV_LP 33            /* CDF entries per stream (cachegen_encoder.py:287-289: int(bins.max()) + 1) */
 #define B200KV_GROUP_TOKENS 256 /* CACHEGEN_GPU_MAX_TOKENS_PER_CHUNK (cachegen_basics.py:13) */
 #define B200KV_MAX_PLANES 128   /* 2 * nlayers upper bound */
@@ -47,6 +48,12 @@ typedef struct b200kv_kv_desc {
     int64_t sL, sKV, sT, sH;   /* element strides (sL/sKV ignored when planes != NULL) */
     int32_t L, H, D;           /* layers, kv heads, head size; channels C = H*D */
     int32_t dtype;             /* B200KV_DT_* of the KV elements */
+    const int64_t* slot_map;   /* DEVICE array or NULL.  Paged KV (vLLM's slot_mapping, lmcache-vllm's
+                                * lmcache_store_kv / lmcache_retrieve_kv, docs LLM_Engine.rst:91-109): token i of the call
+                                * (tok_begin + i for encode, dst_tok[j] + i for decode) lives in row slot_map[i] of every
+                                * plane, i.e. `tok` in the address formula above is replaced by slot_map[tok].  The codec
+                                * kernels gather / scatter through it, so the paged cache is read and written in place.
+                                * Ignored by b200kv_pack_chunks / b200kv_unpack_chunks (must be NULL there). */
 } b200kv_kv_desc;
 
 /* Wire container of one encoded chunk ("B2KV" v1).  All sections 16-byte aligned, little-endian.

@@ -37,6 +37,7 @@ class KvDesc(ctypes.Structure):
         ("sL", c_i64), ("sKV", c_i64), ("sT", c_i64), ("sH", c_i64),
         ("L", c_i32), ("H", c_i32), ("D", c_i32),
         ("dtype", c_i32),
+        ("slot_map", c_vp),     # device int64[ntokens] or NULL (paged KV)
     ]
 
 

@@ -146,6 +146,44 @@ class KvView:
         d.dtype = KvView._code(ref.dtype)
         return KvView(d, (keep, ptrs), T, ref.device, ref.dtype, fmt)
 
+    @staticmethod
+    def from_paged(kv_caches: Sequence[Tuple[torch.Tensor, torch.Tensor]], slot_mapping: torch.Tensor) -> "KvView":
+        """vLLM's paged KV cache used in place: `kv_caches` holds, per layer, the (key_cache, value_cache) pair shaped
+        [num_blocks, block_size, H, D] (or already flattened [num_slots, H, D]); `slot_mapping` (int64, CUDA) gives the
+        cache row of every token of the sequence (block * block_size + offset) -- what lmcache-vllm's
+        lmcache_store_kv / lmcache_retrieve_kv gather and scatter with torch indexing (LLM_Engine.rst:91-109).
+        The codec kernels read (encode) and write (decode) the rows directly; token i of the view is row
+        slot_mapping[i]."""
+        L = len(kv_caches)
+        if L == 0:
+            raise ValueError("Empty kv_caches")
+        if slot_mapping.dtype != torch.int64 or not slot_mapping.is_cuda or slot_mapping.dim() != 1:
+            raise ValueError("slot_mapping must be a 1-D int64 CUDA tensor")
+        slot_mapping = slot_mapping.contiguous()
+        ref = kv_caches[0][0]
+        if not ref.is_cuda:
+            raise RuntimeError("KV caches must live on a CUDA device (no CPU fallback)")
+        keep = [slot_mapping]
+        ptrs = (ctypes.c_void_p * (2 * L))()
+        for l, (k, v) in enumerate(kv_caches):
+            for kvi, t in ((0, k), (1, v)):
+                if t.shape != ref.shape or t.dtype != ref.dtype or t.device != ref.device or t.stride() != ref.stride():
+                    raise ValueError("all K/V caches must share shape, strides, dtype and device")
+                if not t.is_contiguous():
+                    raise ValueError("paged K/V caches must be contiguous (they are written in place)")
+                keep.append(t)
+                ptrs[kvi * L + l] = t.data_ptr()
+        H, D = ref.shape[-2], ref.shape[-1]
+        d = N.KvDesc()
+        d.base = None
+        d.planes = ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p))
+        d.sL = d.sKV = 0
+        d.sT, d.sH = H * D, D
+        d.L, d.H, d.D = L, H, D
+        d.dtype = KvView._code(ref.dtype)
+        d.slot_map = slot_mapping.data_ptr()
+        return KvView(d, (keep, ptrs), slot_mapping.numel(), ref.device, ref.dtype, "vllm")
+
 
 def parse_header(buf) -> N.Header:
     """Validate and return the 64-byte header of a B2KV container (bytes / bytearray / memoryview)."""

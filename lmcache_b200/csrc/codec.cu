@@ -32,6 +32,7 @@ constexpr int TEMPW_SPLIT = 131;   // foreign CDF (chunk > 256 tokens): <= 16 bi
 struct EncParams {
     PlaneTable pt;
     int64_t sT, sH, tok_begin;
+    const int64_t* slot_map;         // paged KV: token i of the call lives in row slot_map[i] of every plane; NULL = row i
     int32_t L, H, D, C, dtype;
     int32_t n_chunks, chunk_tokens, last_chunk_tokens, tpp;   // tpp = tiles per plane
     int32_t tiles_full, tempw;                                 // tiles per full chunk; words per temp row
@@ -48,11 +49,19 @@ __device__ __forceinline__ int chunk_tokens_of(const EncParams& P, int j) {
     return j == P.n_chunks - 1 ? P.last_chunk_tokens : P.chunk_tokens;
 }
 
+// Row of a token inside its plane.  PAGED: the caller's slot mapping (vLLM's paged KV cache: row = block * block_size
+// + offset); every lane of a warp asks for the same token, so the lookup is one broadcast load that hits L1.
+template <bool PAGED>
+__device__ __forceinline__ int64_t tok_row(const int64_t* slot_map, int64_t tok) {
+    if constexpr (PAGED) return __ldg(slot_map + tok);
+    else return tok;
+}
+
 // ------------------------------------------------------------------------------------------ absmax
 // max1 = amax(|x|, channels) per (plane, token), kept in the input half dtype
 // (cachegen_encoder.py:54-55).  |x| ordering == integer ordering of (bits & 0x7fff); a NaN in the row
 // wins (pattern above inf), like torch.amax.  One warp per row, 128-bit loads when alignment allows.
-template <bool VEC>
+template <bool VEC, bool PAGED>
 __global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_tokens) {
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -60,7 +69,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_
     if (warp >= nrows) return;
     const int nl = (int)(warp / total_tokens);
     const int64_t T = warp % total_tokens;
-    const uint16_t* row = P.pt.p[nl] + (P.tok_begin + T) * P.sT;
+    const uint16_t* row = P.pt.p[nl] + tok_row<PAGED>(P.slot_map, P.tok_begin + T) * P.sT;
     uint32_t m = 0;
     if (VEC) {
         const int vec_per_head = P.D >> 3;
@@ -144,7 +153,7 @@ __device__ __forceinline__ bool decode_tile(const EncParams& P, uint32_t tile, T
 // Coder output goes to the tile's temp rows in global memory (sparse 32-bit stores, merged in L2); stream lengths go to
 // the container; the tile's byte total goes to tile_tot.  Compaction into the contiguous payload (collect_bytes in the
 // reference) is done by scan_kernel + compact_kernel afterwards, so no CTA ever waits on another one.
-template <bool FUSED, int DT>
+template <bool FUSED, int DT, bool PAGED>
 __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     // FUSED : symbol rows u32[CT][SYMW] | cdf rows u16[CT][33] (also the histogram) | fac[256] (later fl32(n/t)[257])
@@ -174,8 +183,10 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
     if (FUSED) for (int i = gt + tid; i < kGroup + 8; i += CT) fac[i] = 0.0f;      // padded slots of the last batch
 
     const int h = active ? c / P.D : 0;
-    const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0) * P.sT +
-                          (int64_t)h * P.sH + (active ? c - h * P.D : 0);
+    // first token of this tile in the call's token numbering; cbase = this stream's channel in row 0 of the plane
+    const int64_t tokabs = P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0;
+    const uint16_t* cbase = P.pt.p[nl] + (int64_t)h * P.sH + (active ? c - h * P.D : 0);
+    const uint16_t* src = cbase + (PAGED ? 0 : tokabs * P.sT);          // !PAGED: token tk is at src + tk * sT
     uint32_t* trow = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
     uint32_t cap = (uint32_t)P.tempw;
     // keep the row pointer and the capacity as plain register values: otherwise every flush re-derives the address
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
         for (int i = 0; i < kLp; ++i) crow[i] = 0;
         // pull the whole tile (gt token rows x 256 B) into L2 up front: one prefetch per 128-byte line, spread over
         // the CTA, so pass 1's loads pay L2 latency instead of a DRAM round trip per batch
-        {
+        if (!PAGED) {
             const int lines_per_tok = (ncols * 2 + 127) >> 7;
             const uint16_t* tile0 = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0) * P.sT +
                                     (int64_t)((ct * CT) / P.D) * P.sH + ((ct * CT) % P.D);
@@ -213,13 +224,19 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
             uint16_t xa[BT], xb[BT];
             auto load = [&](uint16_t (&x)[BT], int b) {
                 const int tk = b * BT;
-                const uint16_t* p = src + (int64_t)tk * s1;
-                if (tk + BT <= gt) {
+                if constexpr (PAGED) {
+                    const int64_t* sm = P.slot_map + tokabs + tk;
 #pragma unroll
-                    for (int k = 0; k < BT; ++k) x[k] = __ldg(p + k * s1);
+                    for (int k = 0; k < BT; ++k) x[k] = tk + k < gt ? __ldg(cbase + __ldg(sm + k) * s1) : (uint16_t)0;
                 } else {
+                    const uint16_t* p = src + (int64_t)tk * s1;
+                    if (tk + BT <= gt) {
 #pragma unroll
-                    for (int k = 0; k < BT; ++k) x[k] = tk + k < gt ? __ldg(p + k * s1) : (uint16_t)0;
+                        for (int k = 0; k < BT; ++k) x[k] = __ldg(p + k * s1);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BT; ++k) x[k] = tk + k < gt ? __ldg(p + k * s1) : (uint16_t)0;
+                    }
                 }
             };
             auto quantise = [&](const uint16_t (&x)[BT], int b) {
@@ -320,11 +337,11 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
             }
             EncState2 st;
             st.init();
-            const uint16_t* p = src;
-            for (int tk = 0; tk < gt; tk += 4, p += 4 * s1) {
+            for (int tk = 0; tk < gt; tk += 4) {
                 uint16_t xb[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) xb[k] = (tk + k < gt) ? __ldg(p + k * s1) : (uint16_t)0;
+                for (int k = 0; k < 4; ++k)
+                    xb[k] = (tk + k < gt) ? __ldg(cbase + tok_row<PAGED>(P.slot_map, tokabs + tk + k) * s1) : (uint16_t)0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (tk + k < gt) {
@@ -349,7 +366,7 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
 }
 
 // ------------------------------------------------------------------------------------------ cdf (chunks > 256 tokens)
-template <int DT>
+template <int DT, bool PAGED>
 __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* cnts = smem;                                        // CT * PAIRW counters
@@ -373,8 +390,8 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
 #pragma unroll
     for (int i = 0; i < PAIRW; ++i) prow[i] = 0u;
     const int h = active ? c / P.D : 0;
-    const uint16_t* src = P.pt.p[nl] + (P.tok_begin + (int64_t)j * P.chunk_tokens) * P.sT + (int64_t)h * P.sH +
-                          (active ? c - h * P.D : 0);
+    const int64_t tokabs = P.tok_begin + (int64_t)j * P.chunk_tokens;
+    const uint16_t* cbase = P.pt.p[nl] + (int64_t)h * P.sH + (active ? c - h * P.D : 0);
     for (int tok0 = 0; tok0 < t; tok0 += kGroup) {
         const int gt = min(kGroup, t - tok0);
         __syncthreads();
@@ -385,7 +402,7 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
                 uint16_t xb[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    xb[k] = (tk + k < gt) ? __ldg(src + (int64_t)(tok0 + tk + k) * P.sT) : (uint16_t)0;
+                    xb[k] = (tk + k < gt) ? __ldg(cbase + tok_row<PAGED>(P.slot_map, tokabs + tok0 + tk + k) * P.sT) : (uint16_t)0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (tk + k < gt) prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq)] += 1u;
@@ -524,7 +541,7 @@ __global__ void finalize_kernel(EncParams P) {
     const Layout lo = make_layout(P.L, P.C, t);
     b200kv_header* hd = reinterpret_cast<b200kv_header*>(P.out + (int64_t)j * P.out_stride);
     hd->magic = B200KV_MAGIC;
-    hd->version = B200KV_VERSION;
+    hd->version = B200KV_CONTAINER_VERSION;
     hd->L = P.L; hd->H = P.H; hd->D = P.D;
     hd->ntokens = t;
     hd->ngroups = lo.ngroups;
@@ -546,6 +563,7 @@ struct DecChunk {
 struct DecParams {
     PlaneTable pt;               // destination planes; maxq = C_l = bins // 2 - 1
     int64_t sT, sH;
+    const int64_t* slot_map;     // paged destination: token i lives in row slot_map[i]; NULL = row i
     int32_t L, H, D, C, out_dtype, max_dtype, n_chunks, tpp, tiles_max;
     const DecChunk* chunks;      // device
     unsigned long long* tile_base;   // [n_chunks][tiles_max]: tile sums, then exclusive prefix
@@ -629,9 +647,10 @@ __device__ __forceinline__ uint16_t out_half(float v, int dt) {
 }
 
 // per-thread decode loop: one stream, gt symbols, straight to the destination layout.
-template <int OUT_DT, int NSTEPS>
+// PAGED: dst is the stream's channel in row 0 of the plane and `slots` points at the group's first slot-map entry.
+template <int OUT_DT, int NSTEPS, bool PAGED>
 __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint32_t* erow, const float* lut,
-                                              const float* mx, uint16_t* dst, uint32_t sT, int gt) {
+                                              const float* mx, uint16_t* dst, uint32_t sT, int gt, const int64_t* slots) {
     const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(my_bytes) & 3u);
     WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip), 0u, 0u};
     src.prime();
@@ -640,16 +659,24 @@ __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uin
     uint16_t* d = dst;                                      // running pointer: one 64-bit add per token
     // dec_symbol2 returns 4 * symbol = the byte offset into the fp32 LUT
     auto lut_at = [&](uint32_t s4) { return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lut) + s4); };
-    for (int i = 0; i < gt - 1; ++i, d += sT)
-        *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]), OUT_DT);
-    *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]), OUT_DT);
+    if constexpr (PAGED) {
+        for (int i = 0; i < gt - 1; ++i)
+            dst[__ldg(slots + i) * (int64_t)sT] =
+                out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]), OUT_DT);
+        dst[__ldg(slots + gt - 1) * (int64_t)sT] =
+            out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]), OUT_DT);
+    } else {
+        for (int i = 0; i < gt - 1; ++i, d += sT)
+            *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]), OUT_DT);
+        *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]), OUT_DT);
+    }
 }
 
 // One tile = CT streams of one (chunk, group, plane).  Only the CDF rows (66 B per stream, contiguous in the
 // container so they are staged with one coalesced copy), the row maxima and a 32-entry dequantisation LUT live in
 // shared memory (~10 KB per CTA), so many CTAs stay resident and hide the serial latency of each stream's coder.
 // Symbols are dequantised and stored straight into the destination layout (no uint8 / fp32 intermediates in HBM).
-template <int OUT_DT>
+template <int OUT_DT, bool PAGED>
 __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* tab = smem;                                                            // CT * 33 words: cdf << 16 (rows of 33, odd)
@@ -696,10 +723,11 @@ __global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
     if (!active) return;
     const uint32_t* erow = tab + tid * kLp;
     const int h = c / P.D;
-    uint16_t* dst = const_cast<uint16_t*>(P.pt.p[nl]) + (dc.dst_tok + tok0) * P.sT + (int64_t)h * P.sH + (c - h * P.D);
-    // a group spans <= 256 token rows: 255 * sT must fit the 32-bit element offset used inside the loop
-    if (cq <= 7.0f) decode_stream<OUT_DT, 4>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt);   // <= 16 bins: symbols 0..14
-    else decode_stream<OUT_DT, 5>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt);
+    uint16_t* dst = const_cast<uint16_t*>(P.pt.p[nl]) + (PAGED ? 0 : (dc.dst_tok + tok0) * P.sT) + (int64_t)h * P.sH +
+                    (c - h * P.D);
+    const int64_t* slots = PAGED ? P.slot_map + dc.dst_tok + tok0 : nullptr;
+    if (cq <= 7.0f) decode_stream<OUT_DT, 4, PAGED>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);   // <= 16 bins: symbols 0..14
+    else decode_stream<OUT_DT, 5, PAGED>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -817,6 +845,8 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
                "out / out_stride must be 16-byte aligned");
     B2_REQUIRE(tok_begin >= 0, "tok_begin must be >= 0");
     P.sT = kv->sT; P.sH = kv->sH; P.tok_begin = tok_begin;
+    P.slot_map = kv->slot_map;
+    const bool paged = kv->slot_map != nullptr;
     P.L = kv->L; P.H = kv->H; P.D = kv->D; P.C = kv->H * kv->D; P.dtype = kv->dtype;
     P.n_chunks = n_chunks; P.chunk_tokens = chunk_tokens; P.last_chunk_tokens = last_chunk_tokens;
     P.tpp = tiles_per_plane(P.C);
@@ -854,34 +884,47 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
         const int64_t blocks = (rows + 7) / 8;
         B2_REQUIRE(blocks < (1ll << 31), "too many rows in one call");
         ProfScope prof(kProfAbsmax, stream);
-        if (vec) absmax_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
-        else absmax_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        if (vec && !paged) absmax_kernel<true, false><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        else if (vec) absmax_kernel<true, true><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        else if (!paged) absmax_kernel<false, false><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
+        else absmax_kernel<false, true><<<(unsigned)blocks, 256, 0, stream>>>(P, total_tokens);
         B2_CHECK_CUDA(cudaGetLastError());
     }
     // 2) encode (streams -> temp rows, lengths, tile totals)
     const size_t smem_fused = (size_t)(((CT * SYMW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + 8) * 4;
     const size_t smem_split = (size_t)(((CT * PAIRW + 3) & ~3) + kGroup + 4) * 4;
     const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
-#define B2_LAUNCH_ENC(FUSED, DT, SMEM)                                                                     \
+#define B2_LAUNCH_ENC(FUSED, DT, PAGED, SMEM)                                                              \
     do {                                                                                                   \
-        B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<FUSED, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)(SMEM)));                                                  \
-        encode_kernel<FUSED, DT><<<(unsigned)n_tiles, CT, (SMEM), stream>>>(P);                            \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<FUSED, DT, PAGED>,                                \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));     \
+        encode_kernel<FUSED, DT, PAGED><<<(unsigned)n_tiles, CT, (SMEM), stream>>>(P);                     \
+    } while (0)
+#define B2_LAUNCH_ENC2(FUSED, SMEM)                                                                        \
+    do {                                                                                                   \
+        if (P.dtype == B200KV_DT_BF16) { if (paged) B2_LAUNCH_ENC(FUSED, 0, true, SMEM); else B2_LAUNCH_ENC(FUSED, 0, false, SMEM); } \
+        else { if (paged) B2_LAUNCH_ENC(FUSED, 1, true, SMEM); else B2_LAUNCH_ENC(FUSED, 1, false, SMEM); } \
     } while (0)
     if (fused) {
         ProfScope prof(kProfEncode, stream);
-        if (P.dtype == B200KV_DT_BF16) B2_LAUNCH_ENC(true, 0, smem_fused); else B2_LAUNCH_ENC(true, 1, smem_fused);
+        B2_LAUNCH_ENC2(true, smem_fused);
     } else {
         const unsigned cdf_blocks = (unsigned)((int64_t)n_chunks * per_group);
         {
             ProfScope prof(kProfCdf, stream);
-            if (P.dtype == B200KV_DT_BF16) cdf_kernel<0><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
-            else cdf_kernel<1><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+            if (P.dtype == B200KV_DT_BF16) {
+                if (paged) cdf_kernel<0, true><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+                else cdf_kernel<0, false><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+            } else {
+                if (paged) cdf_kernel<1, true><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+                else cdf_kernel<1, false><<<cdf_blocks, CT, smem_cdf, stream>>>(P);
+            }
         }
         B2_CHECK_CUDA(cudaGetLastError());
         ProfScope prof(kProfEncode, stream);
-        if (P.dtype == B200KV_DT_BF16) B2_LAUNCH_ENC(false, 0, smem_split); else B2_LAUNCH_ENC(false, 1, smem_split);
+        B2_LAUNCH_ENC2(false, smem_split);
     }
+#undef B2_LAUNCH_ENC2
 #undef B2_LAUNCH_ENC
     B2_CHECK_CUDA(cudaGetLastError());
     // 3) compaction (collect_bytes) + headers + sizes
@@ -909,6 +952,7 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     B2_REQUIRE(max_dtype == B200KV_DT_BF16 || max_dtype == B200KV_DT_FP16, "bad max_dtype");
     B2_REQUIRE(dst->sT > 0 && dst->sT < (1ll << 23), "destination token stride out of range");
     P.sT = dst->sT; P.sH = dst->sH;
+    P.slot_map = dst->slot_map;
     P.L = dst->L; P.H = dst->H; P.D = dst->D; P.C = dst->H * dst->D;
     P.out_dtype = dst->dtype; P.max_dtype = max_dtype; P.n_chunks = n_chunks;
     P.tpp = tiles_per_plane(P.C);
@@ -958,13 +1002,15 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     const size_t smem = (size_t)(CT * kLp + kGroup + 32) * 4;
     dim3 grid((unsigned)tiles_max, (unsigned)n_chunks);
     ProfScope prof(kProfDecode, stream);
-    if (P.out_dtype == B200KV_DT_BF16) {
-        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        decode_kernel<0><<<grid, CT, smem, stream>>>(P);
-    } else {
-        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        decode_kernel<1><<<grid, CT, smem, stream>>>(P);
-    }
+#define B2_LAUNCH_DEC(DT, PAGED)                                                                                       \
+    do {                                                                                                               \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<DT, PAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                           (int)smem));                                                                \
+        decode_kernel<DT, PAGED><<<grid, CT, smem, stream>>>(P);                                                       \
+    } while (0)
+    if (P.out_dtype == B200KV_DT_BF16) { if (P.slot_map) B2_LAUNCH_DEC(0, true); else B2_LAUNCH_DEC(0, false); }
+    else { if (P.slot_map) B2_LAUNCH_DEC(1, true); else B2_LAUNCH_DEC(1, false); }
+#undef B2_LAUNCH_DEC
     B2_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

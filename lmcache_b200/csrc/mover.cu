@@ -66,6 +66,7 @@ static int launch_pack(bool pack, const b200kv_kv_desc* kv, int64_t tok_begin, i
                        cudaStream_t stream) {
     PackParams P;
     B2_REQUIRE(kv != nullptr && kv->L > 0 && 2 * kv->L <= B200KV_MAX_PLANES, "bad kv descriptor");
+    B2_REQUIRE(kv->slot_map == nullptr, "pack / unpack do not take a paged (slot_map) descriptor");
     float bins[B200KV_MAX_PLANES];
     for (int i = 0; i < B200KV_MAX_PLANES; ++i) bins[i] = 32.0f;   // unused by pack/unpack; keeps the table valid
     if (int rc = make_plane_table(kv, bins, bins, &P.pt)) return rc;

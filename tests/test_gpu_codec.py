@@ -153,6 +153,63 @@ def test_multichunk_ragged_vs_oracle(codec, T, cs, source):
     assert np.array_equal(_tensor_bits(out).reshape(L, 2, T, C), want)
 
 
+@pytest.mark.parametrize("T,cs,dt", [(600, 256, 0), (300, 64, 1), (700, 512, 0)])
+def test_paged_kv_cache_in_place(codec, T, cs, dt):
+    """vLLM-style paged KV cache + slot_mapping (KvView.from_paged): encoding the scattered rows gives the very
+    container the contiguous gather gives, and decoding scatters straight into the cache rows -- no pack / unpack
+    copies.  Fused (chunk <= 256) and split (chunk 512) kernels, bf16 and fp16, ragged tails."""
+    from lmcache_b200.codec import KvView
+    L, H, D, bs, nblocks = 4, 3, 80, 16, 64               # C = 240: a full tile + a partial one
+    C = H * D
+    g = torch.Generator().manual_seed(T + cs)
+    slots = torch.randperm(nblocks * bs, generator=g)[:T].to(torch.int64)          # token i -> cache row slots[i]
+    bits = O.synth_kv_bits(L, T, C, seed=5 * T + cs)
+    tdt = torch.bfloat16 if dt == 0 else torch.float16
+    dense = _bits_to_tensor(bits, 0).float().to(tdt).reshape(L, 2, T, H, D).cuda()
+    bits = _tensor_bits(dense).reshape(L, 2, T, C)
+    caches = []
+    for l in range(L):
+        k = torch.full((nblocks, bs, H, D), 7.0, dtype=tdt, device="cuda")
+        v = torch.full((nblocks, bs, H, D), -7.0, dtype=tdt, device="cuda")
+        k.view(-1, H, D)[slots.cuda()] = dense[l, 0]
+        v.view(-1, H, D)[slots.cuda()] = dense[l, 1]
+        caches.append((k, v))
+    paged = KvView.from_paged(caches, slots.cuda())
+    assert paged.ntokens == T
+    raws_paged = codec.encode_to_host(paged, 0, T, cs)
+    raws_dense = codec.encode_to_host(KvView.from_blob(dense, "vllm"), 0, T, cs)
+    for j, (a, b) in enumerate(zip(raws_paged, raws_dense)):
+        tj = min(cs, T - j * cs)
+        for u, v in zip(_sections(a, L, H, D, tj), _sections(b, L, H, D, tj)):
+            assert np.array_equal(u, v), j
+    # and against the oracle
+    kb, vb = O.make_bins(MODEL)
+    n_chunks = (T + cs - 1) // cs
+    for j, raw in enumerate(raws_paged):
+        t0, t1 = j * cs, min(T, (j + 1) * cs)
+        enc = O.encode_chunk(bits[:, :, t0:t1], dt, kb, vb)
+        cdf, maxes, lengths, payload = _sections(raw, L, H, D, t1 - t0)
+        assert np.array_equal(cdf, enc["cdf"]) and np.array_equal(maxes, enc["maxes"]), j
+        assert np.array_equal(lengths, np.stack([ln for _, ln, _ in enc["groups"]])), j
+        assert np.array_equal(payload, np.concatenate([b_ for b_, _, _ in enc["groups"]])), j
+    # decode into a fresh paged cache through a different mapping; untouched rows must stay untouched
+    slots2 = torch.randperm(nblocks * bs, generator=g)[:T].to(torch.int64)
+    caches2 = [(torch.full((nblocks, bs, H, D), 3.0, dtype=tdt, device="cuda"),
+                torch.full((nblocks, bs, H, D), 3.0, dtype=tdt, device="cuda")) for _ in range(L)]
+    codec.decode(raws_paged, KvView.from_paged(caches2, slots2.cuda()), [j * cs for j in range(n_chunks)])
+    torch.cuda.synchronize()
+    want = np.concatenate([O.decode_chunk(O.encode_chunk(bits[:, :, j * cs:min(T, (j + 1) * cs)], dt, kb, vb), dt, kb, vb, dt)
+                           for j in range(n_chunks)], axis=2)                     # [L,2,T,C]
+    mask = torch.ones(nblocks * bs, dtype=torch.bool)
+    mask[slots2] = False
+    for l in range(L):
+        for kvi in range(2):
+            flat = caches2[l][kvi].view(-1, H, D)
+            got = _tensor_bits(flat[slots2.cuda()]).reshape(T, C)
+            assert np.array_equal(got, want[l, kvi]), (l, kvi)
+            assert bool((flat[mask.cuda()] == 3.0).all()), "decode wrote outside the mapped rows"
+
+
 def test_tok_begin_and_device_container_decode(codec):
     """Encoding a token sub-range, and decoding straight from the device staging buffer (no host hop)."""
     from lmcache_b200.codec import KvView
