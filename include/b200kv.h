@@ -52,8 +52,8 @@ typedef struct b200kv_kv_desc {
                                 * lmcache_store_kv / lmcache_retrieve_kv, docs LLM_Engine.rst:91-109): token i of the call
                                 * (tok_begin + i for encode, dst_tok[j] + i for decode) lives in row slot_map[i] of every
                                 * plane, i.e. `tok` in the address formula above is replaced by slot_map[tok].  The codec
-                                * kernels gather / scatter through it, so the paged cache is read and written in place.
-                                * Ignored by b200kv_pack_chunks / b200kv_unpack_chunks (must be NULL there). */
+                                * and pack / unpack kernels gather / scatter through it, so the paged cache is read and
+                                * written in place. */
 } b200kv_kv_desc;
 
 /* Wire container of one encoded chunk ("B2KV" v1).  All sections 16-byte aligned, little-endian.

@@ -229,6 +229,91 @@ class LMCacheEngine:
         ret_mask[num_skip_tok + retrieved_token_count:] = False
         return ret, ret_mask
 
+    # ------------------------------------------------------------------ paged KV caches, in place
+    @_lmcache_nvtx_annotate
+    @torch.no_grad()
+    def store_paged(self, tokens: torch.Tensor, kv_caches, slot_mapping: torch.Tensor, skip_existing=True,
+                    blocking=True) -> None:
+        """store() for a vLLM paged KV cache: token i's K/V live in row slot_mapping[i] of every layer's
+        (key_cache, value_cache) [num_blocks, block_size, H, D].  What lmcache-vllm's lmcache_store_kv does with a
+        torch gather per layer + store() (LLM_Engine.rst:91-99); here the backend's kernels read the cache rows
+        directly (cachegen: quantise + code from the rows; local tiers: one gather straight into the chunk blobs)."""
+        if self.metadata.fmt != "vllm":
+            raise ValueError(f"paged KV caches use the vllm layout, engine fmt is {self.metadata.fmt}")
+        assert len(tokens.shape) == 1, f"Invalid shape of tokens: {tokens.shape}"
+        assert len(kv_caches) > 0, "Empty kv_caches"
+        assert len(tokens) == slot_mapping.numel(), "Number of slots does not match the input tokens"
+        if not self._fast_path():
+            flat = [(k.reshape(-1, k.shape[-2], k.shape[-1]), v.reshape(-1, v.shape[-2], v.shape[-1])) for k, v in kv_caches]
+            idx = slot_mapping.to(flat[0][0].device)
+            return self.store(tokens, tuple((k[idx], v[idx]) for k, v in flat), skip_existing, blocking)
+        fmt = "vllm"
+        chunk_hashes = self._prefix_hash(tokens)
+        start_chunk_idx = 0
+        if skip_existing:
+            start_chunk_idx = len(chunk_hashes)
+            for i, h in enumerate(chunk_hashes):
+                if not self.engine_.contains(self._make_key(h, fmt)):
+                    start_chunk_idx = i
+                    break
+        if start_chunk_idx < len(chunk_hashes):
+            view = KvView.from_paged(kv_caches, slot_mapping.cuda())
+            self._geom = (view.L, view.H, view.D, view.dtype)
+            keys = [self._make_key(h, fmt) for h in chunk_hashes[start_chunk_idx:]]
+            self.engine_.put_kv_chunks(keys, view, start_chunk_idx * self.chunk_size, self.chunk_size, blocking=blocking)
+
+    @_lmcache_nvtx_annotate
+    @torch.no_grad()
+    def retrieve_paged(self, tokens: torch.Tensor, kv_caches, slot_mapping: torch.Tensor,
+                       mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """retrieve() straight into a paged KV cache: the longest cached prefix of `tokens` (optionally only the
+        suffix selected by `mask`) is written to rows slot_mapping[i]; returns ret_mask as retrieve() does.  Rows of
+        tokens that are not retrieved -- misses and the masked-off prefix -- are left untouched."""
+        if self.metadata.fmt != "vllm":
+            raise ValueError(f"paged KV caches use the vllm layout, engine fmt is {self.metadata.fmt}")
+        assert len(tokens) == slot_mapping.numel(), "Number of slots does not match the input tokens"
+        flat = [(k.reshape(-1, k.shape[-2], k.shape[-1]), v.reshape(-1, v.shape[-2], v.shape[-1])) for k, v in kv_caches]
+        dev = flat[0][0].device
+        slots = slot_mapping.to(dev)
+        if not self._fast_path():
+            kv, ret_mask = self.retrieve(tokens, mask)
+            if len(kv) > 0:
+                idx = slots[ret_mask.to(dev)]
+                for (kc, vc), (k, v) in zip(flat, kv):
+                    kc[idx] = k.to(kc.dtype)
+                    vc[idx] = v.to(vc.dtype)
+            return ret_mask
+        cs = self.chunk_size
+        num_skip_tok = int(len(mask) - torch.sum(mask)) if mask is not None else 0
+        num_skip_chunk = num_skip_tok // cs
+        extra = num_skip_tok - num_skip_chunk * cs
+        ret_mask = torch.ones_like(tokens, dtype=torch.bool)
+        ret_mask[:num_skip_tok] = False
+        keys = [self._make_key(h, "vllm") for h in self._prefix_hash(tokens, num_skip_chunk)]
+        base = num_skip_chunk * cs
+        view = KvView.from_paged(kv_caches, slots[base:])
+        got_chunks, first = 0, 0
+        if extra > 0 and keys:
+            # the first chunk straddles the mask: decode it next to the cache and scatter only its unmasked tail
+            t0 = min(cs, len(tokens) - base)
+            tmp = torch.empty((view.L, 2, t0, view.H, view.D), dtype=view.dtype, device=dev)
+            if self.engine_.get_kv_into(keys[:1], KvView.from_blob(tmp, "vllm"), 0, cs) == 0:
+                ret_mask[:] = False
+                return ret_mask
+            idx = slots[base + extra: base + t0]
+            for l, (kc, vc) in enumerate(flat):
+                kc[idx] = tmp[l, 0, extra:]
+                vc[idx] = tmp[l, 1, extra:]
+            got_chunks, first = 1, 1
+        if len(keys) > first:
+            got_chunks += self.engine_.get_kv_into(keys[first:], view, first * cs, cs)
+        got = min(base + got_chunks * cs, len(tokens))
+        if got <= num_skip_tok:
+            ret_mask[:] = False
+        else:
+            ret_mask[got:] = False
+        return ret_mask
+
     # ------------------------------------------------------------------ B200-native fast paths
     def _fast_path(self) -> bool:
         f = getattr(self.engine_, "supports_kv_view", None)

@@ -21,6 +21,7 @@ namespace b200kv {
 struct PackParams {
     PlaneTable pt;
     int64_t sT, sH, tok_begin;
+    const int64_t* slot_map;       // paged KV: token i lives in row slot_map[i]; NULL = row i
     int32_t L, H, D, n_chunks, chunk_tokens, last_chunk_tokens, hf_layout;
     uint8_t* chunks;
     int64_t chunk_stride_bytes;
@@ -51,7 +52,9 @@ __global__ void __launch_bounds__(256) pack_kernel(PackParams P) {
         const int v = (int)(r - (int64_t)h * vph);
         const int l = lk >> 1, kv = lk & 1;
         const uint16_t* plane = P.pt.p[kv * P.L + l];
-        const int64_t src_off = (P.tok_begin + j * P.chunk_tokens + tok) * P.sT + (int64_t)h * P.sH + (int64_t)v * VEC;
+        int64_t row = P.tok_begin + j * P.chunk_tokens + tok;
+        if (P.slot_map) row = __ldg(P.slot_map + row);       // consecutive threads share the token: broadcast, L1 hit
+        const int64_t src_off = row * P.sT + (int64_t)h * P.sH + (int64_t)v * VEC;
         int64_t dst_off;   // in halfs, inside the chunk
         if (P.hf_layout) dst_off = (((int64_t)lk * P.H + h) * t + tok) * P.D + (int64_t)v * VEC;
         else dst_off = (((int64_t)lk * t + tok) * P.H + h) * P.D + (int64_t)v * VEC;
@@ -66,7 +69,6 @@ static int launch_pack(bool pack, const b200kv_kv_desc* kv, int64_t tok_begin, i
                        cudaStream_t stream) {
     PackParams P;
     B2_REQUIRE(kv != nullptr && kv->L > 0 && 2 * kv->L <= B200KV_MAX_PLANES, "bad kv descriptor");
-    B2_REQUIRE(kv->slot_map == nullptr, "pack / unpack do not take a paged (slot_map) descriptor");
     float bins[B200KV_MAX_PLANES];
     for (int i = 0; i < B200KV_MAX_PLANES; ++i) bins[i] = 32.0f;   // unused by pack/unpack; keeps the table valid
     if (int rc = make_plane_table(kv, bins, bins, &P.pt)) return rc;
@@ -76,6 +78,7 @@ static int launch_pack(bool pack, const b200kv_kv_desc* kv, int64_t tok_begin, i
     const int64_t chunk_bytes = 2ll * kv->L * 2 * chunk_tokens * kv->H * kv->D;
     B2_REQUIRE(chunk_stride_bytes >= chunk_bytes || n_chunks == 1, "chunk_stride_bytes too small");
     P.sT = kv->sT; P.sH = kv->sH; P.tok_begin = tok_begin;
+    P.slot_map = kv->slot_map;
     P.L = kv->L; P.H = kv->H; P.D = kv->D;
     P.n_chunks = n_chunks; P.chunk_tokens = chunk_tokens; P.last_chunk_tokens = last_chunk_tokens;
     P.hf_layout = hf_layout;

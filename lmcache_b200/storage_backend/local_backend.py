@@ -162,6 +162,8 @@ class LMCLocalBackend(LMCBackendInterface):
         no torch.cat."""
         fmt_hf = getattr(dst, "fmt", "vllm") == "huggingface"
         blob = dst.blob
+        if blob is None:
+            return self._get_kv_scatter(keys, dst, dst_tok0, chunk_size)
         n = 0
         with torch.cuda.device(blob.device):
             stream = torch.cuda.current_stream()
@@ -194,6 +196,34 @@ class LMCLocalBackend(LMCBackendInterface):
                     ev.record(stream)
                     self._inflight = [(e, h) for e, h in self._inflight if not e.query()]
                     self._inflight.append((ev, val.host))
+                n += 1
+        return n
+
+    def _get_kv_scatter(self, keys, dst, dst_tok0: int, chunk_size: int) -> int:
+        """get_kv_into for destinations that are not one blob (the engine's 2L tensors, or a paged KV cache with its
+        slot mapping): each hit chunk is scattered by ONE b200kv_unpack_chunks launch (host tier: after one upload)."""
+        n = 0
+        hf = getattr(dst, "fmt", "vllm") == "huggingface"      # chunk blobs carry the engine's layout
+        with torch.cuda.device(dst.device):
+            stream = torch.cuda.current_stream()
+            for i, key in enumerate(keys):
+                val = self.dict.get(key, None)
+                if val is None:
+                    break
+                if isinstance(val, _HostEntry):
+                    val.wait()
+                    src = val.host.to(dst.device, non_blocking=True)
+                else:
+                    src = val if val.is_cuda else val.cuda()
+                t = src.shape[3] if hf else src.shape[2]
+                tok = dst_tok0 + i * chunk_size
+                if tok + t > dst.ntokens or src.dtype != dst.dtype:
+                    break
+                src = src.contiguous()
+                N.check(N.lib().b200kv_unpack_chunks(ctypes.c_void_p(src.data_ptr()), src.numel() * src.element_size(), 1,
+                                                     t, t, 1 if hf else 0, ctypes.byref(dst.desc), tok,
+                                                     stream.cuda_stream), "unpack_chunks")
+                src.record_stream(stream)
                 n += 1
         return n
 

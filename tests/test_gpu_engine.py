@@ -390,3 +390,79 @@ def test_remote_cachegen_matches_reference_chain(fmt, pipelined, lmserver, autor
     tdim = 2 if fmt == "vllm" else 3
     assert torch.equal(torch.stack([torch.stack(p) for p in r3]).view(torch.int16),
                        want.narrow(tdim, 300, T - 300).contiguous().view(torch.int16))
+
+
+# ---------------------------------------------------------------- paged KV caches in place
+def _paged_caches(kv, slots, nrows, fill):
+    """scatter the dense per-layer (K, V) [T,H,D] into fresh paged caches [nrows/16, 16, H, D]"""
+    out = []
+    for k, v in kv:
+        kc = torch.full((nrows // 16, 16) + tuple(k.shape[1:]), fill, dtype=k.dtype, device="cuda")
+        vc = torch.full((nrows // 16, 16) + tuple(k.shape[1:]), fill, dtype=k.dtype, device="cuda")
+        kc.view(-1, *k.shape[1:])[slots] = k
+        vc.view(-1, *k.shape[1:])[slots] = v
+        out.append((kc, vc))
+    return out
+
+
+@pytest.mark.parametrize("backend", ["cuda", "cpu", "lm-cachegen", "lm-torch"])
+def test_engine_paged_store_and_retrieve(backend, lmserver, autorelease):
+    """store_paged / retrieve_paged against a scattered cache give exactly what store / retrieve give on the
+    gathered tensors: same chunks in the store, same values in the mapped rows, unmapped / unretrieved rows untouched;
+    prefix hit, miss and a suffix mask that is not chunk aligned."""
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    model = "mistralai/Mistral-7B-Instruct-v0.2"
+    T, cs, nrows = 700, 256, 1024
+    L, H, D = (32, 8, 128) if backend == "lm-cachegen" else (4, 2, 64)
+    tokens = generate_tokens(T, "cuda")
+    kv = generate_kv_cache(T, "vllm", "cuda", L, H, D)
+    g = torch.Generator().manual_seed(3)
+    slots = torch.randperm(nrows, generator=g)[:T].cuda()
+    caches = _paged_caches(kv, slots, nrows, 9.0)
+    if backend.startswith("lm-"):
+        cfg = LMCacheEngineConfig(cs, None, lmserver, backend[3:], False, False)
+    else:
+        cfg = LMCacheEngineConfig.from_legacy(chunk_size=cs, backend=backend)
+    name = model if backend == "lm-cachegen" else "paged_" + backend
+    eng = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", name)))
+    eng.store_paged(tokens, caches, slots)
+    dense, m = eng.retrieve(tokens)                       # what the store now holds, as the dense API sees it
+    assert torch.sum(m) == T
+    ref = autorelease(LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=cs, backend="cuda"), dumb_metadata("vllm", name)))
+    if backend == "lm-cachegen":                          # lossy codec: compare with a dense store through the same codec
+        cfg2 = LMCacheEngineConfig(cs, None, lmserver, "cachegen", False, False)
+        ref = autorelease(LMCacheEngine(cfg2, dumb_metadata("vllm", model)))
+    ref.store(tokens, kv, skip_existing=False)            # same keys: overwrites with the dense-encoded chunks
+    want, _ = ref.retrieve(tokens)
+    for (a, b), (c, d) in zip(dense, want):
+        assert torch.equal(a.view(torch.int16), c.view(torch.int16)) and torch.equal(b.view(torch.int16), d.view(torch.int16))
+    # retrieve into a fresh cache with another mapping: longer query -> prefix hit of the 2 full chunks + tail chunk miss
+    slots2 = torch.randperm(nrows, generator=g)[:T + 100].cuda()
+    caches2 = [(torch.full_like(k, 5.0), torch.full_like(v, 5.0)) for k, v in caches]
+    q = torch.cat([tokens, generate_tokens(100, "cuda")])
+    m2 = eng.retrieve_paged(q, caches2, slots2)
+    assert int(torch.sum(m2)) == 512 and bool(m2[:512].all())
+    untouched = torch.ones(nrows, dtype=torch.bool, device="cuda")
+    untouched[slots2[:512]] = False
+    for l, (kc, vc) in enumerate(caches2):
+        for kvi, c in enumerate((kc, vc)):
+            flat = c.view(-1, H, D)
+            assert torch.equal(flat[slots2[:512]].view(torch.int16), want[l][kvi][:512].view(torch.int16)), (l, kvi)
+            assert bool((flat[untouched] == 5.0).all())
+    # suffix mask (300 tokens skipped, not chunk aligned) on the exact sequence: rows of tokens < 300 stay as they are
+    caches3 = [(torch.full_like(k, 5.0), torch.full_like(v, 5.0)) for k, v in caches]
+    mask = torch.ones(T, dtype=torch.bool)
+    mask[:300] = False
+    m3 = eng.retrieve_paged(tokens, caches3, slots, mask)
+    assert int(torch.sum(m3)) == T - 300 and int(m3.nonzero()[0]) == 300
+    untouched = torch.ones(nrows, dtype=torch.bool, device="cuda")
+    untouched[slots[300:]] = False
+    for l, (kc, vc) in enumerate(caches3):
+        for kvi, c in enumerate((kc, vc)):
+            flat = c.view(-1, H, D)
+            assert torch.equal(flat[slots[300:]].view(torch.int16), want[l][kvi][300:].view(torch.int16)), (l, kvi)
+            assert bool((flat[untouched] == 5.0).all())
+    # total miss
+    m4 = eng.retrieve_paged(generate_tokens(T, "cuda") + 20000, caches3, slots)
+    assert int(torch.sum(m4)) == 0
