@@ -91,6 +91,17 @@ B2_HD uint32_t bfind32(uint32_t x) {
 #endif
 }
 
+// (1 << p) - 1 for 0 <= p <= 31: one BMSK, no constant register
+B2_HD uint32_t low_mask(uint32_t p) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(p));
+    return r;
+#else
+    return (1u << p) - 1u;
+#endif
+}
+
 // (x << n) | ones(n), 0 <= n <= 31 : one funnel shift with an all-ones low word
 B2_HD uint32_t shl_fill1(uint32_t x, uint32_t n) { return funnel_l(0xFFFFFFFFu, x, n); }
 
@@ -381,7 +392,7 @@ B2_HD void enc_symbol2(EncState2& st, uint32_t c_lo, uint32_t width, uint32_t* r
     // k = n + m in one go: p = position of the first differing bit (n = 31 - p agreed bits above it); below it the
     // E3 run continues while x has 1 and h has 0, so k = 30 - (position of the first bit below p with ~x | h)
     const uint32_t p = bfind32((x ^ h) | 1u);
-    const uint32_t f = ((~x) | h) & ~(0xFFFFFFFFu << p);
+    const uint32_t f = ((~x) | h) & low_mask(p);
     const uint32_t k = 30u - bfind32(f);                         // <= 18: the coded interval is >= 2^14 wide
     st.x = x << k;
     st.rng = shl_fill1(h, k) - st.x;
@@ -612,7 +623,7 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
     const uint32_t x = st.x + plo;
     const uint32_t h = st.x + phi - 1u;
     const uint32_t p = bfind32((x ^ h) | 1u);
-    const uint32_t f = ((~x) | h) & ~(0xFFFFFFFFu << p);
+    const uint32_t f = ((~x) | h) & low_mask(p);
     const uint32_t k = 30u - bfind32(f);                         // <= 18 for 16-bit CDFs
     const uint32_t t = funnel_l(st.nxt, st.cur, st.pos);         // the next 32 unread stream bits
     st.off = funnel_l(t, off - plo, k);                          // ((off - plo) << k) | next k bits

@@ -645,6 +645,12 @@ __device__ __forceinline__ uint16_t out_half(float v, int dt) {
     // hardware RNE converts (NaN payloads are canonicalised; every finite / inf value matches torch's cast)
     return dt ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
+// typed store of the converted value (the 16-bit result goes straight from F2FP to STG.U16)
+template <int OUT_DT>
+__device__ __forceinline__ void store_half(uint16_t* p, float v) {
+    if constexpr (OUT_DT) *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+    else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
+}
 
 // per-thread decode loop: one stream, gt symbols, straight to the destination layout.
 // PAGED: dst is the stream's channel in row 0 of the plane and `slots` points at the group's first slot-map entry.
@@ -661,14 +667,14 @@ __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uin
     auto lut_at = [&](uint32_t s4) { return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(lut) + s4); };
     if constexpr (PAGED) {
         for (int i = 0; i < gt - 1; ++i)
-            dst[__ldg(slots + i) * (int64_t)sT] =
-                out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]), OUT_DT);
-        dst[__ldg(slots + gt - 1) * (int64_t)sT] =
-            out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]), OUT_DT);
+            store_half<OUT_DT>(dst + __ldg(slots + i) * (int64_t)sT,
+                               dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]));
+        store_half<OUT_DT>(dst + __ldg(slots + gt - 1) * (int64_t)sT,
+                           dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]));
     } else {
         for (int i = 0; i < gt - 1; ++i, d += sT)
-            *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]), OUT_DT);
-        *d = out_half(dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]), OUT_DT);
+            store_half<OUT_DT>(d, dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, false)), mx[i]));
+        store_half<OUT_DT>(d, dequant_value(lut_at(dec_symbol2<NSTEPS>(st, src, erow, true)), mx[gt - 1]));
     }
 }
 
@@ -677,7 +683,7 @@ __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uin
 // shared memory (~10 KB per CTA), so many CTAs stay resident and hide the serial latency of each stream's coder.
 // Symbols are dequantised and stored straight into the destination layout (no uint8 / fp32 intermediates in HBM).
 template <int OUT_DT, bool PAGED>
-__global__ void __launch_bounds__(CT) decode_kernel(DecParams P) {
+__global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* tab = smem;                                                            // CT * 33 words: cdf << 16 (rows of 33, odd)
     float* mx = reinterpret_cast<float*>(smem + CT * kLp);                           // kGroup
