@@ -254,6 +254,44 @@ def test_full_width_chunk_vs_torch_reference_chain(codec):
     assert torch.equal(out2.view(torch.int16), out.view(torch.int16))
 
 
+def test_baseline_block_full_size_properties(codec):
+    """BASELINE configs[1] at full size (32L/32H/128D, 8192 tokens = 4 GiB, 32 chunks in ONE batched call):
+    decoded block == the reference's torch op chain applied chunk by chunk (bit-exact); containers of the batched
+    call == containers of per-chunk calls (checksum of checksums); decode(encode(decoded)) == decoded (idempotence);
+    total size below 8 bits/symbol."""
+    import zlib
+    import ref_torch
+    from lmcache_b200.codec import KvView
+    L, H, D, T, cs = 32, 32, 128, 8192, 256
+    g = torch.Generator(device="cuda").manual_seed(2)
+    sigma = torch.exp(0.5 * torch.randn((L, 2, 1, H * D), device="cuda", generator=g)).clamp(0.1, 8.0)
+    kv = torch.empty((L, 2, T, H * D), dtype=torch.bfloat16, device="cuda")
+    for t0 in range(0, T, 1024):                                  # generate in slabs: no 16 GiB fp32 temporary
+        kv[:, :, t0:t0 + 1024] = (torch.randn((L, 2, 1024, H * D), device="cuda", generator=g) * sigma).to(torch.bfloat16)
+    kv = kv.reshape(L, 2, T, H, D)
+    view = KvView.from_blob(kv, "vllm")
+    raws = codec.encode_to_host(view, 0, T, cs)
+    assert len(raws) == T // cs
+    crc_batched = zlib.crc32(b"".join(zlib.crc32(bytes(r)[64:]).to_bytes(4, "little") for r in raws))
+    crc_single = zlib.crc32(b"".join(
+        zlib.crc32(bytes(codec.encode_to_host(view, j * cs, cs, cs)[0])[64:]).to_bytes(4, "little") for j in range(T // cs)))
+    assert crc_batched == crc_single
+    assert sum(len(r) for r in raws) * 8 < 8.0 * kv.numel()
+    out = torch.empty_like(kv)
+    codec.decode(raws, KvView.from_blob(out, "vllm"), [j * cs for j in range(T // cs)])
+    torch.cuda.synchronize()
+    kb, vb = (torch.tensor(b) for b in O.make_bins(MODEL))
+    for j in range(T // cs):
+        want = ref_torch.roundtrip(kv[:, :, j * cs:(j + 1) * cs], kb, vb, "vllm")
+        assert torch.equal(out[:, :, j * cs:(j + 1) * cs].view(torch.int16), want.view(torch.int16)), j
+    del want
+    raws2 = codec.encode_to_host(KvView.from_blob(out, "vllm"), 0, T, cs)
+    out2 = torch.empty_like(kv)
+    codec.decode(raws2, KvView.from_blob(out2, "vllm"), [j * cs for j in range(T // cs)])
+    torch.cuda.synchronize()
+    assert torch.equal(out2.view(torch.int16), out.view(torch.int16))
+
+
 def test_extreme_inputs(codec):
     """all-zero block, single outlier rows, +/-inf and NaN rows: no crash, parity with the oracle."""
     from lmcache_b200.codec import KvView
