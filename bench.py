@@ -389,14 +389,19 @@ def run_e2e(args, codec, kv, out, out_view, staging, stride, dev, world, barrier
                 d2h += sz
             ev_out[b] = torch.cuda.Event()
             ev_out[b].record(s_out)
-        s_out.synchronize()
-        # ---- retrieve: upload containers, decode into the KV blob
+        # ---- retrieve: upload containers, decode into the KV blob.  No host sync in between: the upload of batch b
+        # waits (on the copy stream) for its containers' download and for the store side to be done with the slot.
         ev_up = [torch.cuda.Event() for _ in range(nb)]
         ev_dec = [torch.cuda.Event() for _ in range(nb)]
         for b in range(nb):
             slot = b & 1
+            s_in.wait_event(ev_out[b])                    # containers of batch b are in host memory
             if b >= 2:
                 s_in.wait_event(ev_dec[b - 2])
+            else:
+                last = nb - 1 if ((nb - 1) & 1) == slot else nb - 2          # last store batch that used this slot
+                if last >= 0:
+                    s_in.wait_event(ev_out[last])
             k = min(B, n_chunks - b * B)
             for j in range(k):
                 cj = b * B + j
