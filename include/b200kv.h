@@ -189,6 +189,29 @@ int b200kv_event_elapsed_ms(void* start, void* stop, float* ms);
 int b200kv_profile_enable(int32_t on);
 int b200kv_profile_last(float* ms, int32_t n);
 
+/*
+ * lm:// remote tier, client and server.  Host-only: no device work, usable without a GPU.
+ * Wire-compatible with lmcache/protocol.py:4-70 (158-byte client header "ii150s", 8-byte server header "ii"), so either
+ * side interoperates with the reference's Python client (storage_backend/connector/lm_connector.py:15-84) and server
+ * (lmcache/server/__main__.py:29-104).  Payloads are sent from / received into caller memory in one pass (Python bytes,
+ * a pinned slab, ...); a connection serialises whole request / response exchanges; the server's EXIST / GET are O(1)
+ * hash lookups under a reader-writer lock (the reference scans list_keys()).  Keys are <= 150 bytes.
+ */
+int b200kv_lm_server_start(const char* host, int32_t port, void** server); /* port 0 = ephemeral; threads run until stop */
+int32_t b200kv_lm_server_port(void* server);
+int64_t b200kv_lm_server_num_keys(void* server);
+int b200kv_lm_server_stop(void* server);
+int b200kv_lm_connect(const char* host, int32_t port, void** conn);
+int b200kv_lm_close(void* conn);
+int b200kv_lm_put(void* conn, const char* key, const void* data, int64_t len);      /* connection.set(); no server ack */
+int b200kv_lm_exists(void* conn, const char* key);                                  /* 1 present, 0 absent, <0 error */
+/* GET / LIST in two calls, because the caller allocates the destination once the length is known:
+ *   n = b200kv_lm_get_begin(conn, key)   payload length >= 0, -1 = miss, < -1 = error
+ *   b200kv_lm_read(conn, dst, n)         payload into caller memory (must follow a successful begin, also for n = 0) */
+int64_t b200kv_lm_get_begin(void* conn, const char* key);
+int64_t b200kv_lm_list_begin(void* conn);                                           /* keys joined by '\n' */
+int b200kv_lm_read(void* conn, void* dst, int64_t len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,17 @@ SIGNATURES = {
     "b200kv_event_elapsed_ms": (c_i32, [c_vp, c_vp, ctypes.POINTER(ctypes.c_float)]),
     "b200kv_profile_enable": (c_i32, [c_i32]),
     "b200kv_profile_last": (c_i32, [ctypes.POINTER(ctypes.c_float), c_i32]),
+    "b200kv_lm_server_start": (c_i32, [ctypes.c_char_p, c_i32, ctypes.POINTER(c_vp)]),
+    "b200kv_lm_server_port": (c_i32, [c_vp]),
+    "b200kv_lm_server_num_keys": (c_i64, [c_vp]),
+    "b200kv_lm_server_stop": (c_i32, [c_vp]),
+    "b200kv_lm_connect": (c_i32, [ctypes.c_char_p, c_i32, ctypes.POINTER(c_vp)]),
+    "b200kv_lm_close": (c_i32, [c_vp]),
+    "b200kv_lm_put": (c_i32, [c_vp, ctypes.c_char_p, c_vp, c_i64]),
+    "b200kv_lm_exists": (c_i32, [c_vp, ctypes.c_char_p]),
+    "b200kv_lm_get_begin": (c_i64, [c_vp, ctypes.c_char_p]),
+    "b200kv_lm_list_begin": (c_i64, [c_vp]),
+    "b200kv_lm_read": (c_i32, [c_vp, c_vp, c_i64]),
 }
 PROFILE_SLOTS = ("absmax", "cdf", "encode", "compact", "tile_sum", "tile_scan", "decode")
 

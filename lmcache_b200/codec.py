@@ -6,6 +6,7 @@ engine fast paths are thin layers over `CacheGenCodec`.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import threading
 from dataclasses import dataclass
@@ -238,6 +239,10 @@ class CacheGenCodec:
         self._sizes: Optional[PinnedBuffer] = None
         self._dec_in: Optional[torch.Tensor] = None
         self._dec_event: Optional[torch.cuda.Event] = None
+        self._pin_lock = threading.Lock()
+        self._pin_in_lock = threading.Lock()
+        self._pin_out: Optional[PinnedBuffer] = None      # containers on their way out (encode_to_pinned)
+        self._pin_in: Optional[PinnedBuffer] = None       # containers on their way in (pinned_staging)
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -310,6 +315,56 @@ class CacheGenCodec:
             del hd
         pin.close()
         return outs
+
+    @contextlib.contextmanager
+    def encode_to_pinned(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
+                         stream: Optional[torch.cuda.Stream] = None):
+        """encode + one device->host copy per container into the codec's page-locked slab (kept across calls, grown on
+        demand); yields one writable memoryview per container.  The views -- e.g. handed to a socket send -- are valid
+        inside the `with` block only: the slab is reused by the next call (serialised by a lock)."""
+        batch = self.encode(view, tok_begin, n_tokens, chunk_size, stream)
+        total = sum((s + 15) & ~15 for s in batch.sizes)
+        with self._pin_lock:
+            if self._pin_out is None or self._pin_out.nbytes < total:
+                if self._pin_out is not None:
+                    self._pin_out.close()
+                self._pin_out = PinnedBuffer(max(total, 1) * 5 // 4)
+            pin = self._pin_out
+            lib = N.lib()
+            sp = _stream_ptr(stream)
+            offs, o = [], 0
+            with torch.cuda.device(view.device):
+                for j, s in enumerate(batch.sizes):
+                    N.check(lib.b200kv_copy_async(pin.host_ptr + o, batch.buf.data_ptr() + j * batch.stride, s, sp), "copy")
+                    offs.append(o)
+                    o += (s + 15) & ~15
+                N.check(lib.b200kv_stream_sync(sp), "stream_sync")
+            views = [pin.view(offs[j], batch.sizes[j]) for j in range(len(offs))]
+            for v in views:
+                parse_header(v)        # raises on encoder error status
+            try:
+                yield views
+            finally:
+                del views
+
+    @contextlib.contextmanager
+    def pinned_staging(self, nbytes: int):
+        """A page-locked receive slab of at least nbytes (kept across calls): a remote tier reads containers straight
+        into it and decode() uploads from it with true asynchronous copies."""
+        with self._pin_in_lock:
+            if self._pin_in is None or self._pin_in.nbytes < nbytes:
+                if self._pin_in is not None:
+                    self._dec_sync()
+                    self._pin_in.close()
+                self._pin_in = PinnedBuffer(max(nbytes, 1) * 5 // 4)
+            try:
+                yield self._pin_in
+            finally:
+                self._dec_sync()       # the uploads out of the slab must finish before the next user overwrites it
+
+    def _dec_sync(self) -> None:
+        if self._dec_event is not None:
+            self._dec_event.synchronize()
 
     # ------------------------------------------------------------------ decode
     def _order_decode(self, tstream, need_in: int, need_ws: int) -> None:

@@ -1,4 +1,5 @@
-"""Minimal lm:// cache server: `python -m lmcache_b200.server <host> <port>`.
+"""lm:// cache server: `python -m lmcache_b200.server <host> <port> [--python]`.
+Default: the native server of libb200kv (csrc/lmnet.cu); `--python` runs the pure-Python one below.
 
 Speaks the reference wire protocol (lmcache/protocol.py, lmcache/server/__main__.py:29-93): opaque bytes
 in an in-memory dict, thread per client, no ack on PUT.  It never touches KV math; it exists so the
@@ -77,11 +78,36 @@ class LMCacheServer:
             self.sock.close()
 
 
+def run_native(host: str, port: int) -> None:
+    """The same server in C++ (csrc/lmnet.cu): thread per client, O(1) EXIST / GET under a reader-writer lock,
+    payloads received into / sent from one buffer each.  Runs until the process is terminated."""
+    import ctypes
+    import signal
+    import time
+
+    from lmcache_b200 import _native as N
+    lib = N.lib()
+    h = ctypes.c_void_p()
+    N.check(lib.b200kv_lm_server_start(host.encode(), port, ctypes.byref(h)), "lm_server_start")
+    stop = []
+    signal.signal(signal.SIGTERM, lambda *_: stop.append(1))
+    try:
+        while not stop:
+            time.sleep(0.2)
+    except KeyboardInterrupt:
+        pass
+    lib.b200kv_lm_server_stop(h)
+
+
 def main():
-    if len(sys.argv) not in (3, 4):
-        print(f"Usage: {sys.argv[0]} <host> <port> [cpu]")
+    args = [a for a in sys.argv[1:] if a != "--python"]
+    if len(args) not in (2, 3):
+        print(f"Usage: {sys.argv[0]} <host> <port> [cpu] [--python]")
         sys.exit(1)
-    LMCacheServer(sys.argv[1], int(sys.argv[2])).run()
+    if "--python" in sys.argv[1:]:
+        LMCacheServer(args[0], int(args[1])).run()
+    else:
+        run_native(args[0], int(args[1]))
 
 
 if __name__ == "__main__":

@@ -1,6 +1,7 @@
 """lm:// client (lmcache/storage_backend/connector/lm_connector.py:15-84): blocking TCP, fixed headers
 from lmcache_b200.protocol.  One lock covers a whole request/response exchange, so concurrent put / get
 threads cannot interleave on the socket (the reference locks sends only, see its TODO:1)."""
+import ctypes
 import socket
 import threading
 from typing import List, Optional
@@ -52,6 +53,32 @@ class LMCServerConnector(RemoteConnector):
             if meta.code != Constants.SERVER_SUCCESS:
                 return None
             return self._recv_exact(meta.length)
+
+    def get_into(self, key: str, dst_ptr: int, cap: int) -> Optional[int]:
+        """GET straight into caller memory (e.g. a page-locked slab): returns the payload length, None on a miss.
+        A payload larger than `cap` is drained and reported as a miss."""
+        with self.lock:
+            self._request(Constants.CLIENT_GET, key)
+            hdr = self._recv_exact(ServerMetaMessage.packlength())
+            if hdr is None:
+                return None
+            meta = ServerMetaMessage.deserialize(bytes(hdr))
+            if meta.code != Constants.SERVER_SUCCESS:
+                return None
+            n = meta.length
+            if n > cap:
+                self._recv_exact(n)
+                return None
+            if n == 0:
+                return 0
+            view = memoryview((ctypes.c_char * n).from_address(dst_ptr)).cast("B")
+            got = 0
+            while got < n:
+                k = self.sock.recv_into(view[got:], n - got)
+                if k == 0:
+                    return None
+                got += k
+            return n
 
     def list(self) -> List[str]:
         with self.lock:

@@ -107,6 +107,14 @@ class LMCRemoteBackend(LMCBackendInterface):
 
     def _put_view_blocking(self, keys, view, tok_begin: int, chunk_size: int) -> None:
         n_tokens = view.ntokens - tok_begin
+        if hasattr(self.serializer, "view_to_pinned_batch"):
+            # containers are sent from the page-locked slab the device->host copies landed in
+            with self.serializer.view_to_pinned_batch(view, chunk_size, tok_begin, n_tokens) as blobs:
+                assert len(blobs) == len(keys)
+                for key, mv in zip(keys, blobs):
+                    self.connection.set(self._combine_key(key), mv)
+                    self.existing_keys.add(key)
+            return
         blobs = self.serializer.view_to_bytes_batch(view, chunk_size, tok_begin, n_tokens)
         assert len(blobs) == len(keys)
         for key, bs in zip(keys, blobs):
@@ -126,6 +134,21 @@ class LMCRemoteBackend(LMCBackendInterface):
     def get_kv_into(self, keys: List[CacheEngineKey], dst, dst_tok0: int, chunk_size: int) -> int:
         """Fetch consecutive chunks until the first miss and decode them with ONE batched launch straight into `dst`
         (chunk i lands at token dst_tok0 + i * chunk_size).  Returns (number of chunks, tokens written)."""
+        if hasattr(self.connection, "get_into") and hasattr(self.deserializer, "pinned_staging"):
+            # receive straight into a page-locked slab and upload from there (true async copies, no bytearrays)
+            bound = (self.deserializer.container_bound(dst.L, dst.H, dst.D, chunk_size) + 63) & ~63
+            with self.deserializer.pinned_staging(bound * len(keys)) as pin:
+                blobs = []
+                for i, key in enumerate(keys):
+                    if not self.contains(key):
+                        break
+                    n = self.connection.get_into(self._combine_key(key), pin.host_ptr + i * bound, bound)
+                    if n is None or n == 0:
+                        break
+                    blobs.append(pin.view(i * bound, n))
+                if blobs:
+                    self.deserializer.decode_into(blobs, dst, [dst_tok0 + i * chunk_size for i in range(len(blobs))])
+                return len(blobs)
         blobs = []
         for key in keys:
             if not self.contains(key):

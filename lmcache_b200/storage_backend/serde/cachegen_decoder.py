@@ -47,6 +47,13 @@ class CacheGenDeserializer(Deserializer):
     def out_dtype(self) -> torch.dtype:
         return self._out_dtype()
 
+    def container_bound(self, L: int, H: int, D: int, chunk_tokens: int) -> int:
+        """Upper bound of one container's size (what a receive slab must reserve per chunk)."""
+        return self.codec.out_stride(L, H, D, chunk_tokens)
+
+    def pinned_staging(self, nbytes: int):
+        return self.codec.pinned_staging(nbytes)
+
     @_lmcache_nvtx_annotate
     def from_bytes_batch(self, containers: Sequence, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Decode consecutive chunks into ONE blob (the retrieve-side torch.cat disappears):

@@ -57,3 +57,10 @@ class CacheGenSerializer(Serializer):
         with one launch sequence and one device->host copy pass."""
         n = view.ntokens - tok_begin if n_tokens is None else n_tokens
         return self.codec.encode_to_host(view, tok_begin, n, chunk_size or self.chunk_size)
+
+    def view_to_pinned_batch(self, view: KvView, chunk_size: Optional[int] = None, tok_begin: int = 0,
+                             n_tokens: Optional[int] = None):
+        """Same, as a context manager yielding memoryviews over the codec's page-locked slab: a connector can send the
+        containers from where the device->host copy put them (no bytes objects, no extra host copy)."""
+        n = view.ntokens - tok_begin if n_tokens is None else n_tokens
+        return self.codec.encode_to_pinned(view, tok_begin, n, chunk_size or self.chunk_size)

@@ -127,13 +127,57 @@ if os.environ.get('EXTRA_ONLY') == 'paged':
     print(json.dumps(out, indent=1))
     sys.exit(0)
 
+# ---------------- raw lm:// connector throughput on loopback: native (csrc/lmnet.cu) and pure-Python, all pairings
+def lm_raw_section():
+    import ctypes
+    import threading
+    from lmcache_b200 import _native as N
+    from lmcache_b200.server.__main__ import LMCacheServer
+    from lmcache_b200.storage_backend.connector.lm_connector import LMCServerConnector
+    from lmcache_b200.storage_backend.connector.native_connector import LMCNativeConnector
+    lib = N.lib()
+    h = ctypes.c_void_p()
+    N.check(lib.b200kv_lm_server_start(b"127.0.0.1", 0, ctypes.byref(h)))
+    nport = lib.b200kv_lm_server_port(h)
+    srv = LMCacheServer("127.0.0.1", 0)
+    pport = srv.sock.getsockname()[1]
+    threading.Thread(target=srv.run, daemon=True).start()
+    blob = bytes(bytearray(os.urandom(1 << 20)) * 22)           # one 22 MiB container, about a 256-token chunk
+    res = {}
+    for sname, port in (("native_server", nport), ("python_server", pport)):
+        for cname, C in (("native_client", LMCNativeConnector), ("python_client", LMCServerConnector)):
+            c = C("127.0.0.1", port)
+            n, best_put, best_get = 16, 1e9, 1e9
+            for rep in range(3):
+                t0 = time.perf_counter()
+                for i in range(n):
+                    c.set(f"k{rep}_{i}", blob)
+                while not c.exists(f"k{rep}_{n - 1}"):
+                    pass
+                t1 = time.perf_counter()
+                for i in range(n):
+                    assert len(c.get(f"k{rep}_{i}")) == len(blob)
+                t2 = time.perf_counter()
+                best_put, best_get = min(best_put, t1 - t0), min(best_get, t2 - t1)
+            res[f"{sname}+{cname}"] = {"put_GBps": round(n * len(blob) / best_put / 1e9, 2),
+                                       "get_GBps": round(n * len(blob) / best_get / 1e9, 2)}
+            c.close()
+    lib.b200kv_lm_server_stop(h)
+    srv.sock.close()
+    res["note"] = "16 x 22 MiB values over one loopback TCP connection, best of 3; bytes on the wire"
+    return res
+
+
+if os.environ.get('EXTRA_ONLY') in (None, 'lm'):
+    out["lm_connector_raw"] = lm_raw_section()
+
 # ---------------- host mover through the engine (local cpu tier), 8192 tokens x 32L x 32H x 128D = 4 GiB
 L, H, D, T = 32, 32, 128, 8192
 kv = tuple((torch.randn(T, H, D, device="cuda").to(torch.bfloat16), torch.randn(T, H, D, device="cuda").to(torch.bfloat16))
            for _ in range(L))
 raw = 2 * L * T * H * D * 2
 toks = torch.randint(0, 32000, (T,), generator=g, dtype=torch.int64).cuda()
-for backend in ("cpu", "cuda"):
+for backend in (("cpu", "cuda") if os.environ.get('EXTRA_ONLY') is None else ()):
     meta = LMCacheEngineMetadata("test_model", 1, 0, "vllm", "bfloat16")
     eng = LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=256, backend=backend), meta)
     t0 = time.perf_counter()
@@ -172,7 +216,30 @@ try:
         rt_best, _ = timeit(lambda: eng.retrieve(toks2), n=3, warm=1)
         out["engine_lm_cachegen_" + ("fast_path" if fast else "generic_path")] = {
             "store_GBps": round(raw2 / st_best / 1e9, 2), "retrieve_GBps": round(raw2 / rt_best / 1e9, 2), "raw_bytes": raw2,
-            "note": "python socket + in-process python server dominate; GB/s of raw KV"}
+            "note": "lm:// (Python-socket client, pinned-slab zero copy) + native server process on loopback; GB/s of raw KV"}
+        if fast:
+            from lmcache_b200.codec import KvView
+            be = eng.engine_
+            view = KvView.from_tuple(kv2, "vllm")
+            t0 = time.perf_counter(); hs = sha256_prefix_chain(toks2, 256); t1 = time.perf_counter()
+            for _ in range(2):
+                ta = time.perf_counter()
+                with be.serializer.view_to_pinned_batch(view, 256, 0, T2) as blobs:
+                    tb = time.perf_counter()
+                    nbytes = sum(len(b) for b in blobs)
+                    for i, mv in enumerate(blobs):
+                        be.connection.set(f"brk{i}", mv)
+                    while not be.connection.exists(f"brk{len(blobs) - 1}"):
+                        pass
+                    tc = time.perf_counter()
+            tg = time.perf_counter()
+            got = [be.connection.get(f"brk{i}") for i in range(len(blobs))]
+            th = time.perf_counter()
+            out["engine_lm_cachegen_store_breakdown"] = {
+                "hash_ms": round((t1 - t0) * 1e3, 2), "encode_to_pinned_ms": round((tb - ta) * 1e3, 2),
+                "send_ms": round((tc - tb) * 1e3, 2), "wire_bytes": nbytes,
+                "send_GBps_wire": round(nbytes / (tc - tb) / 1e9, 2), "get_ms": round((th - tg) * 1e3, 2),
+                "get_GBps_wire": round(nbytes / (th - tg) / 1e9, 2)}
         eng.close()
 finally:
     srv.terminate(); srv.wait()
