@@ -25,6 +25,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <cerrno>
 #include <cstring>
 #include <memory>
@@ -104,8 +105,8 @@ struct Server {
     std::atomic<bool> stop{false};
     std::thread acceptor;
     std::mutex conn_mu;
-    std::vector<int> conns;
-    std::vector<std::thread> workers;
+    std::vector<int> conns;                 // open client sockets (a worker removes its own on exit)
+    std::atomic<int> active{0};             // running worker threads (detached; stop() waits for zero)
     std::shared_mutex mu;
     std::unordered_map<std::string, std::shared_ptr<Blob>> store;
 
@@ -164,7 +165,17 @@ struct Server {
                 break;      // unknown command: drop the connection, as the reference does by raising
             }
         }
-        ::close(fd);
+        {
+            std::lock_guard<std::mutex> lk(conn_mu);
+            for (size_t i = 0; i < conns.size(); ++i)
+                if (conns[i] == fd) {
+                    conns[i] = conns.back();
+                    conns.pop_back();
+                    break;
+                }
+            ::close(fd);
+        }
+        active.fetch_sub(1);
     }
 
     void accept_loop() {
@@ -178,9 +189,12 @@ struct Server {
                 ::close(fd);
                 break;
             }
-            std::lock_guard<std::mutex> lk(conn_mu);
-            conns.push_back(fd);
-            workers.emplace_back([this, fd] { serve(fd); });
+            {
+                std::lock_guard<std::mutex> lk(conn_mu);
+                conns.push_back(fd);
+            }
+            active.fetch_add(1);
+            std::thread([this, fd] { serve(fd); }).detach();
         }
     }
 };
@@ -261,8 +275,7 @@ int b200kv_lm_server_stop(void* server) {
         std::lock_guard<std::mutex> lk(s->conn_mu);
         for (int fd : s->conns) ::shutdown(fd, SHUT_RDWR);       // wakes workers blocked in recv
     }
-    for (auto& w : s->workers)
-        if (w.joinable()) w.join();
+    while (s->active.load() != 0) std::this_thread::sleep_for(std::chrono::milliseconds(1));
     delete s;
     return 0;
 }
