@@ -426,6 +426,9 @@ def test_engine_paged_store_and_retrieve(backend, lmserver, autorelease):
         cfg = LMCacheEngineConfig.from_legacy(chunk_size=cs, backend=backend)
     name = model if backend == "lm-cachegen" else "paged_" + backend
     eng = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", name)))
+    # in two steps, so that the second call skips the two chunks already present and starts at token 512
+    # (tok_begin > 0 through the slot mapping)
+    eng.store_paged(tokens[:512], [(k, v) for k, v in caches], slots[:512])
     eng.store_paged(tokens, caches, slots)
     dense, m = eng.retrieve(tokens)                       # what the store now holds, as the dense API sees it
     assert torch.sum(m) == T
