@@ -27,7 +27,7 @@ constexpr int SYMW = 43;           // words per symbol row: ceil(256 / 6); odd -
 constexpr int PAIRW = 33;          // split mode: words per CDF-pair row (32 symbols + cdf[32]); odd
 constexpr int TEMPW_FUSED = 40;    // words per stream in the tile's temp rows: own-CDF streams of <= 256 symbols
                                    //   cost <= 256*log2(31) + 2 bits = 159 bytes
-constexpr int TEMPW_SPLIT = 131;   // foreign CDF (chunk > 256 tokens): <= 16 bits / symbol + termination
+constexpr int TEMPW_SPLIT = 132;   // foreign CDF (chunk > 256 tokens): <= 16 bits / symbol + termination; 16-byte rows
 
 struct EncParams {
     PlaneTable pt;
@@ -36,6 +36,7 @@ struct EncParams {
     int32_t L, H, D, C, dtype;
     int32_t n_chunks, chunk_tokens, last_chunk_tokens, tpp;   // tpp = tiles per plane
     int32_t tiles_full, tempw;                                 // tiles per full chunk; words per temp row
+    int32_t stage_bytes;                                       // compact_kernel: bytes of shared-memory stage per CTA
     uint8_t* out;
     int64_t out_stride;
     uint64_t* sizes_out;
@@ -141,6 +142,40 @@ __device__ __forceinline__ bool decode_tile(const EncParams& P, uint32_t tile, T
     id->tok0 = id->g * kGroup;
     id->gt = min(kGroup, id->t - id->tok0);
     return true;
+}
+
+// Walk one stream's gt tokens in register double-buffered batches of BT loads (the loads of batch b+1 are in flight
+// while batch b is consumed) and hand every quantised symbol to `f(symbol)`, in token order.  Used where symbols are
+// consumed on the fly (chunk-wide histogram, coding against a chunk-wide CDF).
+template <int DT, bool PAGED, int BT, class F>
+__device__ __forceinline__ void for_each_symbol(const uint16_t* cbase, const int64_t* slot_map, int64_t tokabs, int64_t s1,
+                                                int gt, const float* fac, float maxq, F&& f) {
+    const int nbatch = (gt + BT - 1) / BT;
+    uint16_t xa[BT], xb[BT];
+    auto load = [&](uint16_t (&x)[BT], int b) {
+        const int tk = b * BT;
+#pragma unroll
+        for (int k = 0; k < BT; ++k)
+            x[k] = tk + k < gt ? __ldg(cbase + tok_row<PAGED>(slot_map, tokabs + tk + k) * s1) : (uint16_t)0;
+    };
+    auto use = [&](const uint16_t (&x)[BT], int b) {
+        const int tk = b * BT;
+        uint32_t q[BT];
+#pragma unroll
+        for (int k = 0; k < BT; ++k) q[k] = quant_symbol(half_to_float(x[k], DT), fac[min(tk + k, kGroup - 1)], maxq);
+#pragma unroll
+        for (int k = 0; k < BT; ++k)
+            if (tk + k < gt) f(q[k]);
+    };
+    load(xa, 0);
+    for (int b = 0; b < nbatch; b += 2) {
+        if (b + 1 < nbatch) load(xb, b + 1);
+        use(xa, b);
+        if (b + 1 < nbatch) {
+            if (b + 2 < nbatch) load(xa, b + 2);
+            use(xb, b + 1);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ encode
@@ -337,19 +372,10 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
             }
             EncState2 st;
             st.init();
-            for (int tk = 0; tk < gt; tk += 4) {
-                uint16_t xb[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    xb[k] = (tk + k < gt) ? __ldg(cbase + tok_row<PAGED>(P.slot_map, tokabs + tk + k) * s1) : (uint16_t)0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (tk + k < gt) {
-                        const uint32_t pr = prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq)];
-                        enc_symbol2(st, pr & 0xffffu, pr >> 16, trow, cap);
-                    }
-                }
-            }
+            for_each_symbol<DT, PAGED, 4>(cbase, P.slot_map, tokabs, s1, gt, fac, maxq, [&](uint32_t q) {
+                const uint32_t pr = prow[q];
+                enc_symbol2(st, pr & 0xffffu, pr >> 16, trow, cap);
+            });
             len = enc_finish2(st, trow, cap);
             if (st.w > cap) atomicOr(&P.err[j], 1u);
         }
@@ -397,17 +423,9 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
         __syncthreads();
         for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[tok0 + i], DT));
         __syncthreads();
-        if (active) {
-            for (int tk = 0; tk < gt; tk += 4) {
-                uint16_t xb[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    xb[k] = (tk + k < gt) ? __ldg(cbase + tok_row<PAGED>(P.slot_map, tokabs + tok0 + tk + k) * P.sT) : (uint16_t)0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (tk + k < gt) prow[quant_symbol(half_to_float(xb[k], DT), fac[tk + k], maxq)] += 1u;
-            }
-        }
+        if (active)
+            for_each_symbol<DT, PAGED, 12>(cbase, P.slot_map, tokabs + tok0, P.sT, gt, fac, maxq,
+                                           [&](uint32_t q) { prow[q] += 1u; });
     }
     if (active) {   // counts -> CDF values, written back over the counter row
         uint32_t cnt[32];
@@ -466,11 +484,51 @@ __global__ void __launch_bounds__(1024) enc_scan_kernel(EncParams P) {
     if (threadIdx.x == 0) P.totals[j] = s_carry;
 }
 
+// one stream: temp row (MSB-first native words, 16-byte aligned) -> len bytes at d.  16-byte loads, all of a row's loads
+// (ten at a time for the long split-mode rows) in flight before the first use -- a word-at-a-time loop left one load in
+// flight per thread and the kernel waiting on L2/DRAM latency.
+__device__ __forceinline__ void copy_row(uint8_t* d, const uint32_t* srcw, uint32_t len, bool short_row) {
+    auto put_word = [&](uint32_t w, uint32_t v) {
+        const uint32_t nb = min(4u, len - 4u * w);
+#pragma unroll
+        for (uint32_t b = 0; b < 4u; ++b)
+            if (b < nb) d[4u * w + b] = (uint8_t)(v >> (24u - 8u * b));
+    };
+    auto put_vec = [&](uint32_t qq, const uint4& v) {
+        put_word(4u * qq, v.x);
+        if (16u * qq + 4u < len) put_word(4u * qq + 1u, v.y);
+        if (16u * qq + 8u < len) put_word(4u * qq + 2u, v.z);
+        if (16u * qq + 12u < len) put_word(4u * qq + 3u, v.w);
+    };
+    constexpr int NV = TEMPW_FUSED / 4;
+    static_assert(TEMPW_SPLIT % 4 == 0 && TEMPW_FUSED % 4 == 0, "temp rows must be 16-byte multiples");
+    if (short_row) {                                       // fused mode: the whole row is <= NV vectors
+        uint4 v[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+            if (16u * q < len) v[q] = __ldg(reinterpret_cast<const uint4*>(srcw) + q);
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+            if (16u * q < len) put_vec((uint32_t)q, v[q]);
+    } else {                                               // split mode: rows up to 33 vectors, four in flight
+        constexpr int NL = 4;
+        for (uint32_t q0 = 0; 16u * q0 < len; q0 += NL) {
+            uint4 v[NL];
+#pragma unroll
+            for (int q = 0; q < NL; ++q)
+                if (16u * (q0 + q) < len) v[q] = __ldg(reinterpret_cast<const uint4*>(srcw) + q0 + q);
+#pragma unroll
+            for (int q = 0; q < NL; ++q)
+                if (16u * (q0 + q) < len) put_vec(q0 + q, v[q]);
+        }
+    }
+}
+
 // move each tile's streams from its temp rows to their final, contiguous place in the payload
 // (collect_bytes, cachegen_encoder.py:225-238).  Each thread copies its own stream into a shared-memory image of the
 // tile's byte range (placed at the destination's 16-byte phase), then the CTA writes that range with 16-byte vector
 // stores: the payload is written as full sectors no matter how short the individual streams are.
-__global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
+__global__ void __launch_bounds__(CT, 9) compact_kernel(EncParams P) {
     extern __shared__ __align__(16) uint8_t stage[];      // 16 + CT * tempw * 4 bytes
     __shared__ uint32_t s_warp[CT / 32];
     const int tid = threadIdx.x;
@@ -492,36 +550,23 @@ __global__ void __launch_bounds__(CT) compact_kernel(EncParams P) {
     }
     uint8_t* dst = cont + lo.off_payload + base;
     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    // the image of the tile's byte range must fit the shared-memory stage the launch provided; a tile coded against a
+    // foreign CDF may (rarely) exceed it, then every thread writes its own stream straight to the payload
+    const bool staged = phase + tile_total <= (uint32_t)P.stage_bytes;
     if (len) {
-        uint8_t* d = stage + phase + my_off;
         const uint32_t* srcw = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
-        auto put_word = [&](uint32_t w, uint32_t v) {        // rows are MSB-first native words
-            const uint32_t nb = min(4u, len - 4u * w);
-#pragma unroll
-            for (uint32_t b = 0; b < 4u; ++b)
-                if (b < nb) d[4u * w + b] = (uint8_t)(v >> (24u - 8u * b));
-        };
-        if (P.tempw == TEMPW_FUSED) {
-            // 160-byte rows, 16-byte aligned: all of the row's 16-byte loads are issued before the first use
-            // (a word-at-a-time loop left one load in flight per thread and the kernel waiting on L2/DRAM latency)
-            constexpr int NV = TEMPW_FUSED / 4;
-            uint4 v[NV];
-#pragma unroll
-            for (int q = 0; q < NV; ++q)
-                if (16u * q < len) v[q] = __ldg(reinterpret_cast<const uint4*>(srcw) + q);
-#pragma unroll
-            for (int q = 0; q < NV; ++q)
-                if (16u * q < len) {
-                    put_word(4u * q, v[q].x);
-                    if (16u * q + 4u < len) put_word(4u * q + 1u, v[q].y);
-                    if (16u * q + 8u < len) put_word(4u * q + 2u, v[q].z);
-                    if (16u * q + 12u < len) put_word(4u * q + 3u, v[q].w);
-                }
-        } else {
-            const uint32_t nw = (len + 3u) >> 2;
-            for (uint32_t w = 0; w < nw; ++w) put_word(w, __ldg(srcw + w));
+        // two instantiations, so that the staged one compiles to shared-memory stores and not to generic ones
+        if (staged) {
+            copy_row(stage + phase + my_off, srcw, len, P.tempw == TEMPW_FUSED);
+        } else {                                             // rare: plain word loop, keeps the kernel's registers low
+            uint8_t* d = dst + my_off;
+            for (uint32_t w = 0; 4u * w < len; ++w) {
+                const uint32_t v = __ldg(srcw + w);
+                for (uint32_t b = 0; b < 4u && 4u * w + b < len; ++b) d[4u * w + b] = (uint8_t)(v >> (24u - 8u * b));
+            }
         }
     }
+    if (!staged) return;                                     // uniform per CTA
     __syncthreads();
     // [phase, phase + tile_total) of `stage` -> dst - phase + same offsets; vector body, byte head / tail
     const uint32_t lo_b = phase, hi_b = phase + tile_total;
@@ -936,10 +981,12 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     // 3) compaction (collect_bytes) + headers + sizes
     {
         ProfScope prof(kProfFinalize, stream);
-        B2_CHECK_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)((size_t)CT * TEMPW_SPLIT * 4 + 32)));
+        // stage = the fused mode's worst case (128 x 160 B + alignment phase); in split mode a tile can in principle
+        // reach 128 x 528 B, but sizing the stage for that would leave 3 CTAs per SM for streams that are typically
+        // a few dozen bytes long -- oversized tiles take the direct path inside the kernel
+        P.stage_bytes = CT * TEMPW_FUSED * 4 + 32;
         enc_scan_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(P);
-        compact_kernel<<<(unsigned)n_tiles, CT, (size_t)CT * P.tempw * 4 + 32, stream>>>(P);
+        compact_kernel<<<(unsigned)n_tiles, CT, (size_t)P.stage_bytes, stream>>>(P);
         finalize_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P);
     }
     B2_CHECK_CUDA(cudaGetLastError());

@@ -210,6 +210,36 @@ def test_paged_kv_cache_in_place(codec, T, cs, dt):
             assert bool((flat[mask.cuda()] == 3.0).all()), "decode wrote outside the mapped rows"
 
 
+def test_split_mode_oversized_tiles_take_the_direct_path(codec):
+    """One 2048-token chunk (CDF over the whole chunk): seven groups of near-constant values and one group of values
+    spread over all bins.  That group's symbols are rare chunk-wide (~10 bits each), so its tiles exceed the
+    compaction kernel's shared-memory stage and are written by the per-thread direct path; the rest is staged.
+    Container and decoded values must equal the oracle's either way."""
+    from lmcache_b200.codec import KvView
+    L, H, D, T = 2, 1, 128, 2048
+    C = H * D
+    rng = np.random.default_rng(77)
+    x = np.zeros((L, 2, T, C), np.float32)
+    x[:, :, :, 0] = 8.0                                            # row max in every row: the scale is fixed
+    x[:, :, 768:1024, 1:] = rng.uniform(-8.0, 8.0, size=(L, 2, 256, C - 1)).astype(np.float32)
+    x[:, :, :768, 1:] += rng.choice([0.0, 0.6], size=(L, 2, 768, C - 1), p=[0.95, 0.05]).astype(np.float32)
+    bits = O.f32_to_bf16_bits(x)
+    kv = _bits_to_tensor(bits, 0).reshape(L, 2, T, H, D).cuda()
+    raw = codec.encode_to_host(KvView.from_blob(kv, "vllm"), 0, T, T)[0]
+    kb, vb = O.make_bins(MODEL)
+    enc = O.encode_chunk(bits, 0, kb, vb)
+    cdf, maxes, lengths, payload = _sections(raw, L, H, D, T)
+    assert np.array_equal(cdf, enc["cdf"]) and np.array_equal(maxes, enc["maxes"])
+    want_len = np.stack([ln for _, ln, _ in enc["groups"]])
+    assert np.array_equal(lengths, want_len)
+    assert int(want_len[3].reshape(-1, 128).sum(axis=1).max()) > 128 * 160 + 32      # group 3's tiles really are oversized
+    assert np.array_equal(payload, np.concatenate([b for b, _, _ in enc["groups"]]))
+    out = torch.empty_like(kv)
+    codec.decode([raw], KvView.from_blob(out, "vllm"), [0])
+    torch.cuda.synchronize()
+    assert np.array_equal(_tensor_bits(out).reshape(L, 2, T, C), O.decode_chunk(enc, 0, kb, vb, 0))
+
+
 def test_tok_begin_and_device_container_decode(codec):
     """Encoding a token sub-range, and decoding straight from the device staging buffer (no host hop)."""
     from lmcache_b200.codec import KvView
