@@ -335,7 +335,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32->u8 (bf16 KV)",
             "data": "synthetic",
             "config": {"workload": f"CacheGen encode+decode, {L}L/{H}H/{D}D {T}-token bf16 KV block per GPU, "
-                                   f"chunk_size {cs} -> {n_chunks} chunks" + (" (BASELINE configs[1])" if H == 32 else " (side measurement, not the BASELINE shape)"),
+                                   f"chunk_size {cs} -> {n_chunks} chunks" + (" (BASELINE configs[1])" if (H, T) == (32, 8192) else " (BASELINE configs[2] shape: 65536-token offload + reload; e2e is that config's metric)" if (H, T) == (32, 65536) else " (side measurement, not a BASELINE shape)"),
                        "raw_bytes_per_gpu": raw_bytes, "container_bytes": container_bytes,
                        "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
                        "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity},
