@@ -121,7 +121,35 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML from a thread every ~2 ms (the default timed
+    region is ~55 ms, `nvidia-smi -lms 100` would see one sample), nvidia-smi as the fallback."""
+
     def __init__(self, index):
+        self.nvml = None
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.samples, self.mask, self._stop = pynvml, [], 0, False
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop:
+                    try:
+                        self.samples.append(pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                        self.mask |= reasons_fn(self.h)
+                    except pynvml.NVMLError:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:       # noqa: BLE001 -- no NVML: fall back to the nvidia-smi poller
+            self.nvml = None
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         try:
@@ -135,6 +163,20 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            n = self.nvml
+            self._stop = True
+            self.thread.join()
+            sm = sorted(self.samples)
+            try:
+                smax = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+            except n.NVMLError:
+                smax = None
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            reasons = sorted(k for k, b in bits.items() if self.mask & b)
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": smax, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
