@@ -322,6 +322,56 @@ def test_baseline_block_full_size_properties(codec):
     assert torch.equal(out2.view(torch.int16), out.view(torch.int16))
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_layouts_and_offsets_vs_oracle(codec, seed):
+    """Seeded sweep over shapes the fixed cases do not pin: odd head sizes (scalar kernels), partial channel tiles,
+    1..700 tokens, chunk sizes on both sides of 256, both dtypes, blob / tuple / huggingface sources, tok_begin > 0,
+    decode at a destination offset into a larger blob.  Container sections and decoded values == oracle."""
+    from lmcache_b200.codec import KvView
+    rng = np.random.default_rng(9000 + seed)
+    L = int(rng.integers(1, 5))
+    H = int(rng.integers(1, 5))
+    D = int(rng.choice([8, 20, 33, 64, 72, 80, 128]))
+    T = int(rng.integers(1, 701))
+    cs = int(rng.choice([16, 64, 200, 256, 300, 512]))
+    dt = int(rng.integers(0, 2))
+    src = str(rng.choice(["blob", "tuple", "hf_blob"]))
+    tok_begin = int(rng.integers(0, T)) if T > 1 and rng.random() < 0.5 else 0
+    C = H * D
+    bits = O.synth_kv_bits(L, T, C, seed=seed)
+    tdt = torch.bfloat16 if dt == 0 else torch.float16
+    kv = _bits_to_tensor(bits, 0).float().to(tdt).reshape(L, 2, T, H, D).cuda()
+    bits = _tensor_bits(kv).reshape(L, 2, T, C)
+    if src == "blob":
+        view = KvView.from_blob(kv, "vllm")
+    elif src == "hf_blob":
+        view = KvView.from_blob(kv.permute(0, 1, 3, 2, 4).contiguous(), "huggingface")
+    else:
+        view = KvView.from_tuple(tuple((kv[l, 0].clone(), kv[l, 1].clone()) for l in range(L)), "vllm")
+    n = T - tok_begin
+    raws = codec.encode_to_host(view, tok_begin, n, cs)
+    kb, vb = O.make_bins(MODEL)
+    n_chunks = (n + cs - 1) // cs
+    assert len(raws) == n_chunks
+    pad = int(rng.integers(0, 40))
+    out = torch.full((L, 2, pad + n, H, D), 2.0, dtype=tdt, device="cuda")
+    wants = []
+    for j, raw in enumerate(raws):
+        t0, t1 = tok_begin + j * cs, min(T, tok_begin + (j + 1) * cs)
+        enc = O.encode_chunk(bits[:, :, t0:t1], dt, kb, vb)
+        cdf, maxes, lengths, payload = _sections(raw, L, H, D, t1 - t0)
+        assert np.array_equal(cdf, enc["cdf"]) and np.array_equal(maxes, enc["maxes"]), (seed, j)
+        assert np.array_equal(lengths, np.stack([ln for _, ln, _ in enc["groups"]])), (seed, j)
+        assert np.array_equal(payload, np.concatenate([b for b, _, _ in enc["groups"]])), (seed, j)
+        wants.append(O.decode_chunk(enc, dt, kb, vb, dt))
+    codec.decode(raws, KvView.from_blob(out, "vllm"), [pad + j * cs for j in range(n_chunks)])
+    torch.cuda.synchronize()
+    got = _tensor_bits(out).reshape(L, 2, pad + n, C)
+    assert np.array_equal(got[:, :, pad:], np.concatenate(wants, axis=2)), seed
+    if pad:
+        assert bool((out[:, :, :pad] == 2.0).all()), "decode wrote in front of its destination offset"
+
+
 def test_extreme_inputs(codec):
     """all-zero block, single outlier rows, +/-inf and NaN rows: no crash, parity with the oracle."""
     from lmcache_b200.codec import KvView
