@@ -12,12 +12,16 @@
 //   coder       torchac lineage as called at cachegen_encoder.py:255-260 / cachegen_decoder.py:65-66
 //               (32-bit low/high, 16-bit CDF, E1/E2/E3 renormalisation, MSB-first bit packing)
 //
-// The coder below produces exactly the bit-by-bit reference bitstream but renormalises in two
-// count-leading-zeros batches per symbol instead of a bit loop:
-//   n = clz(low ^ high)                 E1/E2 shifts: the n leading bits agree and are emitted
-//   m = clz(((~low | high) << 1) | 1)   E3 shifts: m more "pending" bits
-// and the decoder finds the symbol with a 5-step search on the products (span * cdf[s]) >> 16, which
-// is equivalent to the reference's 64-bit division + binary search on the CDF.
+// Two coders live here, both producing exactly the bit-by-bit reference bitstream:
+//   * EncState / DecState (enc_symbol, dec_symbol): a direct restatement with batched shifts
+//       n = clz(low ^ high)                 E1/E2 shifts: the n leading bits agree and are emitted
+//       m = clz(((~low | high) << 1) | 1)   E3 shifts: m more "pending" bits
+//     kept as the readable baseline the host tests compare against;
+//   * EncState2 / DecState2 (enc_symbol2, dec_symbol2): what the kernels run.  They track the ABSOLUTE
+//     low (pending bits = carry resolution), so every shift of any kind is one funnel shift with one
+//     count k = n + m, emission needs no pending counter, and the decoder finds the symbol with an
+//     approximate reciprocal + a fixed-depth branch-free search that the exact interval products verify
+//     (DESIGN.md sections 3.2 and 3.3).
 #pragma once
 #include <stdint.h>
 

@@ -8,9 +8,10 @@
 // Thread mapping: one arithmetic-coder stream = one (plane nl, channel c) = one thread; a CTA owns a
 // tile of CT consecutive channels of one plane (and one <=256-token group).  Global KV reads/writes are
 // then naturally coalesced along the channel dimension (a warp touches 64 contiguous bytes per token)
-// and the tile's byte streams are contiguous in the container, so they are staged through shared
-// memory and written/read as one contiguous segment.  Stream compaction (collect_bytes in the
-// reference) happens inside the encode kernel with a decoupled look-back prefix over tiles.
+// and the tile's byte streams are contiguous in the container.  The coder writes each stream to a temp
+// row in global memory; stream compaction (collect_bytes in the reference) is a separate scan + gather
+// pass (enc_scan_kernel, compact_kernel) that stages a tile's byte range in shared memory and writes it
+// with 16-byte stores, so no CTA ever waits on another one.  DESIGN.md section 3 has the per-kernel story.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
