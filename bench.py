@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=256)
     ap.add_argument("--heads", type=int, default=32, help="KV heads (32 = BASELINE configs[1]; 8 = GQA shapes, side measurement)")
     ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks in the bounded CPU sample")
+    ap.add_argument("--coder", default="rans", choices=["rans", "ac"], help="payload coder: rans = container v2 (default), ac = v1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -264,13 +265,13 @@ def main():
     n_chunks = (T + cs - 1) // cs
     raw_bytes = L * 2 * T * C * 2
     lib = N.lib()
-    codec = CacheGenCodec(MODEL)
+    codec = CacheGenCodec(MODEL, coder=args.coder)
     kv = synth_kv_torch(T, dev, 1234 + 2 + rank)
     view = KvView.from_blob(kv, "vllm")
     out = torch.empty_like(kv)
     out_view = KvView.from_blob(out, "vllm")
     stride = codec.out_stride(L, H, D, cs)
-    staging = torch.empty(stride * n_chunks, dtype=torch.uint8, device=dev)
+    staging = torch.empty(stride * n_chunks + N.READ_SLACK, dtype=torch.uint8, device=dev)
     dst_tok = [j * cs for j in range(n_chunks)]
     ntoks = [min(cs, T - j * cs) for j in range(n_chunks)]
     stream = torch.cuda.current_stream()
@@ -411,7 +412,7 @@ def run_e2e(args, codec, kv, out, out_view, staging, stride, dev, world, barrier
     host_digest = PinnedBuffer(4096)
     per_batch_bytes = L * 2 * batch_tok * C * 2
     dev_in = [torch.empty((L, 2, batch_tok, H, D), dtype=torch.bfloat16, device=dev) for _ in range(2)]
-    dev_cont = [torch.empty(stride * B, dtype=torch.uint8, device=dev) for _ in range(2)]
+    dev_cont = [torch.empty(stride * B + N.READ_SLACK, dtype=torch.uint8, device=dev) for _ in range(2)]
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     cur = torch.cuda.current_stream()
     # stage the raw KV into host memory once (not timed)
@@ -472,9 +473,10 @@ def run_e2e(args, codec, kv, out, out_view, staging, stride, dev, world, barrier
                 h2d += sizes_all[cj]
             ev_up[b].record(s_in)
             cur.wait_event(ev_up[b])
-            codec.decode_raw(dev_cont[slot].data_ptr(), [j * stride for j in range(k)],
+            codec.decode_raw(dev_cont[slot].data_ptr(), dev_cont[slot].numel(), [j * stride for j in range(k)],
+                             [sizes_all[b * B + j] for j in range(k)],
                              [min(cs, T - (b * B + j) * cs) for j in range(k)], out_view,
-                             [(b * B + j) * cs for j in range(k)], N.DT_BF16)
+                             [(b * B + j) * cs for j in range(k)], N.DT_BF16, codec.coder)
             ev_dec[b].record(cur)
         N.check(lib.b200kv_copy_async(host_digest.host_ptr, out.data_ptr(), 4096, cur.cuda_stream))
         d2h += 4096

@@ -31,14 +31,17 @@
 extern "C" {
 #endif
 
-#define B200KV_VERSION 2           /* ABI version; 2: b200kv_kv_desc.slot_map */
-#define B200KV_CONTAINER_VERSION 1 /* "B2KV" wire container version (b200kv_header.version) */
+#define B200KV_VERSION 3           /* ABI version; 2: b200kv_kv_desc.slot_map; 3: coder selection, decode status, total_bytes */
+#define B200KV_CODER_AC 0          /* payload = torchac-lineage arithmetic coder; container version 1 */
+#define B200KV_CODER_RANS 1        /* payload = rANS, 32-bit state / 16-bit renormalisation; container version 2 */
+#define B200KV_CONTAINER_VERSION(coder) ((coder) + 1) /* "B2KV" wire container version (b200kv_header.version) */
 #define B200KV_LP 33            /* CDF entries per stream (cachegen_encoder.py:287-289: int(bins.max()) + 1) */
 #define B200KV_GROUP_TOKENS 256 /* CACHEGEN_GPU_MAX_TOKENS_PER_CHUNK (cachegen_basics.py:13) */
 #define B200KV_MAX_PLANES 128   /* 2 * nlayers upper bound */
 #define B200KV_DT_BF16 0
 #define B200KV_DT_FP16 1
 
+#define B200KV_READ_SLACK 640   /* bytes that must be readable past the end of every container handed to the decoder */
 #define B200KV_MAGIC 0x564B3242u /* "B2KV" little-endian */
 #define B200KV_HEADER_BYTES 64
 
@@ -56,12 +59,16 @@ typedef struct b200kv_kv_desc {
                                 * written in place. */
 } b200kv_kv_desc;
 
-/* Wire container of one encoded chunk ("B2KV" v1).  All sections 16-byte aligned, little-endian.
+/* Wire container of one encoded chunk ("B2KV" v1 / v2).  All sections 16-byte aligned, little-endian.
  * Logical content == CacheGenGPUEncoderOutput (cachegen_basics.py:109-142):
  *   cdf [2L,C,33] int16 | max_tensors_key/value [2,L,t] half | per <=256-token group:
  *   bytestream_lengths [2L,C] int32 + bytestream (streams in (nl,c) row-major order, no padding).
  * Flat instead of pickled CUDA tensors so it can be produced on the device in one buffer and moved
- * with one async copy. */
+ * with one async copy.
+ * Versions 1 and 2 differ ONLY in the bytes of each stream inside `bytestream`: the reference's coder lives in the
+ * un-vendored torchac_cuda wheel, so the bitstream is this build's own.  v1 = 32-bit binary arithmetic
+ * coder (torchac lineage, MSB-first bits); v2 = rANS over the same 16-bit CDFs: LE32 final state, then LE16
+ * renormalisation words in decode order (normative description: lmcache_b200/csrc/ac_core.cuh). */
 typedef struct b200kv_header {
     uint32_t magic, version;
     uint32_t L, H, D;
@@ -88,7 +95,8 @@ int b200kv_device_count(void);
 int b200kv_container_layout(int32_t L, int32_t H, int32_t D, int32_t ntokens, b200kv_layout* out);
 
 /* Bytes of device scratch b200kv_encode_chunks / b200kv_decode_chunks need for a call. */
-int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks);
+int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks,
+                                      int32_t coder);
 int64_t b200kv_decode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks);
 
 /*
@@ -105,10 +113,11 @@ int64_t b200kv_decode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t c
  * the header status set if the payload does not fit).  sizes_out[j] (device or mapped-host memory)
  * receives total_bytes of chunk j.
  * key_bins / value_bins: HOST float arrays of length L (make_key_bins / make_value_bins, :339-350).
+ * coder: B200KV_CODER_* -- which entropy coder fills the bytestreams (and hence header.version).
  */
 int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_chunks, int32_t chunk_tokens,
-                         int32_t last_chunk_tokens, const float* key_bins, const float* value_bins, void* out,
-                         int64_t out_stride, uint64_t* sizes_out, void* workspace, int64_t workspace_bytes,
+                         int32_t last_chunk_tokens, const float* key_bins, const float* value_bins, int32_t coder,
+                         void* out, int64_t out_stride, uint64_t* sizes_out, void* workspace, int64_t workspace_bytes,
                          void* stream);
 
 /*
@@ -124,12 +133,22 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
  * L/H/D; ntokens[j] (HOST int32 array) tokens each.  Chunk j's tokens are written to `dst` at token
  * index dst_tok[j] (HOST int64 array) using dst's strides; dst->dtype is the output dtype
  * (bf16 for vllm, fp16 for huggingface, cachegen_decoder.py:189-200) and max_dtype the dtype of the
- * stored max tensors.
+ * stored max tensors.  total_bytes[j] (HOST int64 array) = header.total_bytes of container j and containers_bytes = the
+ * size of the `containers` buffer; the call fails unless offsets[j] + total_bytes[j] + B200KV_READ_SLACK <=
+ * containers_bytes for every j (the slack bytes may hold anything, e.g. the next container).  Given that, the kernels
+ * never read outside the buffer whatever the lengths section says: stream starts are clamped to the payload and a
+ * stream reads a bounded number of bytes from its start (a corrupt or truncated blob from a remote tier is a cache
+ * miss, not an illegal address).
+ * coder = header.version - 1 of the containers (one call, one coder).
+ * status_out: NULL, or DEVICE / mapped-host uint32[n_chunks], zeroed by the call and then OR-ed with
+ *   1 = a rANS stream did not return to its initial state (payload or CDF bytes damaged),
+ *   2 = stream offsets beyond the payload (lengths section damaged); valid once the stream has run.
  */
-int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const int32_t* ntokens,
-                         const int64_t* dst_tok, int32_t n_chunks, int32_t max_dtype, const b200kv_kv_desc* dst,
-                         const float* key_bins, const float* value_bins, void* workspace,
-                         int64_t workspace_bytes, void* stream);
+int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const int64_t* offsets,
+                         const int64_t* total_bytes, const int32_t* ntokens, const int64_t* dst_tok, int32_t n_chunks,
+                         int32_t max_dtype,
+                         int32_t coder, const b200kv_kv_desc* dst, const float* key_bins, const float* value_bins,
+                         uint32_t* status_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Token-id prefix hash.  Replaces LMCacheEngine._chunk_tokens/_hash/_prefix_hash

@@ -16,11 +16,15 @@ LIB_PATH = os.path.join(_HERE, "libb200kv.so")
 
 DT_BF16 = 0
 DT_FP16 = 1
+CODER_AC = 0       # container version 1: arithmetic coder
+CODER_RANS = 1     # container version 2: rANS
+CODERS = {"ac": CODER_AC, "rans": CODER_RANS}
 LP = 33
 GROUP_TOKENS = 256
 MAX_PLANES = 128
 MAGIC = 0x564B3242
 HEADER_BYTES = 64
+READ_SLACK = 640     # B200KV_READ_SLACK
 
 c_i32, c_i64, c_vp, c_u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_uint64
 
@@ -67,12 +71,12 @@ SIGNATURES = {
     "b200kv_last_error": (ctypes.c_char_p, []),
     "b200kv_device_count": (c_i32, []),
     "b200kv_container_layout": (c_i32, [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Layout)]),
-    "b200kv_encode_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32]),
+    "b200kv_encode_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "b200kv_decode_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32]),
-    "b200kv_encode_chunks": (c_i32, [ctypes.POINTER(KvDesc), c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
+    "b200kv_encode_chunks": (c_i32, [ctypes.POINTER(KvDesc), c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i64,
                                       c_vp, c_vp, c_i64, c_vp]),
-    "b200kv_decode_chunks": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(KvDesc), c_vp, c_vp,
-                                      c_vp, c_i64, c_vp]),
+    "b200kv_decode_chunks": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(KvDesc),
+                                      c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "b200kv_sha256_chain": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "b200kv_pack_chunks": (c_i32, [ctypes.POINTER(KvDesc), c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "b200kv_unpack_chunks": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(KvDesc), c_i64, c_vp]),

@@ -194,13 +194,32 @@ def parse_header(buf) -> N.Header:
     hd = N.Header.from_buffer_copy(bytes(mv[:N.HEADER_BYTES]))
     if hd.magic != N.MAGIC:
         raise ValueError("not a B2KV container (bad magic)")
-    if hd.version != 1:
+    if hd.version not in (1, 2):
         raise ValueError(f"unsupported B2KV version {hd.version}")
     if hd.total_bytes > mv.nbytes:
         raise ValueError("truncated B2KV container")
     if hd.status != 0:
         raise ValueError(f"B2KV container carries encoder error status {hd.status}")
+    check_header(hd)
     return hd
+
+
+def check_header(hd: "N.Header") -> None:
+    """Structural checks that make a damaged blob a miss (ValueError) instead of bad device addresses: the section
+    offsets follow from (L, H, D, ntokens), so total_bytes must be exactly fixed sections + payload."""
+    if not (0 < hd.L <= N.MAX_PLANES // 2 and hd.H > 0 and hd.D > 0 and hd.ntokens > 0):
+        raise ValueError("B2KV header carries an impossible shape")
+    if hd.max_dtype not in (N.DT_BF16, N.DT_FP16):
+        raise ValueError("B2KV header carries an unknown max_dtype")
+    lo = N.container_layout(hd.L, hd.H, hd.D, hd.ntokens)
+    if hd.ngroups != (hd.ntokens + N.GROUP_TOKENS - 1) // N.GROUP_TOKENS:
+        raise ValueError("B2KV header: ngroups does not match ntokens")
+    if hd.total_bytes != lo.off_payload + hd.payload_bytes:
+        raise ValueError("B2KV header: total_bytes != fixed sections + payload_bytes (truncated or corrupt)")
+    nstreams = 2 * hd.L * hd.H * hd.D * hd.ngroups
+    per_stream = 4 if hd.version == 2 else 1          # rANS streams are >= 4 bytes, arithmetic-coder streams >= 1
+    if hd.payload_bytes < per_stream * nstreams or hd.payload_bytes > lo.max_total_bytes:
+        raise ValueError("B2KV header: payload_bytes impossible for this shape")
 
 
 @dataclass
@@ -210,6 +229,7 @@ class EncodedBatch:
     stride: int
     sizes: List[int]             # total bytes per container (host, valid after the call returns)
     max_dtype: int = 0           # dtype code of the stored row maxima (== input dtype)
+    coder: int = N.CODER_RANS    # which entropy coder filled the payloads (container version - 1)
 
     def container(self, j: int) -> torch.Tensor:
         return self.buf[j * self.stride: j * self.stride + self.sizes[j]]
@@ -223,9 +243,16 @@ class CacheGenCodec:
     its buffers and is guarded by its own lock.
     """
 
-    def __init__(self, model_name: str):
+    def __init__(self, model_name: str, coder: Optional[str] = None):
+        """coder: "rans" (container version 2, the default) or "ac" (version 1, the torchac-lineage arithmetic coder);
+        the environment variable LMCACHE_B200_CODER overrides the default.  Decoding accepts both."""
+        import os
         from lmcache_b200.storage_backend.serde.cachegen_basics import CacheGenConfig
         N.require_cuda()
+        name = (coder or os.environ.get("LMCACHE_B200_CODER", "rans")).lower()
+        if name not in N.CODERS:
+            raise ValueError(f"unknown coder {name!r} (expected one of {sorted(N.CODERS)})")
+        self.coder = N.CODERS[name]
         self.config = CacheGenConfig.from_model_name(model_name)
         kb, vb = self.config.key_bins_list(), self.config.value_bins_list()
         self.nlayers = len(kb)
@@ -239,6 +266,8 @@ class CacheGenCodec:
         self._sizes: Optional[PinnedBuffer] = None
         self._dec_in: Optional[torch.Tensor] = None
         self._dec_event: Optional[torch.cuda.Event] = None
+        self._dec_status: Optional[PinnedBuffer] = None   # uint32 per chunk of the last decode call (mapped host memory)
+        self._dec_status_n = 0
         self._pin_lock = threading.Lock()
         self._pin_in_lock = threading.Lock()
         self._pin_out: Optional[PinnedBuffer] = None      # containers on their way out (encode_to_pinned)
@@ -273,10 +302,10 @@ class CacheGenCodec:
         stride = self.out_stride(view.L, view.H, view.D, chunk_size)
         lib = N.lib()
         with self._enc_lock, torch.cuda.device(view.device):
-            ws_bytes = lib.b200kv_encode_workspace_bytes(view.L, view.H, view.D, chunk_size, n_chunks)
+            ws_bytes = lib.b200kv_encode_workspace_bytes(view.L, view.H, view.D, chunk_size, n_chunks, self.coder)
             self._enc_ws = self._grow(self._enc_ws, ws_bytes, view.device)
             if out is None:
-                self._enc_out = self._grow(self._enc_out, stride * n_chunks, view.device)
+                self._enc_out = self._grow(self._enc_out, stride * n_chunks + N.READ_SLACK, view.device)
                 out = self._enc_out
             elif out.numel() < stride * n_chunks:
                 raise ValueError("encode output buffer too small")
@@ -284,7 +313,7 @@ class CacheGenCodec:
                 self._sizes = PinnedBuffer(max(4096, 8 * n_chunks))
             sp = _stream_ptr(stream)
             N.check(lib.b200kv_encode_chunks(ctypes.byref(view.desc), tok_begin, n_chunks, chunk_size, last,
-                                             self._kb, self._vb, out.data_ptr(), stride, self._sizes.dev_ptr,
+                                             self._kb, self._vb, self.coder, out.data_ptr(), stride, self._sizes.dev_ptr,
                                              self._enc_ws.data_ptr(), self._enc_ws.numel(), sp), "encode_chunks")
             N.check(lib.b200kv_stream_sync(sp), "stream_sync")
             sizes = list((ctypes.c_uint64 * n_chunks).from_address(self._sizes.host_ptr))
@@ -292,7 +321,7 @@ class CacheGenCodec:
             for j, s in enumerate(sizes):
                 if s < N.HEADER_BYTES or s > stride:
                     raise N.NativeError(f"encoder produced an invalid container size {s} for chunk {j}")
-            return EncodedBatch(out, stride, [int(s) for s in sizes], int(view.desc.dtype))
+            return EncodedBatch(out, stride, [int(s) for s in sizes], int(view.desc.dtype), self.coder)
 
     def encode_to_host(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
                        stream: Optional[torch.cuda.Stream] = None) -> List[bytes]:
@@ -378,10 +407,12 @@ class CacheGenCodec:
         else:
             tstream.wait_event(self._dec_event)
 
-    def decode_raw(self, base_ptr: int, offsets: Sequence[int], ntokens: Sequence[int], dst: KvView,
-                   dst_tok: Sequence[int], max_dtype: int, stream: Optional[torch.cuda.Stream] = None,
-                   _locked: bool = False) -> None:
-        """Decode containers that already sit in device memory at base_ptr + offsets[j] (asynchronous)."""
+    def decode_raw(self, base_ptr: int, buf_bytes: int, offsets: Sequence[int], totals: Sequence[int],
+                   ntokens: Sequence[int], dst: KvView, dst_tok: Sequence[int], max_dtype: int, coder: int,
+                   stream: Optional[torch.cuda.Stream] = None, _locked: bool = False) -> None:
+        """Decode containers that already sit in device memory at base_ptr + offsets[j] (asynchronous).  `buf_bytes` is
+        the size of the buffer behind base_ptr: it must extend N.READ_SLACK bytes past every container (checked by the
+        library); totals[j] = header.total_bytes."""
         n = len(offsets)
         if n == 0:
             return
@@ -394,10 +425,17 @@ class CacheGenCodec:
             if not _locked:
                 self._order_decode(tstream, 0, ws_bytes)
             self._dec_ws = self._grow(self._dec_ws, ws_bytes, dst.device)
-            N.check(lib.b200kv_decode_chunks(base_ptr, N.i64_array(list(offsets)), N.i32_array(list(ntokens)),
-                                             N.i64_array(list(dst_tok)), n, int(max_dtype), ctypes.byref(dst.desc),
-                                             self._kb, self._vb, self._dec_ws.data_ptr(), self._dec_ws.numel(),
-                                             tstream.cuda_stream), "decode_chunks")
+            if self._dec_status is None or self._dec_status.nbytes < 4 * n:
+                if self._dec_status is not None:
+                    self._dec_sync()
+                self._dec_status = PinnedBuffer(max(4096, 8 * n))
+            self._dec_status_n = n
+            N.check(lib.b200kv_decode_chunks(base_ptr, int(buf_bytes), N.i64_array(list(offsets)),
+                                             N.i64_array(list(totals)), N.i32_array(list(ntokens)),
+                                             N.i64_array(list(dst_tok)), n, int(max_dtype), int(coder),
+                                             ctypes.byref(dst.desc), self._kb, self._vb, self._dec_status.dev_ptr,
+                                             self._dec_ws.data_ptr(), self._dec_ws.numel(), tstream.cuda_stream),
+                    "decode_chunks")
             if self._dec_event is None:
                 self._dec_event = torch.cuda.Event()
             self._dec_event.record(tstream)
@@ -408,11 +446,21 @@ class CacheGenCodec:
             with self._dec_lock, torch.cuda.device(dst.device):
                 run()
 
+    def decode_status(self) -> List[int]:
+        """Wait for the most recent decode call and return its per-chunk status words (0 = clean; bit 0: a rANS stream
+        did not return to its initial state, bit 1: stream offsets beyond the payload).  A nonzero word means the
+        container's bytes were damaged after its header was written: treat the chunk as a miss."""
+        with self._dec_lock:
+            if self._dec_status is None or self._dec_event is None:
+                return []
+            self._dec_event.synchronize()
+            return list((ctypes.c_uint32 * self._dec_status_n).from_address(self._dec_status.host_ptr))
+
     def decode_device_batch(self, batch: EncodedBatch, ntokens: Sequence[int], dst: KvView, dst_tok: Sequence[int],
                             stream: Optional[torch.cuda.Stream] = None) -> None:
         """Decode an EncodedBatch straight from its device staging buffer (no host hop, no header reads)."""
-        self.decode_raw(batch.buf.data_ptr(), [j * batch.stride for j in range(len(batch.sizes))], ntokens, dst,
-                        dst_tok, batch.max_dtype, stream)
+        self.decode_raw(batch.buf.data_ptr(), batch.buf.numel(), [j * batch.stride for j in range(len(batch.sizes))],
+                        batch.sizes, ntokens, dst, dst_tok, batch.max_dtype, batch.coder, stream)
 
     def decode(self, containers: Sequence[Union[bytes, bytearray, memoryview, torch.Tensor]], dst: KvView,
                dst_tok: Sequence[int], stream: Optional[torch.cuda.Stream] = None) -> None:
@@ -427,8 +475,9 @@ class CacheGenCodec:
             if isinstance(c, torch.Tensor):
                 hb = c[:N.HEADER_BYTES].cpu().numpy().tobytes()
                 hd = N.Header.from_buffer_copy(hb)
-                if hd.magic != N.MAGIC or hd.status != 0 or hd.total_bytes > c.numel():
+                if hd.magic != N.MAGIC or hd.version not in (1, 2) or hd.status != 0 or hd.total_bytes > c.numel():
                     raise ValueError("bad B2KV container tensor")
+                check_header(hd)
             else:
                 hd = parse_header(c)
             if (hd.L, hd.H, hd.D) != (dst.L, dst.H, dst.D):
@@ -436,8 +485,10 @@ class CacheGenCodec:
                                  f"{dst.L}/{dst.H}/{dst.D}")
             heads.append(hd)
         max_dtype = heads[0].max_dtype
-        if any(h.max_dtype != max_dtype for h in heads):
-            raise ValueError("containers of one decode call must share max_dtype")
+        if any(h.max_dtype != max_dtype or h.version != heads[0].version for h in heads):
+            raise ValueError("containers of one decode call must share max_dtype and container version")
+        coder = int(heads[0].version) - 1
+        totals = [int(h.total_bytes) for h in heads]
         ntoks = [int(h.ntokens) for h in heads]
         tmax = max(ntoks)
         for tok, nt in zip(dst_tok, ntoks):
@@ -446,12 +497,13 @@ class CacheGenCodec:
         with self._dec_lock, torch.cuda.device(dst.device):
             tstream = stream if stream is not None else torch.cuda.current_stream()
             sp = tstream.cuda_stream
-            need_in = sum(((int(h.total_bytes) + 15) & ~15) + 16 for h in heads) + 16
+            need_in = sum((int(h.total_bytes) + 15) & ~15 for h in heads) + N.READ_SLACK
             self._order_decode(tstream, need_in, lib.b200kv_decode_workspace_bytes(dst.L, dst.H, dst.D, tmax, n))
             if n == 1 and isinstance(containers[0], torch.Tensor) and containers[0].is_cuda \
-                    and containers[0].data_ptr() % 16 == 0 and containers[0].numel() >= int(heads[0].total_bytes) + 16:
+                    and containers[0].data_ptr() % 16 == 0 and containers[0].numel() >= totals[0] + N.READ_SLACK:
                 keep_dev = containers[0]
-                self.decode_raw(keep_dev.data_ptr(), [0], ntoks, dst, dst_tok, max_dtype, tstream, _locked=True)
+                self.decode_raw(keep_dev.data_ptr(), keep_dev.numel(), [0], totals, ntoks, dst, dst_tok, max_dtype, coder,
+                                tstream, _locked=True)
                 return
             self._dec_in = self._grow(self._dec_in, need_in, dst.device)
             base_ptr = self._dec_in.data_ptr()
@@ -468,5 +520,6 @@ class CacheGenCodec:
                 N.check(lib.b200kv_copy_async(base_ptr + o, src_ptr, nb, sp), "copy")
                 del keep
                 offsets.append(o)
-                o += ((nb + 15) & ~15) + 16
-            self.decode_raw(base_ptr, offsets, ntoks, dst, dst_tok, max_dtype, tstream, _locked=True)
+                o += (nb + 15) & ~15
+            self.decode_raw(base_ptr, self._dec_in.numel(), offsets, totals, ntoks, dst, dst_tok, max_dtype, coder, tstream,
+                            _locked=True)

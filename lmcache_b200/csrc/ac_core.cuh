@@ -638,6 +638,114 @@ B2_HD uint32_t dec_symbol2(DecState2& st, Src& src, const uint32_t* e, bool last
     return s4;
 }
 
+// ---------------------------------------------------------------- rANS coder ("B2KV" container version 2)
+// The arithmetic-coder bitstream is this build's own (the reference's coder lives in the absent torchac_cuda wheel;
+// SURVEY.md 8c), so container version 2 carries a cheaper entropy coder over the SAME per-stream 16-bit CDF section,
+// the same stream order and the same lengths section: range-ANS with a 32-bit state and 16-bit renormalisation.
+//
+// Normative stream format, one stream = one (plane, channel) over one group of g <= 256 tokens, CDF c[0..32]
+// (c[32] := 65536), start(s) = c[s], freq(s) = c[s+1] - c[s] >= 1:
+//   encoder   x = 2^16; for i = g-1 .. 0:  s = sym[i]; if (x >> 16) >= freq(s): push halfword (x & 0xffff), x >>= 16;
+//             x = (x / freq(s)) << 16 | ... i.e.  x = ((x / f) << 16) + (x mod f) + start(s)
+//   bytes     x as a little-endian uint32, then the pushed halfwords in REVERSE push order, each little-endian;
+//             length = 4 + 2 * pushes (always even)
+//   decoder   x = LE32(bytes[0..4)); for i = 0 .. g-1:  slot = x & 0xffff; s = max{ s : c[s] <= slot }; emit s;
+//             x = freq(s) * (x >> 16) + slot - start(s); if x < 2^16: x = (x << 16) | next LE16
+//             after the last symbol x == 2^16 again (a free integrity check of the stream).
+// No carries, no pending bits, no bit counting: one multiply per decoded symbol, one division per encoded symbol,
+// at most one 16-bit renormalisation step per symbol.  Cost: the 32-bit final state instead of the arithmetic
+// coder's ~2 termination bits (+19 bits per stream on average, measured).
+constexpr uint32_t kRansLow = 1u << 16;
+
+// decoder table entry i (0..31): (c[i] << 16) | freq(i).  The search compares entries against (slot << 16) | 0xffff
+// (c[i] <= slot  <=>  entry <= key, because freq <= 0xffff), and the winning entry carries start and freq.
+B2_HD uint32_t rans_table_entry(uint32_t c_i, uint32_t c_next) { return (c_i << 16) | ((c_next - c_i) & 0xffffu); }
+
+// x / f and x mod f for x < f << 16, 1 <= f < 2^16.  Device: one reciprocal, biased low so that the estimate is q or
+// q - 1 (never above), then one fix-up; exact whatever the approximation did.  Host: plain division.
+B2_HD uint32_t rans_divmod(uint32_t x, uint32_t f, uint32_t* rem) {
+#if defined(__CUDA_ARCH__)
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rn(f)));
+    // relative error of float(x) (RZ: <= 0), rcp (1 ulp) and the two products is < 2^-21; the factor keeps the
+    // estimate at or below the true quotient, and q < 2^16 bounds the shortfall by 0.06 < 1
+    uint32_t q = __float2uint_rz(__uint2float_rz(x) * (rc * 0.99999952316284179688f));
+    uint32_t r = x - q * f;
+    if (r >= f) { q += 1u; r -= f; }
+    *rem = r;
+    return q;
+#else
+    *rem = x % f;
+    return x / f;
+#endif
+}
+
+// Encoder step on the state alone; `emit(h)` receives the low halfword when the state must shrink first.
+template <class Emit>
+B2_HD void rans_enc_symbol(uint32_t& x, uint32_t start, uint32_t freq, Emit&& emit) {
+    const uint32_t xh = x >> 16;
+    if (xh >= freq) { emit(x & 0xffffu); x = xh; }
+    uint32_t r;
+    const uint32_t q = rans_divmod(x, freq, &r);
+    x = (q << 16) + r + start;
+}
+
+// Decoder state: x plus a two-word window over the stream's halfwords (aligned 32-bit loads, one word of look-ahead).
+// `sel` is the PRMT selector that builds (x << 16) | next halfword from (x, cur): 0x1054 takes cur's low half,
+// 0x1076 its high half.
+struct RansDec {
+    uint32_t x, cur, nxt, sel;
+};
+
+B2_HD uint32_t prmt32(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8u * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+
+// Word source concept: uint32_t next_le() -- next aligned 4 stream bytes as a little-endian word.
+// `odd` = 1 when the stream starts at the upper halfword of its first aligned word.
+template <class Src>
+B2_HD void rans_dec_init(RansDec& st, Src& src, uint32_t odd) {
+    const uint32_t w0 = src.next_le();
+    const uint32_t w1 = src.next_le();
+    st.x = funnel_r(w0, w1, 16u * odd);             // the 4 state bytes, wherever they start
+    st.cur = w1;
+    st.nxt = src.next_le();
+    st.sel = 0x1054u + 0x22u * odd;
+}
+
+// pull one halfword into the state (x < 2^16 on entry)
+template <class Src>
+B2_HD void rans_dec_renorm(RansDec& st, Src& src) {
+    if (st.x < kRansLow) {
+        st.x = prmt32(st.x, st.cur, st.sel);
+        const bool wrap = st.sel == 0x1076u;
+        st.sel ^= 0x22u;
+        if (wrap) { st.cur = st.nxt; st.nxt = src.next_le(); }
+    }
+}
+
+// Decode one symbol from table pk[0..31] (rans_table_entry); NSTEPS = 5 searches symbols 0..31, NSTEPS = 4
+// symbols 0..15.  Plain-C++ restatement used by the host tests; the kernels run the same arithmetic with the two top
+// search levels held in registers (codec.cu, rans_decode_stream).
+template <int NSTEPS, class Src>
+B2_HD uint32_t rans_dec_symbol(RansDec& st, Src& src, const uint32_t* pk) {
+    const uint32_t key = (st.x << 16) | 0xffffu;
+    uint32_t s = 0;
+#pragma unroll
+    for (int step = 1 << (NSTEPS - 1); step > 0; step >>= 1) s = pk[s + step] <= key ? s + step : s;
+    const uint32_t e = pk[s];
+    st.x = (e & 0xffffu) * (st.x >> 16) + ((key - e) >> 16);
+    rans_dec_renorm(st, src);
+    return s;
+}
+
 // ---------------------------------------------------------------- container layout (host + device)
 B2_HD int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
 

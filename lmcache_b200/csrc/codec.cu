@@ -29,6 +29,10 @@ constexpr int PAIRW = 33;          // split mode: words per CDF-pair row (32 sym
 constexpr int TEMPW_FUSED = 40;    // words per stream in the tile's temp rows: own-CDF streams of <= 256 symbols
                                    //   cost <= 256*log2(31) + 2 bits = 159 bytes
 constexpr int TEMPW_SPLIT = 132;   // foreign CDF (chunk > 256 tokens): <= 16 bits / symbol + termination; 16-byte rows
+constexpr int TEMPW_FUSED_RANS = 48;   // rANS, own-CDF streams: <= 95 renormalisation halfwords for ANY symbol order
+                                       //   (ideal <= 1268.5 bits, < 1 bit of overshoot per step); the 32-bit
+                                       //   final state goes to its own array.  Split mode: <= 1 halfword per symbol = 128 words
+constexpr int CODER_AC = 0, CODER_RANS = 1;   // B2KV container version = coder + 1
 
 struct EncParams {
     PlaneTable pt;
@@ -38,10 +42,12 @@ struct EncParams {
     int32_t n_chunks, chunk_tokens, last_chunk_tokens, tpp;   // tpp = tiles per plane
     int32_t tiles_full, tempw;                                 // tiles per full chunk; words per temp row
     int32_t stage_bytes;                                       // compact_kernel: bytes of shared-memory stage per CTA
+    int32_t coder;                                             // CODER_AC | CODER_RANS
     uint8_t* out;
     int64_t out_stride;
     uint64_t* sizes_out;
     uint32_t* temp;                  // [n_tiles][CT][tempw] coder output before compaction
+    uint32_t* rstate;                // rANS: [n_tiles][CT] final coder states (the first 4 bytes of every stream)
     uint32_t* tile_tot;              // [n_chunks][tiles_full] bytes per tile, then exclusive prefix (in place)
     unsigned long long* totals;      // [n_chunks] payload bytes
     unsigned int* err;               // [n_chunks]
@@ -179,6 +185,45 @@ __device__ __forceinline__ void for_each_symbol(const uint16_t* cbase, const int
     }
 }
 
+// Same walk from the last token to the first (rANS codes a stream back to front so that the decoder runs forwards).
+template <int DT, bool PAGED, int BT, class F>
+__device__ __forceinline__ void for_each_symbol_rev(const uint16_t* cbase, const int64_t* slot_map, int64_t tokabs, int64_t s1,
+                                                    int gt, const float* fac, float maxq, F&& f) {
+    const int nbatch = (gt + BT - 1) / BT;
+    uint16_t xa[BT], xb[BT];
+    auto load = [&](uint16_t (&x)[BT], int b) {
+        const int tk = b * BT;
+#pragma unroll
+        for (int k = 0; k < BT; ++k)
+            x[k] = tk + k < gt ? __ldg(cbase + tok_row<PAGED>(slot_map, tokabs + tk + k) * s1) : (uint16_t)0;
+    };
+    auto use = [&](const uint16_t (&x)[BT], int b) {
+        const int tk = b * BT;
+        uint32_t q[BT];
+#pragma unroll
+        for (int k = 0; k < BT; ++k) q[k] = quant_symbol(half_to_float(x[k], DT), fac[min(tk + k, kGroup - 1)], maxq);
+#pragma unroll
+        for (int k = BT - 1; k >= 0; --k)
+            if (tk + k < gt) f(q[k]);
+    };
+    load(xa, nbatch - 1);
+    for (int b = nbatch - 1; b >= 0; b -= 2) {
+        if (b >= 1) load(xb, b - 1);
+        use(xa, b);
+        if (b >= 1) {
+            if (b >= 2) load(xa, b - 2);
+            use(xb, b - 1);
+        }
+    }
+}
+
+// rANS encoder step as the kernels run it: the state shrinks by one halfword when it must (stored at a descending
+// halfword pointer into the stream's temp row -- the row then holds the halfwords in decode order), then
+// x = (x / f) << 16 | (x mod f) + start with the reciprocal division of ac_core.cuh.
+__device__ __forceinline__ void rans_put(uint32_t& x, uint16_t*& wp, uint32_t start, uint32_t freq) {
+    rans_enc_symbol(x, start, freq, [&](uint32_t h) { *--wp = (uint16_t)h; });
+}
+
 // ------------------------------------------------------------------------------------------ encode
 // One tile = CT consecutive channels of one plane and one <= 256-token group; one thread = one coder stream.
 // FUSED (chunk <= 256 tokens): quantise -> 5-bit symbols in shared memory + thread-private histogram -> CDF (the
@@ -189,7 +234,7 @@ __device__ __forceinline__ void for_each_symbol(const uint16_t* cbase, const int
 // Coder output goes to the tile's temp rows in global memory (sparse 32-bit stores, merged in L2); stream lengths go to
 // the container; the tile's byte total goes to tile_tot.  Compaction into the contiguous payload (collect_bytes in the
 // reference) is done by scan_kernel + compact_kernel afterwards, so no CTA ever waits on another one.
-template <bool FUSED, int DT, bool PAGED>
+template <bool FUSED, int DT, bool PAGED, int CODER>
 __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     // FUSED : symbol rows u32[CT][SYMW] | cdf rows u16[CT][33] (also the histogram) | fac[256] (later fl32(n/t)[257])
@@ -329,8 +374,34 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
             uint16_t* dstc = reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
             for (int e = tid; e < ncols * kLp; e += CT) dstc[e] = cdfr[e];
         }
-        // ---- pass 2: arithmetic-code the stream (branch-light core, see ac_core.cuh)
-        if (active) {
+        // ---- pass 2: entropy-code the stream
+        if (active && CODER == CODER_RANS) {
+            // rANS: last token first; halfwords land at a descending pointer, so the row's tail is the stream in
+            // decode order.  Row capacity (96 halfwords) cannot be exceeded: no clamp, no flag.
+            uint32_t x = kRansLow;
+            uint16_t* const wend = reinterpret_cast<uint16_t*>(trow) + 2 * TEMPW_FUSED_RANS;
+            uint16_t* wp = wend;
+            int w = (gt - 1) / SPW;
+            {
+                const uint32_t word = myrow[w];
+                for (int k = gt - 1 - w * SPW; k >= 0; --k) {
+                    const uint32_t sidx = (word >> (5 * k)) & 31u;
+                    const uint32_t c_lo = crow[sidx];
+                    rans_put(x, wp, c_lo, (uint32_t)crow[sidx + 1u] - c_lo);
+                }
+            }
+            for (--w; w >= 0; --w) {
+                const uint32_t word = myrow[w];
+#pragma unroll
+                for (int k = SPW - 1; k >= 0; --k) {
+                    const uint32_t sidx = (word >> (5 * k)) & 31u;       // <= 30: crow[sidx + 1] is a real entry
+                    const uint32_t c_lo = crow[sidx];
+                    rans_put(x, wp, c_lo, (uint32_t)crow[sidx + 1u] - c_lo);
+                }
+            }
+            P.rstate[(int64_t)blockIdx.x * CT + tid] = x;
+            len = 4u + 2u * (uint32_t)(wend - wp);
+        } else if (active) {
             EncState2 st;
             st.init();
             int tk = 0;
@@ -371,14 +442,27 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
                 const uint32_t hi = (i == 31) ? 0x10000u : cv[i + 1];
                 prow[i] = cv[i] | ((hi - cv[i]) << 16);
             }
-            EncState2 st;
-            st.init();
-            for_each_symbol<DT, PAGED, 4>(cbase, P.slot_map, tokabs, s1, gt, fac, maxq, [&](uint32_t q) {
-                const uint32_t pr = prow[q];
-                enc_symbol2(st, pr & 0xffffu, pr >> 16, trow, cap);
-            });
-            len = enc_finish2(st, trow, cap);
-            if (st.w > cap) atomicOr(&P.err[j], 1u);
+            if (CODER == CODER_RANS) {
+                // at most one halfword per symbol: the 264-halfword row cannot overflow
+                uint32_t x = kRansLow;
+                uint16_t* const wend = reinterpret_cast<uint16_t*>(trow) + 2 * TEMPW_SPLIT;
+                uint16_t* wp = wend;
+                for_each_symbol_rev<DT, PAGED, 4>(cbase, P.slot_map, tokabs, s1, gt, fac, maxq, [&](uint32_t q) {
+                    const uint32_t pr = prow[q];
+                    rans_put(x, wp, pr & 0xffffu, pr >> 16);
+                });
+                P.rstate[(int64_t)blockIdx.x * CT + tid] = x;
+                len = 4u + 2u * (uint32_t)(wend - wp);
+            } else {
+                EncState2 st;
+                st.init();
+                for_each_symbol<DT, PAGED, 4>(cbase, P.slot_map, tokabs, s1, gt, fac, maxq, [&](uint32_t q) {
+                    const uint32_t pr = prow[q];
+                    enc_symbol2(st, pr & 0xffffu, pr >> 16, trow, cap);
+                });
+                len = enc_finish2(st, trow, cap);
+                if (st.w > cap) atomicOr(&P.err[j], 1u);
+            }
         }
     }
 
@@ -525,6 +609,35 @@ __device__ __forceinline__ void copy_row(uint8_t* d, const uint32_t* srcw, uint3
     }
 }
 
+// rANS stream: the 32-bit final state (little-endian), then the tail of the temp row -- `nb` bytes of halfwords that the
+// coder stored at descending addresses, already in decode order.  d is 2-byte aligned (every stream length is even).
+// 16-byte loads, four in flight; typical streams (a few dozen bytes) take one round.
+__device__ __forceinline__ void copy_row_rans(uint8_t* d, const uint32_t* row, uint32_t rowbytes, uint32_t nb, uint32_t state) {
+    uint16_t* dh = reinterpret_cast<uint16_t*>(d);
+    dh[0] = (uint16_t)state;
+    dh[1] = (uint16_t)(state >> 16);
+    const uint32_t h0 = (rowbytes - nb) >> 1;                  // first halfword of the stream inside the row
+    const uint32_t hend = rowbytes >> 1;
+    constexpr int NLV = 4;
+    for (uint32_t q0 = h0 >> 3; 8u * q0 < hend; q0 += NLV) {
+        uint4 v[NLV];
+#pragma unroll
+        for (int q = 0; q < NLV; ++q)
+            if (8u * (q0 + q) < hend) v[q] = __ldg(reinterpret_cast<const uint4*>(row) + q0 + q);
+#pragma unroll
+        for (int q = 0; q < NLV; ++q) {
+            if (8u * (q0 + q) < hend) {
+                const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (uint32_t i = 0; i < 8u; ++i) {
+                    const uint32_t hw = 8u * (q0 + q) + i;
+                    if (hw >= h0) dh[2u + hw - h0] = (uint16_t)(w[i >> 1] >> (16u * (i & 1u)));
+                }
+            }
+        }
+    }
+}
+
 // move each tile's streams from its temp rows to their final, contiguous place in the payload
 // (collect_bytes, cachegen_encoder.py:225-238).  Each thread copies its own stream into a shared-memory image of the
 // tile's byte range (placed at the destination's 16-byte phase), then the CTA writes that range with 16-byte vector
@@ -540,7 +653,9 @@ __global__ void __launch_bounds__(CT, 9) compact_kernel(EncParams P) {
     uint8_t* cont = P.out + (int64_t)id.j * P.out_stride;
     const Layout lo = make_layout(P.L, P.C, id.t);
     const int32_t* lengths = reinterpret_cast<const int32_t*>(cont + lo.off_lengths) + ((int64_t)id.g * NL + id.nl) * P.C;
-    const uint32_t len = c < P.C ? min((uint32_t)lengths[c], (uint32_t)P.tempw * 4u) : 0u;
+    const bool rans = P.coder == CODER_RANS;
+    const uint32_t rowbytes = (uint32_t)P.tempw * 4u;
+    const uint32_t len = c < P.C ? min((uint32_t)lengths[c], rowbytes + (rans ? 4u : 0u)) : 0u;
     uint32_t tile_total;
     const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
     const uint64_t base = P.tile_tot[(int64_t)id.j * P.tiles_full + id.tile_in_chunk];
@@ -554,7 +669,12 @@ __global__ void __launch_bounds__(CT, 9) compact_kernel(EncParams P) {
     // the image of the tile's byte range must fit the shared-memory stage the launch provided; a tile coded against a
     // foreign CDF may (rarely) exceed it, then every thread writes its own stream straight to the payload
     const bool staged = phase + tile_total <= (uint32_t)P.stage_bytes;
-    if (len) {
+    if (len && rans) {
+        const uint32_t* srcw = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
+        const uint32_t state = P.rstate[(int64_t)blockIdx.x * CT + tid];
+        if (staged) copy_row_rans(stage + phase + my_off, srcw, rowbytes, max(len, 4u) - 4u, state);
+        else copy_row_rans(dst + my_off, srcw, rowbytes, max(len, 4u) - 4u, state);
+    } else if (len) {
         const uint32_t* srcw = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
         // two instantiations, so that the staged one compiles to shared-memory stores and not to generic ones
         if (staged) {
@@ -587,7 +707,7 @@ __global__ void finalize_kernel(EncParams P) {
     const Layout lo = make_layout(P.L, P.C, t);
     b200kv_header* hd = reinterpret_cast<b200kv_header*>(P.out + (int64_t)j * P.out_stride);
     hd->magic = B200KV_MAGIC;
-    hd->version = B200KV_CONTAINER_VERSION;
+    hd->version = (uint32_t)P.coder + 1u;          // 1: arithmetic coder, 2: rANS
     hd->L = P.L; hd->H = P.H; hd->D = P.D;
     hd->ntokens = t;
     hd->ngroups = lo.ngroups;
@@ -604,6 +724,8 @@ struct DecChunk {
     const uint8_t* base;
     int64_t dst_tok;
     int32_t t, ngroups;
+    uint32_t payload_bytes;      // from the (host-validated) header: stream offsets are clamped to it
+    uint32_t pad;
 };
 
 struct DecParams {
@@ -613,6 +735,8 @@ struct DecParams {
     int32_t L, H, D, C, out_dtype, max_dtype, n_chunks, tpp, tiles_max;
     const DecChunk* chunks;      // device
     unsigned long long* tile_base;   // [n_chunks][tiles_max]: tile sums, then exclusive prefix
+    uint32_t* status;            // [n_chunks] or NULL: bit 0 = a rANS stream did not return to its initial state,
+                                 //   bit 1 = stream offsets beyond the payload (corrupt lengths section)
 };
 
 // tile sums of the stream lengths: one warp per tile
@@ -675,7 +799,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(DecParams P) {
 // load for word i+1 is issued when word i is consumed, so its L2/L1 latency overlaps ~8+ symbols of decoding.
 // Each lane walks its own stream; a 32-byte sector serves 8 consecutive refills from L1.
 struct WordSrc {
-    const uint32_t* base;
+    const uint32_t* base;   // the container, as words
     uint32_t idx;        // next word to load: a 32-bit index keeps the refill to one IMAD.WIDE + one add
     uint32_t ahead;
     __device__ __forceinline__ void prime() { ahead = __ldg(base + idx); ++idx; }
@@ -685,6 +809,16 @@ struct WordSrc {
         ++idx;
         return __byte_perm(w, 0u, 0x0123);
     }
+};
+// Both readers may run past the end of their stream (a decoder consumes at most 18 bits (arithmetic coder) / one
+// halfword (rANS) per symbol, whatever the bytes say): at most B200KV_READ_SLACK bytes past the stream's start, which
+// b200kv_decode_chunks checks against the size of the caller's buffer.  A corrupt lengths section therefore cannot make
+// a kernel read outside that buffer: stream starts are clamped to the payload, reads are bounded from there.
+
+// rANS: aligned little-endian words off a running pointer; the look-ahead lives in the decoder state (RansDec::nxt)
+struct LeWordSrc {
+    const uint32_t* p;
+    __device__ __forceinline__ uint32_t next_le() { return __ldg(p++); }
 };
 
 __device__ __forceinline__ uint16_t out_half(float v, int dt) {
@@ -698,13 +832,25 @@ __device__ __forceinline__ void store_half(uint16_t* p, float v) {
     else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
 }
 
+// value = lut * row_max (one rounded multiply, cachegen_decoder.py:31-35), converted RNE and stored as 16 bits
+// (F2FP + STG.U16, no register merge in between)
+template <int OUT_DT>
+__device__ __forceinline__ void store_dequant(uint16_t* p, float lutv, float row_max) {
+    const float v = __fmul_rn(lutv, row_max);
+    if constexpr (OUT_DT)
+        asm volatile("{\n\t.reg .b16 h;\n\tcvt.rn.f16.f32 h, %1;\n\tst.global.b16 [%0], h;\n\t}" ::"l"(p), "f"(v) : "memory");
+    else
+        asm volatile("{\n\t.reg .b16 h;\n\tcvt.rn.bf16.f32 h, %1;\n\tst.global.b16 [%0], h;\n\t}" ::"l"(p), "f"(v) : "memory");
+}
+
 // per-thread decode loop: one stream, gt symbols, straight to the destination layout.
 // PAGED: dst is the stream's channel in row 0 of the plane and `slots` points at the group's first slot-map entry.
 template <int OUT_DT, int NSTEPS, bool PAGED>
-__device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uint32_t* erow, const float* lut,
-                                              const float* mx, uint16_t* dst, uint32_t sT, int gt, const int64_t* slots) {
-    const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(my_bytes) & 3u);
-    WordSrc src{reinterpret_cast<const uint32_t*>(my_bytes - skip), 0u, 0u};
+__device__ __forceinline__ void decode_stream(const uint8_t* cont, uint32_t my_off, const uint32_t* erow,
+                                              const float* lut, const float* mx, uint16_t* dst, uint32_t sT, int gt,
+                                              const int64_t* slots) {
+    const uint32_t skip = my_off & 3u;            // containers are 16-byte aligned
+    WordSrc src{reinterpret_cast<const uint32_t*>(cont), my_off >> 2, 0u};
     src.prime();
     DecState2 st;
     dec_init2(st, src, skip);
@@ -724,14 +870,70 @@ __device__ __forceinline__ void decode_stream(const uint8_t* my_bytes, const uin
     }
 }
 
-// One tile = CT streams of one (chunk, group, plane).  Only the CDF rows (66 B per stream, contiguous in the
-// container so they are staged with one coalesced copy), the row maxima and a 32-entry dequantisation LUT live in
-// shared memory (~10 KB per CTA), so many CTAs stay resident and hide the serial latency of each stream's coder.
-// Symbols are dequantised and stored straight into the destination layout (no uint8 / fp32 intermediates in HBM).
-template <int OUT_DT, bool PAGED>
+// rANS decode loop (container version 2): one stream, gt symbols, straight to the destination layout.
+// Per symbol: key = (x << 16) | 0xffff; lower-bound search over the stream's packed table pk[i] = (cdf[i] << 16) | freq(i)
+// -- the two top levels sit in registers, the rest are LDS off a running shared-memory address --; the winning entry
+// carries start and freq, so the state update is one multiply-add; at most one 16-bit renormalisation (a PRMT out of the
+// two-word window, a predicated aligned load when the window moves on).  Returns the final state (2^16 when intact).
+template <int OUT_DT, int NSTEPS, bool PAGED>
+__device__ __forceinline__ uint32_t rans_decode_stream(const uint8_t* cont, uint32_t my_off, const uint32_t* pk,
+                                                       const float* lut, const float* mx, uint16_t* dst, uint32_t sT, int gt,
+                                                       const int64_t* slots) {
+    LeWordSrc src{reinterpret_cast<const uint32_t*>(cont) + (my_off >> 2)};
+    RansDec st;
+    rans_dec_init(st, src, (my_off >> 1) & 1u);
+    constexpr uint32_t H = 1u << (NSTEPS - 1);
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(pk);
+    const uint32_t r_mid = pk[H], r_lo = pk[H / 2], r_hi = pk[H + H / 2];
+    const uint32_t lut_rel = (uint32_t)__cvta_generic_to_shared(lut) - a0;     // lut[s] lives at (a0 + 4 s) + lut_rel
+    uint16_t* d = dst;
+    auto step = [&](float row_max, int i) {
+        const uint32_t key = st.x * 65536u + 0xffffu;                            // (x << 16) | 0xffff, one IMAD
+        const bool p1 = r_mid <= key;
+        uint32_t a = p1 ? a0 + 4u * H : a0;
+        const uint32_t m = p1 ? r_hi : r_lo;
+        a = m <= key ? a + 2u * H : a;
+        dec_search_steps<H / 4>(a, key);
+        uint32_t e;
+        float lv;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lv) : "r"(a + lut_rel));
+        st.x = (e & 0xffffu) * (st.x >> 16) + ((key - e) >> 16);
+        // renormalisation, branch-free (a warp takes this path on most symbols, so a branch would run for all lanes
+        // anyway): p = x < 2^16 -> pull the next halfword out of the window; q = p and the window's upper half was
+        // taken -> the window moves on (cur = nxt, nxt = next aligned word)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.lt.u32 p, %0, 65536;\n\t"
+            "@p prmt.b32 %0, %0, %1, %3;\n\t"
+            "setp.eq.and.u32 q, %3, 0x1076, p;\n\t"
+            "@p xor.b32 %3, %3, 0x22;\n\t"
+            "@q mov.b32 %1, %2;\n\t"
+            "@q ld.global.nc.u32 %2, [%4];\n\t"
+            "@q add.u64 %4, %4, 4;\n\t"
+            "}"
+            : "+r"(st.x), "+r"(st.cur), "+r"(st.nxt), "+r"(st.sel), "+l"(src.p));
+        store_dequant<OUT_DT>(PAGED ? dst + __ldg(slots + (PAGED ? i : 0)) * (int64_t)sT : d, lv, row_max);
+        if constexpr (!PAGED) d += sT;
+    };
+    int i = 0;
+    for (; i + 4 <= gt; i += 4) {
+        const float4 m4 = *reinterpret_cast<const float4*>(mx + i);            // four row maxima per LDS.128
+        step(m4.x, i); step(m4.y, i + 1); step(m4.z, i + 2); step(m4.w, i + 3);
+    }
+    for (; i < gt; ++i) step(mx[i], i);
+    return st.x;
+}
+
+// One tile = CT streams of one (chunk, group, plane).  Only the per-stream tables (33 words per stream, built from the
+// 66-byte CDF rows which are contiguous in the container: one coalesced read), the row maxima and a 32-entry
+// dequantisation LUT live in shared memory (~18 KB per CTA), so many CTAs stay resident and hide the serial latency of
+// each stream's coder.  Symbols are dequantised and stored straight into the destination layout (no uint8 / fp32
+// intermediates in HBM).  CODER selects the payload format (container version 1: arithmetic coder, 2: rANS).
+template <int OUT_DT, bool PAGED, int CODER>
 __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* tab = smem;                                                            // CT * 33 words: cdf << 16 (rows of 33, odd)
+    uint32_t* tab = smem;                                                            // CT * 33 words (rows of 33, odd)
     float* mx = reinterpret_cast<float*>(smem + CT * kLp);                           // kGroup
     float* lut = mx + kGroup;                                                        // 32
     __shared__ uint32_t s_warp[CT / 32];
@@ -757,14 +959,24 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     const int32_t* lengths = reinterpret_cast<const int32_t*>(dc.base + lo.off_lengths) + ((int64_t)g * NL + nl) * P.C;
     const uint32_t len = active ? (uint32_t)lengths[c] : 0u;
     uint32_t tile_total;
-    const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
-    const uint8_t* my_bytes = dc.base + lo.off_payload + P.tile_base[(int64_t)j * P.tiles_max + tile] + my_off;
+    const uint32_t my_rel = block_excl_scan(len, s_warp, &tile_total);
+    // the stream's byte offset inside the container; a corrupt lengths section cannot push it outside the payload
+    const unsigned long long want = P.tile_base[(int64_t)j * P.tiles_max + tile] + my_rel;
+    const bool beyond = want + len > (unsigned long long)dc.payload_bytes;
+    const uint32_t my_off = (uint32_t)lo.off_payload + (uint32_t)min(want, (unsigned long long)dc.payload_bytes);
 
-    // stage CDF rows (one contiguous run of ncols * 33 halfwords), row maxima, LUT
+    // stage the per-stream tables (one contiguous run of ncols * 33 halfwords in the container), row maxima, LUT
     const uint16_t* cdf_src = reinterpret_cast<const uint16_t*>(dc.base + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
     for (int e = tid; e < ncols * kLp; e += CT) {
         const uint32_t i = (uint32_t)e % (uint32_t)kLp;
-        tab[e] = dec_table_entry(i, __ldg(cdf_src + e));
+        const uint32_t c0 = __ldg(cdf_src + e);
+        if constexpr (CODER == CODER_RANS) {
+            // (cdf[i] << 16) | freq(i); cdf[32] is stored as 0 and stands for 65536; entry 32 is never searched
+            const uint32_t c1 = i < 31u ? (uint32_t)__ldg(cdf_src + e + 1) : 0x10000u;
+            tab[e] = i < 32u ? rans_table_entry(c0, c1) : 0xFFFFFFFFu;
+        } else {
+            tab[e] = dec_table_entry(i, c0);
+        }
     }
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(dc.base + lo.off_maxes) + (int64_t)nl * dc.t + tok0;
     for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
@@ -778,8 +990,17 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     uint16_t* dst = const_cast<uint16_t*>(P.pt.p[nl]) + (PAGED ? 0 : (dc.dst_tok + tok0) * P.sT) + (int64_t)h * P.sH +
                     (c - h * P.D);
     const int64_t* slots = PAGED ? P.slot_map + dc.dst_tok + tok0 : nullptr;
-    if (cq <= 7.0f) decode_stream<OUT_DT, 4, PAGED>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);   // <= 16 bins: symbols 0..14
-    else decode_stream<OUT_DT, 5, PAGED>(my_bytes, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);
+    uint32_t bad = beyond ? 2u : 0u;
+    if constexpr (CODER == CODER_RANS) {
+        uint32_t xf;
+        if (cq <= 7.0f) xf = rans_decode_stream<OUT_DT, 4, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);
+        else xf = rans_decode_stream<OUT_DT, 5, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);
+        bad |= xf != kRansLow ? 1u : 0u;
+    } else {
+        if (cq <= 7.0f) decode_stream<OUT_DT, 4, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);   // <= 16 bins: symbols 0..14
+        else decode_stream<OUT_DT, 5, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);
+    }
+    if (bad != 0u && P.status != nullptr) atomicOr(&P.status[j], bad);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -830,12 +1051,17 @@ struct ProfScope {
     }
 };
 
-static size_t enc_ws_layout(int64_t n_tiles_alloc, int n_chunks, int tempw, size_t* off_tot, size_t* off_totals,
-                            size_t* off_err, size_t* off_temp) {
+static int enc_tempw(bool fused, int coder) {
+    return fused ? (coder == CODER_RANS ? TEMPW_FUSED_RANS : TEMPW_FUSED) : TEMPW_SPLIT;
+}
+
+static size_t enc_ws_layout(int64_t n_tiles_alloc, int n_chunks, int tempw, int coder, size_t* off_tot, size_t* off_totals,
+                            size_t* off_err, size_t* off_state, size_t* off_temp) {
     size_t o = 0;
     *off_tot = o;    o += (size_t)n_tiles_alloc * 4;  o = (o + 255) & ~(size_t)255;
     *off_totals = o; o += (size_t)n_chunks * 8;       o = (o + 255) & ~(size_t)255;
     *off_err = o;    o += (size_t)n_chunks * 4;       o = (o + 255) & ~(size_t)255;
+    *off_state = o;  o += coder == CODER_RANS ? (size_t)n_tiles_alloc * CT * 4 : 0;  o = (o + 255) & ~(size_t)255;
     *off_temp = o;   o += (size_t)n_tiles_alloc * CT * (size_t)tempw * 4;
     return (o + 255) & ~(size_t)255;
 }
@@ -861,18 +1087,21 @@ int b200kv_container_layout(int32_t L, int32_t H, int32_t D, int32_t ntokens, b2
     out->off_lengths = lo.off_lengths;
     out->off_payload = lo.off_payload;
     out->fixed_bytes = lo.off_payload;
-    // <= 16 bits per symbol (CDF width >= 1/65536) + 2 flush bits + pad, per stream per group; +16 read slack
+    // per stream per group: <= 16 bits per symbol (CDF width >= 1/65536) + termination -- 2 flush bits + pad for the
+    // arithmetic coder, the 32-bit final state for rANS
     const int64_t streams = 2 * (int64_t)L * H * D;
-    out->max_total_bytes = align16(lo.off_payload + streams * (2 * (int64_t)ntokens + 2 * (int64_t)lo.ngroups) + 16);
+    out->max_total_bytes = align16(lo.off_payload + streams * (2 * (int64_t)ntokens + 4 * (int64_t)lo.ngroups) + 16);
     return 0;
 }
 
-int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks) {
+int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks,
+                                      int32_t coder) {
     if (L <= 0 || H <= 0 || D <= 0 || chunk_tokens <= 0 || n_chunks <= 0) return -2;
+    if (coder != CODER_AC && coder != CODER_RANS) return -2;
     const int64_t G = (chunk_tokens + kGroup - 1) / kGroup;
     const int64_t n_tiles = (int64_t)n_chunks * G * 2 * L * tiles_per_plane(H * D);
-    size_t a, b, c, d;
-    return (int64_t)enc_ws_layout(n_tiles, n_chunks, chunk_tokens <= kGroup ? TEMPW_FUSED : TEMPW_SPLIT, &a, &b, &c, &d);
+    size_t a, b, c, d, e;
+    return (int64_t)enc_ws_layout(n_tiles, n_chunks, enc_tempw(chunk_tokens <= kGroup, coder), coder, &a, &b, &c, &d, &e);
 }
 
 int64_t b200kv_decode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks) {
@@ -884,12 +1113,14 @@ int64_t b200kv_decode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t c
 }
 
 int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_chunks, int32_t chunk_tokens,
-                         int32_t last_chunk_tokens, const float* key_bins, const float* value_bins, void* out,
-                         int64_t out_stride, uint64_t* sizes_out, void* workspace, int64_t workspace_bytes,
+                         int32_t last_chunk_tokens, const float* key_bins, const float* value_bins, int32_t coder,
+                         void* out, int64_t out_stride, uint64_t* sizes_out, void* workspace, int64_t workspace_bytes,
                          void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     EncParams P;
     B2_REQUIRE(key_bins && value_bins, "bins are NULL");
+    B2_REQUIRE(coder == CODER_AC || coder == CODER_RANS, "coder must be B200KV_CODER_AC or B200KV_CODER_RANS");
+    P.coder = coder;
     if (int rc = make_plane_table(kv, key_bins, value_bins, &P.pt)) return rc;
     B2_REQUIRE(n_chunks > 0 && chunk_tokens > 0, "n_chunks / chunk_tokens must be positive");
     B2_REQUIRE(last_chunk_tokens > 0 && last_chunk_tokens <= chunk_tokens, "last_chunk_tokens out of range");
@@ -914,9 +1145,9 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     const int64_t n_tiles = (int64_t)n_chunks * tiles_full;     // tiles beyond a ragged last chunk exit at once
     const bool fused = chunk_tokens <= kGroup;
     P.tiles_full = (int32_t)tiles_full;
-    P.tempw = fused ? TEMPW_FUSED : TEMPW_SPLIT;
-    size_t off_tot, off_totals, off_err, off_temp;
-    const size_t need = enc_ws_layout(n_tiles, n_chunks, P.tempw, &off_tot, &off_totals, &off_err, &off_temp);
+    P.tempw = enc_tempw(fused, coder);
+    size_t off_tot, off_totals, off_err, off_state, off_temp;
+    const size_t need = enc_ws_layout(n_tiles, n_chunks, P.tempw, coder, &off_tot, &off_totals, &off_err, &off_state, &off_temp);
     B2_REQUIRE(workspace != nullptr && workspace_bytes >= (int64_t)need, "workspace too small");
     B2_REQUIRE(n_tiles < (1ll << 31) && tiles_full < (1ll << 31), "too many tiles in one call");
     uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -924,7 +1155,8 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     P.totals = reinterpret_cast<unsigned long long*>(ws + off_totals);
     P.err = reinterpret_cast<unsigned int*>(ws + off_err);
     P.temp = reinterpret_cast<uint32_t*>(ws + off_temp);
-    B2_CHECK_CUDA(cudaMemsetAsync(ws, 0, off_temp, stream));     // counters only; temp rows need no init
+    P.rstate = reinterpret_cast<uint32_t*>(ws + off_state);
+    B2_CHECK_CUDA(cudaMemsetAsync(ws, 0, off_state, stream));    // counters only; states and temp rows need no init
 
     // 1) per-(plane, token) absmax -> maxes sections
     const int64_t total_tokens = (int64_t)(n_chunks - 1) * chunk_tokens + last_chunk_tokens;
@@ -946,11 +1178,16 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     const size_t smem_fused = (size_t)(((CT * SYMW + (CT * kLp * 2 + 3) / 4 + 3) & ~3) + kGroup + 8) * 4;
     const size_t smem_split = (size_t)(((CT * PAIRW + 3) & ~3) + kGroup + 4) * 4;
     const size_t smem_cdf = (size_t)(CT * PAIRW + kGroup) * 4;
+#define B2_LAUNCH_ENC1(FUSED, DT, PAGED, CODER, SMEM)                                                      \
+    do {                                                                                                   \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<FUSED, DT, PAGED, CODER>,                         \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));     \
+        encode_kernel<FUSED, DT, PAGED, CODER><<<(unsigned)n_tiles, CT, (SMEM), stream>>>(P);              \
+    } while (0)
 #define B2_LAUNCH_ENC(FUSED, DT, PAGED, SMEM)                                                              \
     do {                                                                                                   \
-        B2_CHECK_CUDA(cudaFuncSetAttribute(encode_kernel<FUSED, DT, PAGED>,                                \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));     \
-        encode_kernel<FUSED, DT, PAGED><<<(unsigned)n_tiles, CT, (SMEM), stream>>>(P);                     \
+        if (coder == CODER_RANS) B2_LAUNCH_ENC1(FUSED, DT, PAGED, CODER_RANS, SMEM);                       \
+        else B2_LAUNCH_ENC1(FUSED, DT, PAGED, CODER_AC, SMEM);                                             \
     } while (0)
 #define B2_LAUNCH_ENC2(FUSED, SMEM)                                                                        \
     do {                                                                                                   \
@@ -978,6 +1215,7 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     }
 #undef B2_LAUNCH_ENC2
 #undef B2_LAUNCH_ENC
+#undef B2_LAUNCH_ENC1
     B2_CHECK_CUDA(cudaGetLastError());
     // 3) compaction (collect_bytes) + headers + sizes
     {
@@ -985,7 +1223,8 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
         // stage = the fused mode's worst case (128 x 160 B + alignment phase); in split mode a tile can in principle
         // reach 128 x 528 B, but sizing the stage for that would leave 3 CTAs per SM for streams that are typically
         // a few dozen bytes long -- oversized tiles take the direct path inside the kernel
-        P.stage_bytes = CT * TEMPW_FUSED * 4 + 32;
+        P.stage_bytes = coder == CODER_RANS ? CT * (TEMPW_FUSED_RANS * 4 + 4) + 32 : CT * TEMPW_FUSED * 4 + 32;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.stage_bytes));
         enc_scan_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(P);
         compact_kernel<<<(unsigned)n_tiles, CT, (size_t)P.stage_bytes, stream>>>(P);
         finalize_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P);
@@ -994,15 +1233,17 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     return 0;
 }
 
-int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const int32_t* ntokens,
-                         const int64_t* dst_tok, int32_t n_chunks, int32_t max_dtype, const b200kv_kv_desc* dst,
-                         const float* key_bins, const float* value_bins, void* workspace,
-                         int64_t workspace_bytes, void* stream_) {
+int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const int64_t* offsets,
+                         const int64_t* total_bytes, const int32_t* ntokens, const int64_t* dst_tok, int32_t n_chunks,
+                         int32_t max_dtype,
+                         int32_t coder, const b200kv_kv_desc* dst, const float* key_bins, const float* value_bins,
+                         uint32_t* status_out, void* workspace, int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DecParams P;
     B2_REQUIRE(key_bins && value_bins, "bins are NULL");
+    B2_REQUIRE(coder == CODER_AC || coder == CODER_RANS, "coder must be B200KV_CODER_AC or B200KV_CODER_RANS");
     if (int rc = make_plane_table(dst, key_bins, value_bins, &P.pt)) return rc;
-    B2_REQUIRE(containers && offsets && ntokens && dst_tok && n_chunks > 0, "bad chunk arrays");
+    B2_REQUIRE(containers && offsets && total_bytes && ntokens && dst_tok && n_chunks > 0, "bad chunk arrays");
     B2_REQUIRE(max_dtype == B200KV_DT_BF16 || max_dtype == B200KV_DT_FP16, "bad max_dtype");
     B2_REQUIRE(dst->sT > 0 && dst->sT < (1ll << 23), "destination token stride out of range");
     P.sT = dst->sT; P.sH = dst->sH;
@@ -1014,6 +1255,12 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     for (int j = 0; j < n_chunks; ++j) {
         B2_REQUIRE(ntokens[j] > 0, "ntokens must be positive");
         B2_REQUIRE((offsets[j] & 15) == 0, "container offsets must be 16-byte aligned");
+        // the fixed sections are addressed from (L, H, D, ntokens); the buffer must hold them in full
+        const Layout lj = make_layout(P.L, P.C, ntokens[j]);
+        B2_REQUIRE(total_bytes[j] >= lj.off_payload && total_bytes[j] - lj.off_payload < (1ll << 32),
+                   "container shorter than its fixed sections (truncated or corrupt)");
+        B2_REQUIRE(offsets[j] >= 0 && offsets[j] + total_bytes[j] + B200KV_READ_SLACK <= containers_bytes,
+                   "containers buffer must extend B200KV_READ_SLACK bytes past the end of every container");
         tmax = ntokens[j] > tmax ? ntokens[j] : tmax;
     }
     const int64_t Gmax = (tmax + kGroup - 1) / kGroup;
@@ -1033,6 +1280,9 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
             hc[j].dst_tok = dst_tok[j];
             hc[j].t = ntokens[j];
             hc[j].ngroups = (ntokens[j] + kGroup - 1) / kGroup;
+            const Layout lj = make_layout(P.L, P.C, ntokens[j]);
+            hc[j].payload_bytes = (uint32_t)(total_bytes[j] - lj.off_payload);
+            hc[j].pad = 0;
         }
         cudaError_t e = cudaMemcpyAsync(ws, hc, sizeof(DecChunk) * (size_t)n_chunks, cudaMemcpyHostToDevice, stream);
         free(hc);
@@ -1040,6 +1290,8 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     }
     P.chunks = reinterpret_cast<const DecChunk*>(ws);
     P.tile_base = reinterpret_cast<unsigned long long*>(ws + off_tb);
+    P.status = status_out;
+    if (status_out) B2_CHECK_CUDA(cudaMemsetAsync(status_out, 0, sizeof(uint32_t) * (size_t)n_chunks, stream));
 
     dim3 gsum((unsigned)((tiles_max + 3) / 4), (unsigned)n_chunks);
     {
@@ -1056,15 +1308,21 @@ int b200kv_decode_chunks(const void* containers, const int64_t* offsets, const i
     const size_t smem = (size_t)(CT * kLp + kGroup + 32) * 4;
     dim3 grid((unsigned)tiles_max, (unsigned)n_chunks);
     ProfScope prof(kProfDecode, stream);
+#define B2_LAUNCH_DEC1(DT, PAGED, CODER)                                                                               \
+    do {                                                                                                               \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<DT, PAGED, CODER>,                                            \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        decode_kernel<DT, PAGED, CODER><<<grid, CT, smem, stream>>>(P);                                                \
+    } while (0)
 #define B2_LAUNCH_DEC(DT, PAGED)                                                                                       \
     do {                                                                                                               \
-        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<DT, PAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                           (int)smem));                                                                \
-        decode_kernel<DT, PAGED><<<grid, CT, smem, stream>>>(P);                                                       \
+        if (coder == CODER_RANS) B2_LAUNCH_DEC1(DT, PAGED, CODER_RANS);                                                \
+        else B2_LAUNCH_DEC1(DT, PAGED, CODER_AC);                                                                      \
     } while (0)
     if (P.out_dtype == B200KV_DT_BF16) { if (P.slot_map) B2_LAUNCH_DEC(0, true); else B2_LAUNCH_DEC(0, false); }
     else { if (P.slot_map) B2_LAUNCH_DEC(1, true); else B2_LAUNCH_DEC(1, false); }
 #undef B2_LAUNCH_DEC
+#undef B2_LAUNCH_DEC1
     B2_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -91,6 +91,7 @@ class CacheGenGPUEncoderOutput:
     max_tensors_value: torch.Tensor   # half [L, t, 1]
     num_heads: int
     head_size: int
+    coder: int = N.CODER_RANS         # entropy coder of the bytestreams = container version - 1 (not in the reference)
 
     def __getitem__(self, key: str):
         return getattr(self, key)
@@ -118,7 +119,7 @@ class CacheGenGPUEncoderOutput:
             gt = min(N.GROUP_TOKENS, t - g * N.GROUP_TOKENS)
             chunks.append(CacheGenGPUBytestream(torch.from_numpy(payload[pos:pos + nb].copy()), lengths[g], gt))
             pos += nb
-        return CacheGenGPUEncoderOutput(chunks, cdf, maxes[0], maxes[1], H, D)
+        return CacheGenGPUEncoderOutput(chunks, cdf, maxes[0], maxes[1], H, D, int(hd.version) - 1)
 
     def to_bytes(self) -> bytes:
         """Re-assemble the flat container from the logical fields (host side; used by tests / tools)."""
@@ -131,7 +132,7 @@ class CacheGenGPUEncoderOutput:
         total = lo.off_payload + len(payload)
         buf = bytearray(total)
         hd = N.Header.from_buffer(buf)
-        hd.magic, hd.version = N.MAGIC, 1
+        hd.magic, hd.version = N.MAGIC, int(self.coder) + 1
         hd.L, hd.H, hd.D, hd.ntokens, hd.ngroups = L, H, D, t, len(self.data_chunks)
         hd.max_dtype = N.DT_BF16 if self.max_tensors_key.dtype == torch.bfloat16 else N.DT_FP16
         hd.payload_bytes, hd.total_bytes, hd.status = len(payload), total, 0

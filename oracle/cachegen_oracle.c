@@ -317,6 +317,108 @@ void oracle_decode_group(const int16_t* cdf, const uint8_t* bytes, const int32_t
     free(start);
 }
 
+/* ------------------------------------------------------------------ a8/a10, container version 2: rANS
+ * The coder of B2KV container version 2 (lmcache_b200/csrc/ac_core.cuh, "rANS coder"): same per-stream CDF, same
+ * stream order (collect_bytes, cachegen_encoder.py:225-238), same lengths section and prefix-sum addressing
+ * (cachegen_decoder.py:52-66) as the arithmetic coder above; only the bytes of a stream differ.  Like the arithmetic
+ * coder's bitstream it is "parity unpinned" against the reference (torchac_cuda absent) -- it is this build's format,
+ * restated here independently of the product code (plain division / modulo, a byte stack) as the checker.
+ *   encoder: x = 2^16; for i = g-1..0: f = c[s+1]-c[s]; if (x >> 16) >= f: push16(x & 0xffff), x >>= 16;
+ *            x = ((x / f) << 16) + (x % f) + c[s]
+ *   stream : LE32(x), then the pushed halfwords in reverse push order (LE16 each)
+ *   decoder: x = LE32; per symbol: slot = x & 0xffff; s = max{s: c[s] <= slot}; x = f*(x>>16) + slot - c[s];
+ *            if x < 2^16: x = (x << 16) | next LE16
+ */
+static int64_t rans_encode_stream(const uint16_t* cdf, const int8_t* sym, int64_t sym_stride, int g,
+                                  uint8_t* out, int64_t cap) {
+    uint16_t stack[512];
+    int k = 0;
+    uint32_t x = 1u << 16;
+    for (int i = g - 1; i >= 0; --i) {
+        const int s = sym[i * sym_stride];
+        const uint32_t c_lo = cdf[s];
+        const uint32_t c_hi = (s == ORACLE_MAXSYM) ? 0x10000u : cdf[s + 1];
+        const uint32_t f = c_hi - c_lo;
+        if ((x >> 16) >= f) { if (k < 512) stack[k] = (uint16_t)(x & 0xffffu); k++; x >>= 16; }
+        x = ((x / f) << 16) + (x % f) + c_lo;
+    }
+    const int64_t n = 4 + 2 * (int64_t)k;
+    if (n <= cap && k <= 512) {
+        out[0] = (uint8_t)x; out[1] = (uint8_t)(x >> 8); out[2] = (uint8_t)(x >> 16); out[3] = (uint8_t)(x >> 24);
+        for (int j = 0; j < k; ++j) {
+            const uint16_t h = stack[k - 1 - j];
+            out[4 + 2 * j] = (uint8_t)h; out[5 + 2 * j] = (uint8_t)(h >> 8);
+        }
+    }
+    return n;
+}
+
+/* returns the final state (2^16 for an intact stream) */
+static uint32_t rans_decode_stream(const uint16_t* cdf, const uint8_t* in, int64_t n, int g, uint8_t* out,
+                                   int64_t out_stride) {
+    uint32_t x = 0;
+    for (int i = 0; i < 4; ++i) x |= (uint32_t)(i < n ? in[i] : 0) << (8 * i);
+    int64_t p = 4;
+    for (int i = 0; i < g; ++i) {
+        const uint32_t slot = x & 0xffffu;
+        int s = 0;
+        while (s < ORACLE_MAXSYM && (uint32_t)cdf[s + 1] <= slot && cdf[s + 1] != 0) s++;   /* cdf[32] wraps to 0 */
+        out[i * out_stride] = (uint8_t)s;
+        const uint32_t c_lo = cdf[s];
+        const uint32_t c_hi = (s == ORACLE_MAXSYM) ? 0x10000u : cdf[s + 1];
+        x = (c_hi - c_lo) * (x >> 16) + slot - c_lo;
+        if (x < (1u << 16)) {
+            const uint32_t h = (uint32_t)(p < n ? in[p] : 0) | ((uint32_t)(p + 1 < n ? in[p + 1] : 0) << 8);
+            x = (x << 16) | h;
+            p += 2;
+        }
+    }
+    return x;
+}
+
+int64_t oracle_encode_group_rans(const int16_t* cdf, const int8_t* sym, int NL, int t_total, int tok0, int g,
+                                 int C, uint8_t* out, int64_t cap, int32_t* lengths) {
+    const int64_t nstreams = (int64_t)NL * C;
+    const int64_t rowcap = 2 * (int64_t)g + 8;
+    uint8_t* stage = (uint8_t*)malloc((size_t)(nstreams * rowcap));
+    if (!stage) return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < nstreams; ++s) {
+        const int nl = (int)(s / C), c = (int)(s % C);
+        const int8_t* sp = sym + ((int64_t)nl * t_total + tok0) * C + c;
+        lengths[s] = (int32_t)rans_encode_stream((const uint16_t*)(cdf + s * ORACLE_LP), sp, C, g,
+                                                 stage + s * rowcap, rowcap);
+    }
+    int64_t total = 0;
+    for (int64_t s = 0; s < nstreams; ++s) total += lengths[s];
+    if (total > cap) { free(stage); return -1; }
+    int64_t off = 0;
+    for (int64_t s = 0; s < nstreams; ++s) {
+        memcpy(out + off, stage + s * rowcap, (size_t)lengths[s]);
+        off += lengths[s];
+    }
+    free(stage);
+    return total;
+}
+
+/* returns the number of streams whose final state is not 2^16 (0 for intact input) */
+int64_t oracle_decode_group_rans(const int16_t* cdf, const uint8_t* bytes, const int32_t* lengths, int NL,
+                                 int t_total, int tok0, int g, int C, uint8_t* out_sym) {
+    const int64_t nstreams = (int64_t)NL * C;
+    int64_t* start = (int64_t*)malloc(sizeof(int64_t) * (size_t)nstreams);
+    int64_t acc = 0, bad = 0;
+    for (int64_t s = 0; s < nstreams; ++s) { start[s] = acc; acc += lengths[s]; }
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int64_t s = 0; s < nstreams; ++s) {
+        const int nl = (int)(s / C), c = (int)(s % C);
+        const uint32_t xf = rans_decode_stream((const uint16_t*)(cdf + s * ORACLE_LP), bytes + start[s], lengths[s], g,
+                                               out_sym + ((int64_t)nl * t_total + tok0) * C + c, C);
+        bad += xf != (1u << 16);
+    }
+    free(start);
+    return bad;
+}
+
 /* ------------------------------------------------------------------ a11: dequantise + assemble
  * do_dequantize (cachegen_decoder.py:24-35): C_l = bins//2 - 1 ; x = ((q - C_l) / C_l) * max
  * with three separately rounded fp32 ops, then the blob is re-interleaved to [L,2,t,H,D] and
@@ -428,4 +530,4 @@ int oracle_set_threads(int n) {
     return omp_get_max_threads();
 }
 
-int oracle_version(void) { return 1; }
+int oracle_version(void) { return 2; }

@@ -51,6 +51,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_encode_group.restype = i64
         L.oracle_decode_group.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
         L.oracle_decode_group.restype = None
+        L.oracle_encode_group_rans.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i64, vp]
+        L.oracle_encode_group_rans.restype = i64
+        L.oracle_decode_group_rans.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        L.oracle_decode_group_rans.restype = i64
         L.oracle_dequantize.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, i64, i64, i64]
         L.oracle_dequantize.restype = None
         L.oracle_sha256_chain.argtypes = [vp, i64, i32, i32, vp]
@@ -118,7 +122,11 @@ def cdf(sym: np.ndarray) -> np.ndarray:
     return out
 
 
-def encode_group(cdf_i16: np.ndarray, sym: np.ndarray, tok0: int, g: int):
+CODER_AC = 0     # B2KV container version 1: torchac-lineage arithmetic coder
+CODER_RANS = 1   # B2KV container version 2: rANS, 32-bit state / 16-bit renormalisation, same CDF section
+
+
+def encode_group(cdf_i16: np.ndarray, sym: np.ndarray, tok0: int, g: int, coder: int = CODER_AC):
     """One <=256-token group -> (bytestream u8 [N], lengths i32 [NL,C]).
     cachegen_encoder.py:225-262,301-316."""
     sym = np.ascontiguousarray(sym, np.int8)
@@ -127,13 +135,14 @@ def encode_group(cdf_i16: np.ndarray, sym: np.ndarray, tok0: int, g: int):
     cap = NL * C * (2 * g + 8)
     out = np.empty(cap, np.uint8)
     lengths = np.empty((NL, C), np.int32)
-    n = lib().oracle_encode_group(_p(cdf_i16), _p(sym), NL, t, tok0, g, C, _p(out), cap, _p(lengths))
+    fn = lib().oracle_encode_group_rans if coder == CODER_RANS else lib().oracle_encode_group
+    n = fn(_p(cdf_i16), _p(sym), NL, t, tok0, g, C, _p(out), cap, _p(lengths))
     assert n >= 0
     return out[:n].copy(), lengths
 
 
 def decode_group(cdf_i16: np.ndarray, bytestream: np.ndarray, lengths: np.ndarray, out_sym: np.ndarray, tok0: int,
-                 g: int) -> None:
+                 g: int, coder: int = CODER_AC) -> None:
     """Inverse of encode_group, writes out_sym[:, tok0:tok0+g, :] (uint8 [NL,t,C]).
     cachegen_decoder.py:52-66,94-104."""
     NL, t, C = out_sym.shape
@@ -141,7 +150,11 @@ def decode_group(cdf_i16: np.ndarray, bytestream: np.ndarray, lengths: np.ndarra
     bs = np.ascontiguousarray(bytestream, np.uint8)
     ln = np.ascontiguousarray(lengths, np.int32)
     cdf_i16 = np.ascontiguousarray(cdf_i16, np.int16)
-    lib().oracle_decode_group(_p(cdf_i16), _p(bs), _p(ln), NL, t, tok0, g, C, _p(out_sym))
+    if coder == CODER_RANS:
+        bad = lib().oracle_decode_group_rans(_p(cdf_i16), _p(bs), _p(ln), NL, t, tok0, g, C, _p(out_sym))
+        assert bad == 0, f"{bad} rANS streams did not return to the initial state"
+    else:
+        lib().oracle_decode_group(_p(cdf_i16), _p(bs), _p(ln), NL, t, tok0, g, C, _p(out_sym))
 
 
 def dequantize(sym_u8: np.ndarray, maxes: np.ndarray, max_dtype: int, key_bins, value_bins, out_dtype: int) -> np.ndarray:
@@ -159,7 +172,7 @@ def dequantize(sym_u8: np.ndarray, maxes: np.ndarray, max_dtype: int, key_bins, 
     return out
 
 
-def encode_chunk(x_bits: np.ndarray, dtype: int, key_bins, value_bins):
+def encode_chunk(x_bits: np.ndarray, dtype: int, key_bins, value_bins, coder: int = CODER_AC):
     """Full encode_function (cachegen_encoder.py:266-325) on one chunk [L,2,t,C]:
     returns dict(cdf, maxes, groups=[(bytestream, lengths, ntokens)], sym)."""
     sym, maxes = quantize(x_bits, dtype, key_bins, value_bins)
@@ -168,9 +181,9 @@ def encode_chunk(x_bits: np.ndarray, dtype: int, key_bins, value_bins):
     groups = []
     for tok0 in range(0, t, GROUP):
         g = min(GROUP, t - tok0)
-        bs, ln = encode_group(c, sym, tok0, g)
+        bs, ln = encode_group(c, sym, tok0, g, coder)
         groups.append((bs, ln, g))
-    return dict(cdf=c, maxes=maxes, groups=groups, sym=sym)
+    return dict(cdf=c, maxes=maxes, groups=groups, sym=sym, coder=coder)
 
 
 def decode_chunk(enc: dict, max_dtype: int, key_bins, value_bins, out_dtype: int) -> np.ndarray:
@@ -181,7 +194,7 @@ def decode_chunk(enc: dict, max_dtype: int, key_bins, value_bins, out_dtype: int
     sym = np.zeros((NL, t, C), np.uint8)
     tok0 = 0
     for bs, ln, g in enc["groups"]:
-        decode_group(c, bs, ln, sym, tok0, g)
+        decode_group(c, bs, ln, sym, tok0, g, enc.get("coder", CODER_AC))
         tok0 += g
     return dequantize(sym, enc["maxes"], max_dtype, key_bins, value_bins, out_dtype)
 

@@ -98,6 +98,53 @@ void sim_decode_stream2(const uint16_t* cdf, const uint8_t* in, int64_t n, int g
         out[i * out_stride] = (uint8_t)((nsteps == 4 ? dec_symbol2<4>(st, src, e, i == g - 1) : dec_symbol2<5>(st, src, e, i == g - 1)) >> 2);   // returns 4 * symbol
 }
 
+
+// ---- rANS (container version 2): the product's rans_enc_symbol / rans_dec_symbol
+int64_t sim_rans_encode_stream(const uint16_t* cdf, const int8_t* sym, int64_t sym_stride, int g, uint8_t* out, int64_t cap) {
+    std::vector<uint16_t> stack;
+    uint32_t x = kRansLow;
+    for (int i = g - 1; i >= 0; --i) {
+        int s = sym[i * sym_stride];
+        uint32_t c_lo = cdf[s];
+        uint32_t c_hi = (s == kMaxSym) ? 0x10000u : cdf[s + 1];
+        rans_enc_symbol(x, c_lo, c_hi - c_lo, [&](uint32_t h) { stack.push_back((uint16_t)h); });
+    }
+    int64_t n = 4 + 2 * (int64_t)stack.size();
+    if (n <= cap) {
+        for (int i = 0; i < 4; ++i) out[i] = (uint8_t)(x >> (8 * i));
+        for (size_t j = 0; j < stack.size(); ++j) {
+            uint16_t h = stack[stack.size() - 1 - j];
+            out[4 + 2 * j] = (uint8_t)h; out[5 + 2 * j] = (uint8_t)(h >> 8);
+        }
+    }
+    return n;
+}
+
+namespace {
+struct LeWordSrc {   // aligned little-endian word reader; the stream may start at the upper halfword of its first word
+    int64_t pos; const uint8_t* buf; int64_t n;
+    uint32_t next_le() {
+        uint32_t w = 0;
+        for (int i = 0; i < 4; ++i) { int64_t p = pos + i; w |= (uint32_t)((p >= 0 && p < n) ? buf[p] : 0xA5u) << (8 * i); }  // garbage outside: must not matter
+        pos += 4;
+        return w;
+    }
+};
+}
+
+// odd = 1: two foreign bytes precede the stream inside its first aligned word.  Returns the final state (2^16 when intact).
+uint32_t sim_rans_decode_stream(const uint16_t* cdf, const uint8_t* in, int64_t n, int g, uint8_t* out, int64_t out_stride, int odd, int nsteps) {
+    LeWordSrc src{-(int64_t)(2 * odd), in, n};
+    RansDec st; rans_dec_init(st, src, (uint32_t)odd);
+    uint32_t pk[32];
+    for (uint32_t i = 0; i < 32u; ++i) pk[i] = rans_table_entry(cdf[i], i == 31u ? 0x10000u : cdf[i + 1]);
+    for (int i = 0; i < g; ++i)
+        out[i * out_stride] = (uint8_t)(nsteps == 4 ? rans_dec_symbol<4>(st, src, pk) : rans_dec_symbol<5>(st, src, pk));
+    return st.x;
+}
+
+uint32_t sim_rans_divmod(uint32_t x, uint32_t f, uint32_t* rem) { return rans_divmod(x, f, rem); }
+
 void sim_cdf(const uint32_t* counts, int t, uint16_t* cdf) {
     CdfAccum a; a.init(t);
     for (uint32_t i = 0; i < (uint32_t)kLp; ++i) cdf[i] = a.next(i, i < 33 ? counts[i] : 0);

@@ -22,7 +22,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in b200kv.h but not exported"
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
-    assert L.b200kv_version() == 2
+    assert L.b200kv_version() == 3
 
 
 def test_layout_arithmetic():

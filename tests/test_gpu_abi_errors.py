@@ -27,22 +27,25 @@ def test_encode_argument_validation():
     bins = N.float_array([32.0] * L)
     lo = N.container_layout(L, H, D, t)
     out = torch.empty(lo.max_total_bytes, dtype=torch.uint8, device="cuda")
-    ws = torch.empty(lib.b200kv_encode_workspace_bytes(L, H, D, t, 1), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(lib.b200kv_encode_workspace_bytes(L, H, D, t, 1, N.CODER_RANS), dtype=torch.uint8, device="cuda")
     sizes = torch.zeros(1, dtype=torch.int64, device="cuda")
     sp = torch.cuda.current_stream().cuda_stream
 
     def call(**kw):
-        a = dict(kv=ctypes.byref(d), tok=0, n=1, ct=t, last=t, kb=bins, vb=bins, out=out.data_ptr(), stride=lo.max_total_bytes,
+        a = dict(kv=ctypes.byref(d), tok=0, n=1, ct=t, last=t, kb=bins, vb=bins, coder=N.CODER_RANS, out=out.data_ptr(),
+                 stride=lo.max_total_bytes,
                  sizes=sizes.data_ptr(), ws=ws.data_ptr(), wsb=ws.numel())
         a.update(kw)
-        return lib.b200kv_encode_chunks(a["kv"], a["tok"], a["n"], a["ct"], a["last"], a["kb"], a["vb"], a["out"], a["stride"],
-                                        a["sizes"], a["ws"], a["wsb"], sp)
+        return lib.b200kv_encode_chunks(a["kv"], a["tok"], a["n"], a["ct"], a["last"], a["kb"], a["vb"], a["coder"], a["out"],
+                                        a["stride"], a["sizes"], a["ws"], a["wsb"], sp)
 
-    assert call() == 0
-    torch.cuda.synchronize()
-    assert int(sizes[0]) > lo.fixed_bytes
+    for coder in (N.CODER_AC, N.CODER_RANS):
+        assert call(coder=coder) == 0
+        torch.cuda.synchronize()
+        assert int(sizes[0]) > lo.fixed_bytes
+        assert N.Header.from_buffer_copy(out[:64].cpu().numpy().tobytes()).version == coder + 1
     for bad in (dict(n=0), dict(ct=0), dict(last=t + 1), dict(out=None), dict(out=out.data_ptr() + 1), dict(wsb=16),
-                dict(kb=None), dict(tok=-1), dict(stride=64)):
+                dict(kb=None), dict(tok=-1), dict(stride=64), dict(coder=2), dict(coder=-1)):
         rc = call(**bad)
         assert rc < 0 and len(N.last_error()) > 0, bad
     bad_desc = _desc(kv, L, H, D, dtype=7)
@@ -51,7 +54,8 @@ def test_encode_argument_validation():
     assert call(kb=bad_bins) < 0
 
 
-def test_slot_too_small_sets_status_not_corruption():
+@pytest.mark.parametrize("coder", [0, 1])
+def test_slot_too_small_sets_status_not_corruption(coder):
     """A payload that does not fit its slot must not be written past it; the header carries a nonzero status."""
     from lmcache_b200 import _native as N
     from lmcache_b200.codec import parse_header
@@ -64,9 +68,9 @@ def test_slot_too_small_sets_status_not_corruption():
     stride = lo.fixed_bytes + 256                                           # far too small for the payload
     guard = 4096
     out = torch.full((stride + guard,), 0xAB, dtype=torch.uint8, device="cuda")
-    ws = torch.empty(lib.b200kv_encode_workspace_bytes(L, H, D, t, 1), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(lib.b200kv_encode_workspace_bytes(L, H, D, t, 1, coder), dtype=torch.uint8, device="cuda")
     sizes = torch.zeros(1, dtype=torch.int64, device="cuda")
-    rc = lib.b200kv_encode_chunks(ctypes.byref(d), 0, 1, t, t, bins, bins, out.data_ptr(), stride, sizes.data_ptr(),
+    rc = lib.b200kv_encode_chunks(ctypes.byref(d), 0, 1, t, t, bins, bins, coder, out.data_ptr(), stride, sizes.data_ptr(),
                                   ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
@@ -87,9 +91,13 @@ def test_decode_and_misc_validation():
     buf = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
     ws = torch.empty(max(1, lib.b200kv_decode_workspace_bytes(L, H, D, t, 1)), dtype=torch.uint8, device="cuda")
     sp = torch.cuda.current_stream().cuda_stream
-    ok = (buf.data_ptr(), N.i64_array([0]), N.i32_array([t]), N.i64_array([0]), 1, 0, ctypes.byref(d), bins, bins, ws.data_ptr(),
-          ws.numel(), sp)
-    for i, bad in [(1, N.i64_array([8])), (2, N.i32_array([0])), (4, 0), (5, 9), (10, 8), (0, None)]:
+    total = N.container_layout(L, H, D, t).fixed_bytes + 4 * 2 * L * H * D
+    ok = (buf.data_ptr(), buf.numel(), N.i64_array([0]), N.i64_array([total]), N.i32_array([t]), N.i64_array([0]), 1, 0,
+          N.CODER_RANS, ctypes.byref(d), bins, bins, None, ws.data_ptr(), ws.numel(), sp)
+    # misaligned offset, zero tokens, zero chunks, bad max_dtype, bad coder, tiny workspace, NULL buffer, a container
+    # shorter than its fixed sections, a buffer without the read slack
+    for i, bad in [(2, N.i64_array([8])), (4, N.i32_array([0])), (6, 0), (7, 9), (8, 5), (14, 8), (0, None),
+                   (3, N.i64_array([100])), (1, total + 16)]:
         a = list(ok)
         a[i] = bad
         assert lib.b200kv_decode_chunks(*a) < 0 and N.last_error(), i
@@ -99,4 +107,5 @@ def test_decode_and_misc_validation():
     assert lib.b200kv_pinned_alloc(None, 16) < 0
     assert lib.b200kv_copy_async(None, buf.data_ptr(), 16, sp) < 0
     assert N.container_layout(1, 1, 1, 1).off_cdf == 64
-    assert lib.b200kv_encode_workspace_bytes(0, 1, 1, 1, 1) < 0
+    assert lib.b200kv_encode_workspace_bytes(0, 1, 1, 1, 1, 0) < 0
+    assert lib.b200kv_encode_workspace_bytes(1, 1, 1, 1, 1, 7) < 0
