@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=256)
     ap.add_argument("--heads", type=int, default=32, help="KV heads (32 = BASELINE configs[1]; 8 = GQA shapes, side measurement)")
     ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks in the bounded CPU sample")
+    ap.add_argument("--data", default="kv8d", choices=list(DATA_KINDS), help="synthetic KV distribution (kv8d = SURVEY 8d, the headline)")
     ap.add_argument("--coder", default="rans", choices=["rans", "ac"], help="payload coder: rans = container v2 (default), ac = v1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -50,19 +51,38 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------ synthetic data
-def synth_kv_torch(tokens, device, seed):
-    """SURVEY.md 8d distribution: N(0,1) * sigma[l,kv,c], sigma ~ LogNormal(0,0.5) clipped [0.1,8], 1% outlier
-    channels x10, cast to bf16.  Generated with torch on `device` (seeded)."""
+DATA_KINDS = ("kv8d", "kv8d_nooutlier", "normal", "uniform", "uniform_signed")
+
+
+def synth_kv_torch(tokens, device, seed, kind="kv8d"):
+    """Synthetic KV, generated with torch on `device` (seeded), cast to bf16.
+      kv8d            SURVEY.md 8d: N(0,1) * sigma[l,kv,c], sigma ~ LogNormal(0,0.5) clipped [0.1,8], 1% outlier channels
+                      x10 (they pin every token's absmax, so almost every symbol is the centre bin: ~0.5 bits/symbol)
+      kv8d_nooutlier  the same without the outlier channels
+      normal          N(0,1) in every channel (~3 bits/symbol)
+      uniform         torch.rand, the reference's own test data (tests/test_serde.py:10-24): U[0,1), upper bins only
+      uniform_signed  U(-1,1): every bin equally likely, the coder's worst case (~4.1 bits/symbol)"""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     sigma = torch.exp(0.5 * torch.randn((L, 2, 1, C), device=device, generator=g)).clamp_(0.1, 8.0)
     outl = torch.rand((L, 2, 1, C), device=device, generator=g) < 0.01
-    sigma = torch.where(outl, sigma * 10.0, sigma)
+    if kind == "kv8d":
+        sigma = torch.where(outl, sigma * 10.0, sigma)
     kv = torch.empty((L, 2, tokens, C), dtype=torch.bfloat16, device=device)
     step = 512
     for t0 in range(0, tokens, step):
         n = min(step, tokens - t0)
-        kv[:, :, t0:t0 + n] = (torch.randn((L, 2, n, C), device=device, generator=g) * sigma).to(torch.bfloat16)
+        if kind in ("kv8d", "kv8d_nooutlier"):
+            blk = torch.randn((L, 2, n, C), device=device, generator=g) * sigma
+        elif kind == "normal":
+            blk = torch.randn((L, 2, n, C), device=device, generator=g)
+        elif kind == "uniform":
+            blk = torch.rand((L, 2, n, C), device=device, generator=g)
+        elif kind == "uniform_signed":
+            blk = torch.rand((L, 2, n, C), device=device, generator=g) * 2.0 - 1.0
+        else:
+            raise ValueError(kind)
+        kv[:, :, t0:t0 + n] = blk.to(torch.bfloat16)
     return kv.reshape(L, 2, tokens, H, D)
 
 
@@ -266,7 +286,7 @@ def main():
     raw_bytes = L * 2 * T * C * 2
     lib = N.lib()
     codec = CacheGenCodec(MODEL, coder=args.coder)
-    kv = synth_kv_torch(T, dev, 1234 + 2 + rank)
+    kv = synth_kv_torch(T, dev, 1234 + 2 + rank, args.data)
     view = KvView.from_blob(kv, "vllm")
     out = torch.empty_like(kv)
     out_view = KvView.from_blob(out, "vllm")
@@ -379,6 +399,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"CacheGen encode+decode, {L}L/{H}H/{D}D {T}-token bf16 KV block per GPU, "
                                    f"chunk_size {cs} -> {n_chunks} chunks" + (" (BASELINE configs[1])" if (H, T) == (32, 8192) else " (BASELINE configs[2] shape: 65536-token offload + reload; e2e is that config's metric)" if (H, T) == (32, 65536) else " (side measurement, not a BASELINE shape)"),
+                       "data_kind": args.data, "coder": args.coder,
                        "raw_bytes_per_gpu": raw_bytes, "container_bytes": container_bytes,
                        "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
                        "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity},

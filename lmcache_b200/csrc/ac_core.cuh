@@ -218,6 +218,25 @@ B2_HD uint32_t quant_symbol(float x, float factor, float maxq) {
     return q <= 30u ? q : 0u;
 }
 
+// The same symbol without the range check, for factors made by quant_factor_safe.  Why that is enough: rows whose
+// maximum is finite and large enough give |x * f| <= MAX (1 + 2^-22), hence symbols 0..2 MAX; a NaN row maximum gives
+// f = NaN and an infinite one f = 0, both of which already yield in-range symbols (F2I(NaN) = 0; finite x -> MAX,
+// x = +-inf -> inf * 0 = NaN -> 0); the only factor that can leave the range is f = +inf (row maximum zero or so
+// small that MAX / max overflows), where the checked quantiser returns 0 for every element (x != 0 -> +-inf ->
+// saturated -> 0; x == 0 -> NaN -> 0) -- exactly what f = NaN produces.  So replacing an infinite factor by NaN keeps
+// every symbol bit-identical and makes the check redundant.
+B2_HD float quant_factor_safe(float maxq, float row_max) {
+    const float f = fdiv(maxq, row_max);
+    return (f2u(f) & 0x7fffffffu) == 0x7f800000u ? u2f(0x7fc00000u) : f;
+}
+B2_HD uint32_t quant_symbol_nc(float x, float factor, float maxq) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__float2int_rn(fadd(fmul(x, factor), maxq));
+#else
+    return quant_symbol(x, factor, maxq);
+#endif
+}
+
 // LUT entry: (sym - C) / C ; value = lut * float(max_half)
 B2_HD float dequant_lut(uint32_t sym, float cq) { return fdiv(fadd((float)sym, -cq), cq); }
 B2_HD float dequant_value(float lut, float row_max) { return fmul(lut, row_max); }

@@ -217,11 +217,30 @@ __device__ __forceinline__ void for_each_symbol_rev(const uint16_t* cbase, const
     }
 }
 
-// rANS encoder step as the kernels run it: the state shrinks by one halfword when it must (stored at a descending
-// halfword pointer into the stream's temp row -- the row then holds the halfwords in decode order), then
-// x = (x / f) << 16 | (x mod f) + start with the reciprocal division of ac_core.cuh.
-__device__ __forceinline__ void rans_put(uint32_t& x, uint16_t*& wp, uint32_t start, uint32_t freq) {
-    rans_enc_symbol(x, start, freq, [&](uint32_t h) { *--wp = (uint16_t)h; });
+// rANS encoder step as the kernels run it (same arithmetic as rans_enc_symbol in ac_core.cuh, laid out for issue slots):
+//   * the state shrinks by one halfword when it must; halfword number k (counted downwards: nk = -k) lands at
+//     row_end + 2 * nk - 2, so the row's tail holds the halfwords in decode order.  The address is one unpredicated
+//     IMAD.WIDE, only the 16-bit store and the count are predicated;
+//   * q = x / f by one reciprocal biased low (estimate is q or q - 1) and one fix-up;
+//   * x' = (q << 16) + (x - q f) + start  ==  x + start + q * (65536 - f): one IMAD.
+__device__ __forceinline__ void rans_put(uint32_t& x, int32_t& nk, const uint16_t* row_end, uint32_t start, uint32_t freq) {
+    const uint32_t xh = x >> 16;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 ad;\n\t"
+        "setp.ge.u32 p, %2, %3;\n\t"
+        "mad.wide.s32 ad, %1, 2, %4;\n\t"
+        "@p st.global.u16 [ad+-2], %0;\n\t"
+        "@p add.s32 %1, %1, -1;\n\t"
+        "selp.b32 %0, %2, %0, p;\n\t"
+        "}"
+        : "+r"(x), "+r"(nk) : "r"(xh), "r"(freq), "l"(row_end) : "memory");
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rn(freq)));
+    uint32_t q = __float2uint_rz(__uint2float_rz(x) * (rc * 0.99999952316284179688f));
+    const uint32_t nf = 0u - freq;
+    const uint32_t r = q * nf + x;                       // x - q f
+    q += r >= freq ? 1u : 0u;
+    x = q * (nf + 65536u) + (x + start);
 }
 
 // ------------------------------------------------------------------------------------------ encode
@@ -260,7 +279,9 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + id.tok0;
     const float maxq = P.pt.maxq[nl];
     const int64_t s1 = P.sT;
-    for (int i = tid; i < gt; i += CT) fac[i] = quant_factor(maxq, half_to_float(maxes[i], DT));
+    // FUSED: "safe" factors (an infinite factor becomes NaN: same symbols, and pass 1 can skip the range check)
+    for (int i = tid; i < gt; i += CT)
+        fac[i] = FUSED ? quant_factor_safe(maxq, half_to_float(maxes[i], DT)) : quant_factor(maxq, half_to_float(maxes[i], DT));
     if (FUSED) for (int i = gt + tid; i < kGroup + 8; i += CT) fac[i] = 0.0f;      // padded slots of the last batch
 
     const int h = active ? c / P.D : 0;
@@ -326,7 +347,7 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
                 // may alias each other, so interleaving them with the arithmetic would serialise the whole batch
                 uint32_t q[BT];
 #pragma unroll
-                for (int k = 0; k < BT; ++k) q[k] = quant_symbol(half_to_float(x[k], DT), fac[tk + k], maxq);
+                for (int k = 0; k < BT; ++k) q[k] = quant_symbol_nc(half_to_float(x[k], DT), fac[tk + k], maxq);
 #pragma unroll
                 for (int half = 0; half < NB; ++half) {
                     if (tk + half * SPW < gt) {
@@ -379,28 +400,28 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
             // rANS: last token first; halfwords land at a descending pointer, so the row's tail is the stream in
             // decode order.  Row capacity (96 halfwords) cannot be exceeded: no clamp, no flag.
             uint32_t x = kRansLow;
-            uint16_t* const wend = reinterpret_cast<uint16_t*>(trow) + 2 * TEMPW_FUSED_RANS;
-            uint16_t* wp = wend;
+            const uint16_t* const wend = reinterpret_cast<const uint16_t*>(trow) + 2 * TEMPW_FUSED_RANS;
+            int32_t nk = 0;                                                // minus the number of halfwords pushed
+            const char* const cb = reinterpret_cast<const char*>(crow);
+            // symbol s -> byte offset 2 s of its CDF entry: ((word >> 5 k) & 31) * 2 as one shift + one mask
+            auto code = [&](uint32_t word, int k) {
+                const uint32_t o = (k == 0 ? word << 1 : word >> (5 * k - 1)) & 62u;     // s <= 30: entry s + 1 is real
+                const uint32_t c_lo = *reinterpret_cast<const uint16_t*>(cb + o);
+                const uint32_t c_hi = *reinterpret_cast<const uint16_t*>(cb + o + 2);
+                rans_put(x, nk, wend, c_lo, c_hi - c_lo);
+            };
             int w = (gt - 1) / SPW;
             {
                 const uint32_t word = myrow[w];
-                for (int k = gt - 1 - w * SPW; k >= 0; --k) {
-                    const uint32_t sidx = (word >> (5 * k)) & 31u;
-                    const uint32_t c_lo = crow[sidx];
-                    rans_put(x, wp, c_lo, (uint32_t)crow[sidx + 1u] - c_lo);
-                }
+                for (int k = gt - 1 - w * SPW; k >= 0; --k) code(word, k);
             }
             for (--w; w >= 0; --w) {
                 const uint32_t word = myrow[w];
 #pragma unroll
-                for (int k = SPW - 1; k >= 0; --k) {
-                    const uint32_t sidx = (word >> (5 * k)) & 31u;       // <= 30: crow[sidx + 1] is a real entry
-                    const uint32_t c_lo = crow[sidx];
-                    rans_put(x, wp, c_lo, (uint32_t)crow[sidx + 1u] - c_lo);
-                }
+                for (int k = SPW - 1; k >= 0; --k) code(word, k);
             }
             P.rstate[(int64_t)blockIdx.x * CT + tid] = x;
-            len = 4u + 2u * (uint32_t)(wend - wp);
+            len = 4u - 2u * (uint32_t)nk;
         } else if (active) {
             EncState2 st;
             st.init();
@@ -445,14 +466,14 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
             if (CODER == CODER_RANS) {
                 // at most one halfword per symbol: the 264-halfword row cannot overflow
                 uint32_t x = kRansLow;
-                uint16_t* const wend = reinterpret_cast<uint16_t*>(trow) + 2 * TEMPW_SPLIT;
-                uint16_t* wp = wend;
+                const uint16_t* const wend = reinterpret_cast<const uint16_t*>(trow) + 2 * TEMPW_SPLIT;
+                int32_t nk = 0;
                 for_each_symbol_rev<DT, PAGED, 4>(cbase, P.slot_map, tokabs, s1, gt, fac, maxq, [&](uint32_t q) {
                     const uint32_t pr = prow[q];
-                    rans_put(x, wp, pr & 0xffffu, pr >> 16);
+                    rans_put(x, nk, wend, pr & 0xffffu, pr >> 16);
                 });
                 P.rstate[(int64_t)blockIdx.x * CT + tid] = x;
-                len = 4u + 2u * (uint32_t)(wend - wp);
+                len = 4u - 2u * (uint32_t)nk;
             } else {
                 EncState2 st;
                 st.init();
@@ -835,12 +856,22 @@ __device__ __forceinline__ void store_half(uint16_t* p, float v) {
 // value = lut * row_max (one rounded multiply, cachegen_decoder.py:31-35), converted RNE and stored as 16 bits
 // (F2FP + STG.U16, no register merge in between)
 template <int OUT_DT>
-__device__ __forceinline__ void store_dequant(uint16_t* p, float lutv, float row_max) {
+__device__ __forceinline__ void store_dequant(uint16_t* base, uint32_t off, float lutv, float row_max, uint32_t two) {
     const float v = __fmul_rn(lutv, row_max);
+    // address = base + 2 * off as ONE IMAD.WIDE (`two` = 2, opaque to ptxas, keeps it off the ALU pipe); the converted value stays in the low half of a 32-bit register
+    // (F2FP.PACK_AB with a zero upper half) and STG.U16 stores that half: no 16-bit register shuffling
     if constexpr (OUT_DT)
-        asm volatile("{\n\t.reg .b16 h;\n\tcvt.rn.f16.f32 h, %1;\n\tst.global.b16 [%0], h;\n\t}" ::"l"(p), "f"(v) : "memory");
+        asm volatile("{\n\t.reg .b64 ad;\n\t.reg .b32 r;\n\t.reg .b16 lo, hi;\n\t"
+                     "mad.wide.u32 ad, %1, %3, %0;\n\t"
+                     "cvt.rn.f16x2.f32 r, 0f00000000, %2;\n\t"
+                     "mov.b32 {lo, hi}, r;\n\t"
+                     "st.global.b16 [ad], lo;\n\t}" ::"l"(base), "r"(off), "f"(v), "r"(two) : "memory");
     else
-        asm volatile("{\n\t.reg .b16 h;\n\tcvt.rn.bf16.f32 h, %1;\n\tst.global.b16 [%0], h;\n\t}" ::"l"(p), "f"(v) : "memory");
+        asm volatile("{\n\t.reg .b64 ad;\n\t.reg .b32 r;\n\t.reg .b16 lo, hi;\n\t"
+                     "mad.wide.u32 ad, %1, %3, %0;\n\t"
+                     "cvt.rn.bf16x2.f32 r, 0f00000000, %2;\n\t"
+                     "mov.b32 {lo, hi}, r;\n\t"
+                     "st.global.b16 [ad], lo;\n\t}" ::"l"(base), "r"(off), "f"(v), "r"(two) : "memory");
 }
 
 // per-thread decode loop: one stream, gt symbols, straight to the destination layout.
@@ -878,43 +909,75 @@ __device__ __forceinline__ void decode_stream(const uint8_t* cont, uint32_t my_o
 template <int OUT_DT, int NSTEPS, bool PAGED>
 __device__ __forceinline__ uint32_t rans_decode_stream(const uint8_t* cont, uint32_t my_off, const uint32_t* pk,
                                                        const float* lut, const float* mx, uint16_t* dst, uint32_t sT, int gt,
-                                                       const int64_t* slots) {
-    LeWordSrc src{reinterpret_cast<const uint32_t*>(cont) + (my_off >> 2)};
+                                                       const int64_t* slots, uint32_t one) {
+    // stream words are addressed as container base + 32-bit word index: the address of the next word is one IMAD.WIDE
+    // (FMA pipe, not predicated), only the load and the index increment are predicated
+    const uint32_t* const wbase = reinterpret_cast<const uint32_t*>(cont);
+    uint32_t idx = my_off >> 2;
+    struct Src {
+        const uint32_t* b; uint32_t& i;
+        __device__ __forceinline__ uint32_t next_le() { return __ldg(b + i++); }
+    } src{wbase, idx};
     RansDec st;
     rans_dec_init(st, src, (my_off >> 1) & 1u);
     constexpr uint32_t H = 1u << (NSTEPS - 1);
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(pk);
+    const uint32_t a0h = a0 + 4u * H;
     const uint32_t r_mid = pk[H], r_lo = pk[H / 2], r_hi = pk[H + H / 2];
     const uint32_t lut_rel = (uint32_t)__cvta_generic_to_shared(lut) - a0;     // lut[s] lives at (a0 + 4 s) + lut_rel
-    uint16_t* d = dst;
+    uint32_t off = 0u;                                                         // element offset of the current token row
+    // The integer ALU pipe (ISETP / SEL / PRMT / LOP3, one warp instruction per 2 cycles) is what bounds this loop, the
+    // FMA pipe idles: additions and shifts are therefore written as IMADs whose multiplier ptxas cannot fold (`one` is
+    // 1 but comes from a kernel parameter), which pins them to the FMA pipe.
+    const uint32_t c64k = one << 16, mone = 0u - one, two = one + one;
     auto step = [&](float row_max, int i) {
-        const uint32_t key = st.x * 65536u + 0xffffu;                            // (x << 16) | 0xffff, one IMAD
+        uint32_t key, xh;
+        asm("mad.lo.u32 %0, %1, %2, 65535;" : "=r"(key) : "r"(st.x), "r"(c64k));      // (x << 16) | 0xffff
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(xh) : "r"(st.x), "r"(c64k));             // x >> 16
         const bool p1 = r_mid <= key;
-        uint32_t a = p1 ? a0 + 4u * H : a0;
+        uint32_t a = p1 ? a0h : a0;
         const uint32_t m = p1 ? r_hi : r_lo;
-        a = m <= key ? a + 2u * H : a;
-        dec_search_steps<H / 4>(a, key);
+        asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+            : "+r"(a) : "r"(m), "r"(key), "r"(one), "n"(2 * H));
+#pragma unroll
+        for (uint32_t st4 = H; st4 >= 4u; st4 >>= 1) {                           // byte steps H, H/2, .., 4 = entries H/4 .. 1
+            uint32_t ev;
+            if (st4 == 16u) asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(ev) : "r"(a));
+            else if (st4 == 8u) asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(ev) : "r"(a));
+            else asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(ev) : "r"(a));
+            asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+                : "+r"(a) : "r"(ev), "r"(key), "r"(one), "r"(st4));
+        }
         uint32_t e;
         float lv;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lv) : "r"(a + lut_rel));
-        st.x = (e & 0xffffu) * (st.x >> 16) + ((key - e) >> 16);
+        // x = freq * (x >> 16) + slot - start
+        uint32_t dl;
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(dl) : "r"(key - e), "r"(c64k));
+        st.x = (e & 0xffffu) * xh + dl;
         // renormalisation, branch-free (a warp takes this path on most symbols, so a branch would run for all lanes
         // anyway): p = x < 2^16 -> pull the next halfword out of the window; q = p and the window's upper half was
         // taken -> the window moves on (cur = nxt, nxt = next aligned word)
+        const uint32_t* const wad = wbase + idx;
         asm volatile(
             "{\n\t.reg .pred p, q;\n\t"
             "setp.lt.u32 p, %0, 65536;\n\t"
-            "@p prmt.b32 %0, %0, %1, %3;\n\t"
             "setp.eq.and.u32 q, %3, 0x1076, p;\n\t"
-            "@p xor.b32 %3, %3, 0x22;\n\t"
+            "@p prmt.b32 %0, %0, %1, %3;\n\t"
+            "@p mad.lo.u32 %3, %3, %7, 0x20ca;\n\t"     // 0x1054 <-> 0x1076: sel = 0x20ca - sel
             "@q mov.b32 %1, %2;\n\t"
-            "@q ld.global.nc.u32 %2, [%4];\n\t"
-            "@q add.u64 %4, %4, 4;\n\t"
+            "@q ld.global.nc.u32 %2, [%5];\n\t"
+            "@q mad.lo.u32 %4, %6, %6, %4;\n\t"         // idx += 1
             "}"
-            : "+r"(st.x), "+r"(st.cur), "+r"(st.nxt), "+r"(st.sel), "+l"(src.p));
-        store_dequant<OUT_DT>(PAGED ? dst + __ldg(slots + (PAGED ? i : 0)) * (int64_t)sT : d, lv, row_max);
-        if constexpr (!PAGED) d += sT;
+            : "+r"(st.x), "+r"(st.cur), "+r"(st.nxt), "+r"(st.sel), "+r"(idx)
+            : "l"(wad), "r"(one), "r"(mone));
+        if constexpr (PAGED) {
+            store_dequant<OUT_DT>(dst + __ldg(slots + i) * (int64_t)sT, 0u, lv, row_max, two);
+        } else {
+            store_dequant<OUT_DT>(dst, off, lv, row_max, two);
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(off) : "r"(one), "r"(sT));
+        }
     };
     int i = 0;
     for (; i + 4 <= gt; i += 4) {
@@ -993,8 +1056,9 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     uint32_t bad = beyond ? 2u : 0u;
     if constexpr (CODER == CODER_RANS) {
         uint32_t xf;
-        if (cq <= 7.0f) xf = rans_decode_stream<OUT_DT, 4, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);
-        else xf = rans_decode_stream<OUT_DT, 5, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);
+        const uint32_t one = min((uint32_t)P.n_chunks, 1u);      // 1, but opaque to the compiler (see rans_decode_stream)
+        if (cq <= 7.0f) xf = rans_decode_stream<OUT_DT, 4, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots, one);
+        else xf = rans_decode_stream<OUT_DT, 5, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots, one);
         bad |= xf != kRansLow ? 1u : 0u;
     } else {
         if (cq <= 7.0f) decode_stream<OUT_DT, 4, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);   // <= 16 bins: symbols 0..14

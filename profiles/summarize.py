@@ -3,6 +3,9 @@
 
     python profiles/summarize.py gpurun_out/prof_encode_r1c.ncu-rep profiles/r1c_encode_kernel.txt [symbols_per_launch]
 
+symbols_per_launch = KV elements one launch codes (2^31 for the 8192-token block): the summary then states
+warp-instructions per warp-symbol step = instructions each lane spends per symbol.
+
 Reads the report with `ncu -i ... --page raw --csv` / `--page source --csv` (no GPU needed)."""
 import csv
 import io
@@ -64,7 +67,7 @@ def main():
             ops[op.split(".")[0]] += int(r[ix["Instructions Executed"]] or 0)
         lines += ["", f"SASS: {len(rows)} instructions, {tot} warp-instructions executed"]
         if nsym:
-            lines.append(f"warp-instructions per 32-symbol step: {tot / (nsym / 32):.1f}")
+            lines.append(f"warp-instructions per warp-symbol step (= per 32 symbols, one per lane): {tot / (nsym / 32.0):.1f}")
         lines.append("opcode mix: " + ", ".join(f"{o} {100 * n / tot:.1f}%" for o, n in ops.most_common(14)))
         mn = {o for o in ops}
         lines.append("tensor / TMA mnemonics present: " + (", ".join(sorted(m for m in mn if m.startswith(("UTC", "UTMA", "UBLKCP", "HMMA", "LDTM")))) or "none (integer/byte path, by design)"))

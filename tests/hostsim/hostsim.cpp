@@ -156,6 +156,14 @@ void sim_quant_row(const uint16_t* x, int dtype, int C, uint16_t max_bits, float
     for (int c = 0; c < C; ++c) sym[c] = (uint8_t)quant_symbol(half_to_float(x[c], dtype), f, maxq);
 }
 
+// the fused encode kernel's pass 1: "safe" factor + unchecked symbol (host build of quant_symbol_nc keeps the check, so
+// this pins quant_factor_safe: an infinite factor must become NaN and nothing else may change)
+void sim_quant_row_safe(const uint16_t* x, int dtype, int C, uint16_t max_bits, float maxq, uint8_t* sym, uint32_t* factor_bits) {
+    float f = quant_factor_safe(maxq, half_to_float(max_bits, dtype));
+    *factor_bits = f2u(f);
+    for (int c = 0; c < C; ++c) sym[c] = (uint8_t)quant_symbol_nc(half_to_float(x[c], dtype), f, maxq);
+}
+
 void sim_dequant_row(const uint8_t* sym, int C, uint16_t max_bits, int max_dtype, float cq, int out_dtype, uint16_t* out) {
     float m = half_to_float(max_bits, max_dtype);
     for (int c = 0; c < C; ++c) out[c] = float_to_half(dequant_value(dequant_lut(sym[c], cq), m), out_dtype);

@@ -175,3 +175,40 @@ def test_rans_divmod_device_formula_bounds(sim):
     for xi, fi in [(65536, 1), (2 ** 32 - 1, 65535), (123456789, 4321)]:
         got = sim.sim_rans_divmod(xi, fi, P(r))
         assert got == xi // fi and int(r[0]) == xi % fi
+
+
+def test_safe_factor_keeps_every_symbol(sim):
+    """quant_factor_safe (the fused encode kernel's clamp-free pass 1): an infinite factor becomes NaN, every other
+    factor is untouched, and the symbols equal the checked quantiser's for ordinary and exotic rows alike."""
+    S = ctypes.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    S.sim_quant_row.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint16, ctypes.c_float, ctypes.c_void_p]
+    S.sim_quant_row_safe.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint16, ctypes.c_float,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(21)
+    C = 64
+    rows = []
+    base = O.f32_to_bf16_bits(rng.standard_normal(C).astype(np.float32))
+    rows.append((base.copy(), 0))
+    z = np.zeros(C, np.uint16); rows.append((z, 0))                                   # all-zero row: max 0 -> factor inf
+    tiny = np.full(C, 0x0001, np.uint16); tiny[::2] = 0x8001; rows.append((tiny, 0))  # bf16 subnormals: MAX / max overflows
+    inf = base.copy(); inf[3] = 0x7f80; inf[9] = 0xff80; rows.append((inf, 0))        # +-inf elements: max inf -> factor 0
+    nan = base.copy(); nan[5] = 0x7fc1; rows.append((nan, 0))                         # NaN element: max NaN
+    h = rng.standard_normal(C).astype(np.float16).view(np.uint16); rows.append((h, 1))
+    hz = np.zeros(C, np.uint16); hz[1] = 0x0001; rows.append((hz, 1))                 # fp16 subnormal maximum (finite factor)
+    for x, dt in rows:
+        a = (x & 0x7fff).astype(np.uint16)
+        f = (a.astype(np.uint32) << 16).view(np.float32) if dt == 0 else a.view(np.float16).astype(np.float32)
+        mb = int(a[np.argmax(np.where(np.isnan(f), np.inf, f))]) if not np.isnan(f).any() else int(a[np.isnan(f)][0])
+        for maxq in (7.0, 15.0):
+            want = np.zeros(C, np.uint8)
+            S.sim_quant_row(P(x), dt, C, mb, maxq, P(want))
+            got = np.zeros(C, np.uint8)
+            fb = np.zeros(1, np.uint32)
+            S.sim_quant_row_safe(P(x), dt, C, mb, maxq, P(got), P(fb))
+            assert np.array_equal(got, want)
+            fm = np.float32(maxq) / ((np.array([mb], np.uint32) << 16).view(np.float32)[0] if dt == 0
+                                     else np.array([mb], np.uint16).view(np.float16)[0].astype(np.float32))
+            if np.isinf(fm):
+                assert np.isnan(fb.view(np.float32)[0])
+            elif not np.isnan(fm):
+                assert fb[0] == np.array([fm], np.float32).view(np.uint32)[0]
