@@ -3,18 +3,25 @@
 
   python bench.py --gpus N --steps K --warmup W            (driver launches N>1 under torchrun)
   python bench.py --impl reference ...                     CPU arm: the oracle port of the reference's path
+  python bench.py --config c4|c5 ...                       BASELINE configs[3] / [4]: engines sharing one lm:// server
 
-Workload (N=1): BASELINE.json configs[1] -- a 32-layer / 32-head / 128-dim, 8192-token bf16 KV block (4 GiB),
-chunk_size 256 -> 32 chunks; every rank codes its own block (weak scaling, no data-path collective: the
-path shards by independent engines).  One step = encode the whole block (absmax -> fused quantise/CDF/
-arithmetic-code/compact -> headers) then decode it back to bf16 KV.
+Workload (N=1, default): BASELINE.json configs[1] -- a 32-layer / 32-head / 128-dim, 8192-token bf16 KV block (4 GiB),
+chunk_size 256 -> 32 chunks; every rank codes its own block (weak scaling, no data-path collective: the path shards by
+independent engines).  One step = encode the whole block (absmax -> fused quantise/CDF/rANS-code/compact -> headers) then
+decode it back to bf16 KV, in waves of 8 chunks on one stream (bounded scratch, no host synchronisation inside a step).
 
-Printed JSON line (rank 0): value = raw bf16 KV bytes / (encode+decode device time), inputs resident in HBM,
-timed with CUDA events on the launch stream, max over ranks.  e2e = the same metric through the C ABI with
-HOST buffers: raw KV starts in pinned host memory, is uploaded, encoded, the containers are copied to
-pinned host memory, uploaded again and decoded; a digest of the result is read back (all copies timed).
-roofline = algorithmic HBM bytes of the dominant kernel / its live event-timed duration vs MEASURED_PEAKS.json.
-cpu_baseline = the CPU oracle (port of the reference path, OpenMP) on a bounded sample of the same workload.
+Printed JSON line (rank 0):
+  value        raw bf16 KV bytes / (encode+decode device time), inputs resident in HBM, CUDA events on the launch stream,
+               max over ranks.
+  e2e          the same metric through the product's public API with HOST memory on the other side:
+               LMCacheEngine.store(tokens, kv) into the compressed page-locked host tier (local_device="cpu",
+               local_serde="cachegen": encode || device->host into the slab) then LMCacheEngine.retrieve(tokens)
+               (host->device || decode); the KV starts on the GPU, as it does in vLLM.  All copies are inside the timed
+               region.  e2e.raw_upload_variant adds an upload of the raw KV from page-locked host memory before every
+               store (the round-1 definition), reported separately because that copy is not part of store().
+  roofline     algorithmic HBM bytes of the dominant kernel / its live event-timed duration vs MEASURED_PEAKS.json.
+  cpu_baseline the CPU oracle (port of the reference path, OpenMP, threads pinned) on a bounded sample of the workload.
+  config.entropy_sweep   the same step on data of higher entropy (up to ~4.1 bits/symbol), beside the headline.
 """
 import argparse
 import ctypes
@@ -42,7 +49,11 @@ def parse_args():
     ap.add_argument("--tokens", type=int, default=8192)
     ap.add_argument("--chunk", type=int, default=256)
     ap.add_argument("--heads", type=int, default=32, help="KV heads (32 = BASELINE configs[1]; 8 = GQA shapes, side measurement)")
-    ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks in the bounded CPU sample")
+    ap.add_argument("--cpu-chunks", type=int, default=8, help="chunks in the bounded CPU sample")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 = BASELINE configs[1] (default, the BENCH/SCALE line); c4 / c5 = configs[3] / [4] (see c45_bench.py)")
+    ap.add_argument("--wave", type=int, default=8, help="chunks per wave of the device-timed step")
+    ap.add_argument("--no-sweep", action="store_true", help="skip config.entropy_sweep")
     ap.add_argument("--data", default="kv8d", choices=list(DATA_KINDS), help="synthetic KV distribution (kv8d = SURVEY 8d, the headline)")
     ap.add_argument("--coder", default="rans", choices=["rans", "ac"], help="payload coder: rans = container v2 (default), ac = v1")
     ap.add_argument("--no-e2e", action="store_true")
@@ -87,9 +98,14 @@ def synth_kv_torch(tokens, device, seed, kind="kv8d"):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm / baseline
-def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321):
+def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321, coder=0):
     """Time the CPU oracle (C port of the reference path, all host threads via OpenMP) on n_chunks chunks of the
-    workload.  Returns (raw GB/s for encode+decode, seconds per step, cores)."""
+    workload.  Threads are pinned (OMP_PROC_BIND=close, OMP_PLACES=cores, set before libgomp starts) and the sample's
+    buffers are first touched by the timed thread team's own warm-up passes, so the figure does not depend on where the
+    kernel happened to place threads and pages.  Returns (raw GB/s from the MEDIAN step, seconds [median, min], cores)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_DYNAMIC", "false")
     import numpy as np
     import torch
 
@@ -109,14 +125,15 @@ def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321):
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         for x in chunks:
-            enc = O.encode_chunk(x, O.DT_BF16, kb, vb)
+            enc = O.encode_chunk(x, O.DT_BF16, kb, vb, coder)
             O.decode_chunk(enc, O.DT_BF16, kb, vb, O.DT_BF16)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    sec = sum(times) / len(times)
+    times.sort()
+    med = times[len(times) // 2]
     raw = n_chunks * chunk * L * 2 * C * 2
-    return raw / sec / 1e9, sec, cores
+    return raw / med / 1e9, (med, times[0]), cores
 
 
 def run_reference_arm(args):
@@ -124,18 +141,24 @@ def run_reference_arm(args):
     if rank != 0:
         return
     n = args.cpu_chunks
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    gbs, sec, cores = cpu_codec_sample(n, args.chunk, steps, warmup)
-    sample = f"{n} of {args.tokens // args.chunk} chunks ([{L},2,{args.chunk},{H},{D}] bf16 each) per step"
+    steps, warmup = max(3, min(args.steps, 5)), max(2, min(args.warmup, 3))
+    gbs, (med, best), cores = cpu_codec_sample(n, args.chunk, steps, warmup)
+    n_all = args.tokens // args.chunk
+    sample = (f"{n} of {n_all} chunks ([{L},2,{args.chunk},{H},{D}] bf16 each) per step; median of {steps} steps after "
+              f"{warmup} warm-ups ({med:.2f} s, best {best:.2f} s); threads pinned (OMP_PROC_BIND=close)")
     print(json.dumps({
         "impl": "reference",
         "metric": "kv_encode_decode_raw_GBps", "value": round(gbs, 4), "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 2),
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(med * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32->u8 (bf16 KV)",
         "data": "synthetic",
         "config": {"workload": f"CacheGen encode+decode, {L}L/{H}H/{D}D {args.tokens}-token bf16 KV block, "
-                               f"chunk_size {args.chunk} (BASELINE configs[1])", "sample": sample},
-        "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+                               f"chunk_size {args.chunk} (BASELINE configs[1])", "sample": sample,
+                   "note": "the reference's own coder (torchac_cuda) is absent, so this arm times the C port of the "
+                           "reference path with the arithmetic coder of the torchac lineage (container v1); a step codes "
+                           f"{n}/{n_all} of the block and value = bytes of those chunks / time"},
+        "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
+                         "best_GBps": round(n * args.chunk * L * 2 * C * 2 / best / 1e9, 4)},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -241,6 +264,19 @@ def parity_spot_check(kv, out, cs):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def regen_kv(kv, seed, kind):
+    """fill the resident block with another distribution, in place (no second 4 GiB allocation)"""
+    import torch
+    T = kv.shape[2]
+    fresh = synth_kv_torch(min(T, 1024), kv.device, seed, kind)      # slab-wise: at most a 0.5 GiB temporary
+    for t0 in range(0, T, fresh.shape[2]):
+        n = min(fresh.shape[2], T - t0)
+        if t0:
+            fresh = synth_kv_torch(n, kv.device, seed + t0, kind)
+        kv[:, :, t0:t0 + n] = fresh[:, :, :n]
+    torch.cuda.synchronize()
+
+
 def main():
     args = parse_args()
     global H, C
@@ -248,12 +284,16 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.config in ("c4", "c5"):
+        import c45_bench
+        c45_bench.main(args)
+        return
     import torch
 
     import __graft_entry__ as ge
     ge.build_cuda()
     from lmcache_b200 import _native as N
-    from lmcache_b200.codec import CacheGenCodec, KvView, PinnedBuffer
+    from lmcache_b200.codec import CacheGenCodec, KvView
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -291,23 +331,74 @@ def main():
     out = torch.empty_like(kv)
     out_view = KvView.from_blob(out, "vllm")
     stride = codec.out_stride(L, H, D, cs)
-    staging = torch.empty(stride * n_chunks + N.READ_SLACK, dtype=torch.uint8, device=dev)
-    dst_tok = [j * cs for j in range(n_chunks)]
-    ntoks = [min(cs, T - j * cs) for j in range(n_chunks)]
+    W = max(1, min(args.wave, n_chunks))
+    staging = torch.empty(stride * W + N.READ_SLACK, dtype=torch.uint8, device=dev)      # ONE wave, reused in stream order
     stream = torch.cuda.current_stream()
+    ws_enc = lib.b200kv_encode_workspace_bytes(L, H, D, cs, W, codec.coder)
+    ws_dec = lib.b200kv_decode_workspace_bytes(L, H, D, cs, W)
 
-    def step_device():
-        batch = codec.encode(view, 0, T, cs, out=staging)            # syncs once to learn the sizes
-        codec.decode_device_batch(batch, ntoks, out_view, dst_tok)
-        return batch
+    def waves():
+        for c0 in range(0, n_chunks, W):
+            k = min(W, n_chunks - c0)
+            yield c0, k, min(k * cs, T - c0 * cs)
+
+    def step_device(collect=None):
+        """encode -> decode, wave by wave on one stream; the decoder takes the slot bound as each container's extent, so
+        nothing in the step waits for the host"""
+        for c0, k, nt in waves():
+            ticket = codec.encode_async(view, c0 * cs, nt, cs, out=staging)
+            if collect is not None:
+                collect(ticket, c0, k)
+            codec.decode_raw(staging.data_ptr(), staging.numel(), [j * stride for j in range(k)], [stride] * k,
+                             [min(cs, T - (c0 + j) * cs) for j in range(k)], out_view, [(c0 + j) * cs for j in range(k)],
+                             N.DT_BF16, codec.coder)
+
+    def measure_sizes():
+        sizes = []
+        step_device(lambda ticket, c0, k: sizes.extend(ticket.wait().sizes))
+        torch.cuda.synchronize()
+        return sizes
+
+    def profile_kernels(steps):
+        """per-kernel live timing (events around each launch inside the library), summed over a step's waves"""
+        lib.b200kv_profile_enable(1)
+        acc = {k: [] for k in N.PROFILE_SLOTS}
+        for _ in range(steps):
+            tot = {k: 0.0 for k in N.PROFILE_SLOTS}
+            for c0, k, nt in waves():
+                ticket = codec.encode_async(view, c0 * cs, nt, cs, out=staging)
+                codec.decode_raw(staging.data_ptr(), staging.numel(), [j * stride for j in range(k)], [stride] * k,
+                                 [min(cs, T - (c0 + j) * cs) for j in range(k)], out_view,
+                                 [(c0 + j) * cs for j in range(k)], N.DT_BF16, codec.coder)
+                buf = (ctypes.c_float * 8)()
+                N.check(lib.b200kv_profile_last(buf, 8))
+                for i, name in enumerate(N.PROFILE_SLOTS):
+                    if buf[i] >= 0:
+                        tot[name] += buf[i]
+            for name, v in tot.items():
+                if v > 0:
+                    acc[name].append(v)
+        lib.b200kv_profile_enable(0)
+        return {k: sum(v) / len(v) for k, v in acc.items() if v}
+
+    def timed(steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            step_device()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / steps
 
     # ---- warm-up + parity spot check (not timed)
     for _ in range(max(args.warmup, 3)):
-        batch = step_device()
-    torch.cuda.synchronize()
-    container_bytes = sum(batch.sizes)
-    payload_bytes = container_bytes - n_chunks * N.container_layout(L, H, D, cs).fixed_bytes
+        step_device()
+    sizes = measure_sizes()
+    container_bytes = sum(sizes)
+    fixed = N.container_layout(L, H, D, cs).fixed_bytes
+    payload_bytes = container_bytes - n_chunks * fixed
     parity = parity_spot_check(kv, out, cs)
+    status_words = codec.decode_status()
 
     # ---- timed: K steps, device-resident inputs (4 GiB >> 126 MB L2: no reuse between iterations)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -324,18 +415,7 @@ def main():
     ms_step = max_over_ranks(ms_total, dev) / args.steps          # device time, max over ranks
     value = aggregate_gbps(raw_bytes, ms_step, world)              # weak scaling: every rank codes its own block
 
-    # ---- per-kernel live timing (events around each launch inside the library), separate passes
-    lib.b200kv_profile_enable(1)
-    prof = {k: [] for k in N.PROFILE_SLOTS}
-    for _ in range(args.steps):
-        step_device()
-        buf = (ctypes.c_float * 8)()
-        N.check(lib.b200kv_profile_last(buf, 8))
-        for i, k in enumerate(N.PROFILE_SLOTS):
-            if buf[i] >= 0:
-                prof[k].append(buf[i])
-    lib.b200kv_profile_enable(0)
-    kern_ms = {k: sum(v) / len(v) for k, v in prof.items() if v}
+    kern_ms = profile_kernels(args.steps)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -343,7 +423,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
-    alg = {  # algorithmic HBM bytes per launch
+    alg = {  # algorithmic HBM bytes per step: read 2 B/elem + write w, and the reverse
         "absmax": raw_bytes,
         "encode": raw_bytes + container_bytes,
         "decode": container_bytes + raw_bytes,
@@ -352,46 +432,72 @@ def main():
                   "achieved_GBps": round(alg[k] / (kern_ms[k] * 1e-3) / 1e9, 1),
                   "frac": round(alg[k] / (kern_ms[k] * 1e-3) / 1e9 / peak, 4)} for k in alg if k in kern_ms}
     dom = max((k for k in ("encode", "decode") if k in kern_ms), key=lambda k: kern_ms[k])
-    # DRAM traffic per launch of the dominant kernel: from the committed ncu --set full capture of this very workload
-    traffic = None
+    # DRAM traffic and instruction counts of one launch come from the COMMITTED ncu --set full capture of this workload
+    # (profiles/r2_traffic.json, made by profiles/traffic.py from the .ncu-rep); they are not measured in this run
+    traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
-        if tj["workload"] == {"tokens": T, "chunk": cs}:
-            for k in alg:
-                if k in rl_all and f"{k}_kernel" in tj:
-                    rl_all[k]["ncu_dram_bytes"] = tj[f"{k}_kernel"]["dram_read_bytes"] + tj[f"{k}_kernel"]["dram_write_bytes"]
-            traffic = rl_all[dom].get("ncu_dram_bytes")
-            # the bound that actually binds these kernels: warp-instruction issue (1 / clk / SMSP).  Instruction counts
-            # come from the same committed ncu capture, the duration and the SM clock are measured live.
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if tj["workload"] == {"tokens": T, "chunk": cs, "data": args.data, "coder": args.coder}:
+            traffic_src = "profiles/r2_traffic.json (committed ncu capture, not measured in this run)"
             sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
             n_smsp = torch.cuda.get_device_properties(dev).multi_processor_count * 4
             for k in alg:
-                wi = tj.get(f"{k}_kernel", {}).get("warp_inst_executed")
-                if k in rl_all and wi:
-                    rl_all[k]["issue"] = {"warp_inst": wi, "issue_slots": round(kern_ms[k] * 1e-3 * sm_mhz * 1e6 * n_smsp),
-                                          "frac": round(wi / (kern_ms[k] * 1e-3 * sm_mhz * 1e6 * n_smsp), 4),
-                                          "ncu_alu_pipe_pct": tj[f"{k}_kernel"].get("ncu_alu_pipe_pct")}
+                e = tj.get(f"{k}_kernel")
+                if k in rl_all and e:
+                    rl_all[k]["ncu_dram_bytes"] = e["dram_read_bytes"] + e["dram_write_bytes"]
+                    if e.get("warp_inst_executed"):
+                        slots = kern_ms[k] * 1e-3 * sm_mhz * 1e6 * n_smsp
+                        rl_all[k]["issue"] = {"warp_inst": e["warp_inst_executed"], "issue_slots": round(slots),
+                                              "frac": round(e["warp_inst_executed"] / slots, 4),
+                                              "ncu_alu_pipe_pct": e.get("ncu_alu_pipe_pct")}
+            traffic = rl_all[dom].get("ncu_dram_bytes")
     except (OSError, KeyError, ValueError):
         pass
     roofline = {"kernel": f"{dom}_kernel", "bound": "hbm", "achieved": rl_all[dom]["achieved_GBps"], "peak": peak,
-                "unit": "GB/s", "frac": rl_all[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "issue/ALU-bound integer kernels (DESIGN.md section 5): DRAM at <15 % of peak; traffic is the ncu "
-                        "dram read+write of one launch, algorithmic bytes are alg_bytes; kernels[*].issue.frac = "
-                        "warp instructions (ncu) / issue slots (live duration x SM clock x SMSPs): the bound that binds",
+                "unit": "GB/s", "frac": rl_all[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
+                "note": "integer coder kernels bound by instruction issue / ALU and shared-memory wavefronts (DESIGN.md "
+                        "section 5), DRAM below 20 % of peak; achieved = algorithmic bytes of a step / summed live "
+                        "event-timed duration of the kernel's launches in that step",
                 "kernels": rl_all, "other_kernels_ms": {k: round(v, 4) for k, v in kern_ms.items() if k not in alg}}
 
-    # ---- e2e through the C ABI with host buffers
+    # ---- the same step on data of higher entropy (not the headline; same shape, same code)
+    sweep = None
+    if not args.no_sweep and world == 1:
+        sweep = [{"data": args.data, "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
+                  "ms_per_step": round(ms_step, 4), "encode_ms": round(kern_ms.get("encode", 0), 4),
+                  "decode_ms": round(kern_ms.get("decode", 0), 4), "container_bytes": container_bytes,
+                  "GBps": round(value, 1), "parity_spot_check": parity}]
+        for kind in [k for k in ("kv8d_nooutlier", "normal", "uniform", "uniform_signed") if k != args.data]:
+            regen_kv(kv, 99 + rank, kind)
+            step_device()
+            sz = measure_sizes()
+            par = parity_spot_check(kv, out, cs)
+            ms = timed(3)
+            km = profile_kernels(2)
+            sweep.append({"data": kind, "payload_bits_per_symbol": round(8.0 * (sum(sz) - n_chunks * fixed) / (raw_bytes / 2), 4),
+                          "ms_per_step": round(ms, 4), "encode_ms": round(km.get("encode", 0), 4),
+                          "decode_ms": round(km.get("decode", 0), 4), "container_bytes": sum(sz),
+                          "GBps": round(raw_bytes / (ms * 1e-3) / 1e9, 1), "parity_spot_check": par})
+
+    # ---- e2e through LMCacheEngine.store()/retrieve() with the compressed host tier
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, codec, kv, out, out_view, staging, stride, dev, world, barrier)
+        del out, out_view, staging
+        torch.cuda.empty_cache()
+        if sweep is not None:
+            kv = synth_kv_torch(T, dev, 1234 + 2 + rank, args.data)
+        e2e = run_e2e(args, kv, dev, world, rank, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        gbs, sec, cores = cpu_codec_sample(args.cpu_chunks, cs, 2, 1)
+        gbs, (med, best), cores = cpu_codec_sample(args.cpu_chunks, cs, 3, 2)
         cpu = {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_chunks} of {n_chunks} chunks per step, {sec:.2f} s/step, OpenMP oracle"}
+               "sample": f"{args.cpu_chunks} of {n_chunks} chunks per step, median of 3 steps after 2 warm-ups "
+                         f"({med:.2f} s, best {best:.2f} s), OpenMP oracle with pinned threads, arithmetic coder (v1)"}
 
     if rank == 0:
+        nlaunch_step = sum(1 for _ in waves()) * 8     # per wave: absmax, encode, scan, compact, finalize + tile_sum, tile_scan, decode
         line = {
             "metric": "kv_encode_decode_raw_GBps", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
@@ -399,13 +505,17 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"CacheGen encode+decode, {L}L/{H}H/{D}D {T}-token bf16 KV block per GPU, "
                                    f"chunk_size {cs} -> {n_chunks} chunks" + (" (BASELINE configs[1])" if (H, T) == (32, 8192) else " (BASELINE configs[2] shape: 65536-token offload + reload; e2e is that config's metric)" if (H, T) == (32, 65536) else " (side measurement, not a BASELINE shape)"),
-                       "data_kind": args.data, "coder": args.coder,
+                       "data_kind": args.data, "coder": args.coder + (" (B2KV container v2)" if args.coder == "rans" else " (B2KV container v1)"),
                        "raw_bytes_per_gpu": raw_bytes, "container_bytes": container_bytes,
                        "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
-                       "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity},
+                       "wave_chunks": W, "device_scratch_bytes": {"staging": staging_bytes(stride, W, N), "encode_workspace": int(ws_enc),
+                                                                  "decode_workspace": int(ws_dec)},
+                       "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity,
+                       "decode_status_words_nonzero": sum(1 for w in status_words if w),
+                       "entropy_sweep": sweep},
             "encode_GBps": round(raw_bytes / (sum(kern_ms.get(k, 0) for k in ("absmax", "cdf", "encode", "compact")) * 1e-3) / 1e9, 1),
             "decode_GBps": round(raw_bytes / (sum(kern_ms.get(k, 0) for k in ("tile_sum", "tile_scan", "decode")) * 1e-3) / 1e9, 1),
-            "gpu_launches": (3 + sum(1 for k in kern_ms if k != "compact")) * args.steps,   # compact slot = scan + compact + finalize
+            "gpu_launches": nlaunch_step * args.steps,
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -413,116 +523,97 @@ def main():
         dist.destroy_process_group()
 
 
-def run_e2e(args, codec, kv, out, out_view, staging, stride, dev, world, barrier):
-    """raw KV in pinned host memory -> H2D -> encode -> containers D2H to pinned host -> H2D -> decode -> digest D2H.
-    Copies run on side streams and overlap with the kernels of neighbouring chunk batches."""
+def staging_bytes(stride, W, N):
+    return int(stride * W + N.READ_SLACK)
+
+
+def run_e2e(args, kv, dev, world, rank, barrier):
+    """LMCacheEngine.store(tokens, kv) -> compressed page-locked host tier -> LMCacheEngine.retrieve(tokens), wall clock.
+    No stream choreography here: the pipelines (encode || D2H, H2D || decode) live in the product
+    (lmcache_b200/pipeline.py, LMCLocalCompressedBackend)."""
     import torch
 
-    from lmcache_b200 import _native as N
-    from lmcache_b200.codec import KvView, PinnedBuffer
-    lib = N.lib()
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.codec import PinnedBuffer
+    from lmcache_b200.config import LMCacheEngineConfig, LMCacheEngineMetadata
+    from lmcache_b200.dist_util import max_over_ranks
     T, cs = args.tokens, args.chunk
     n_chunks = (T + cs - 1) // cs
     raw_bytes = L * 2 * T * C * 2
-    B = 4                                        # chunks per pipeline batch
-    nb = (n_chunks + B - 1) // B
-    batch_tok = B * cs
-    # host buffers: raw KV laid out per batch as [L,2,batch_tok,H,D] blobs; containers at fixed stride
-    host_raw = PinnedBuffer(raw_bytes)
-    host_cont = PinnedBuffer(stride * n_chunks)
-    host_digest = PinnedBuffer(4096)
-    per_batch_bytes = L * 2 * batch_tok * C * 2
-    dev_in = [torch.empty((L, 2, batch_tok, H, D), dtype=torch.bfloat16, device=dev) for _ in range(2)]
-    dev_cont = [torch.empty(stride * B + N.READ_SLACK, dtype=torch.uint8, device=dev) for _ in range(2)]
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    os.environ["LMCACHE_B200_CODER"] = args.coder
+    cfg = LMCacheEngineConfig.from_legacy(chunk_size=cs, backend="cpu", local_serde="cachegen")
+    engine = LMCacheEngine(cfg, LMCacheEngineMetadata(MODEL, world, rank, "vllm", "bfloat16"))
+    backend = engine.engine_
+    kv_tuple = tuple((kv[l, 0], kv[l, 1]) for l in range(L))          # the engine's input: L pairs of [T,H,D] tensors
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    tokens = torch.randint(0, 32000, (T,), device=dev, generator=g)
+    digest = PinnedBuffer(4096)
+    lib = None
+    from lmcache_b200 import _native as N
+    lib = N.lib()
     cur = torch.cuda.current_stream()
-    # stage the raw KV into host memory once (not timed)
-    for b in range(nb):
-        blob = kv[:, :, b * batch_tok:(b + 1) * batch_tok].contiguous()
-        N.check(lib.b200kv_copy_async(host_raw.host_ptr + b * per_batch_bytes, blob.data_ptr(), blob.numel() * 2,
-                                      cur.cuda_stream))
-        torch.cuda.synchronize()
-    sizes_all = [0] * n_chunks
+    t_first = time.perf_counter()
+    engine.store(tokens, kv_tuple, skip_existing=False, blocking=True)   # also pays the slab's cudaHostAlloc
+    first_store_s = time.perf_counter() - t_first
 
-    def one_step():
-        h2d = d2h = 0
-        ev_in = [torch.cuda.Event() for _ in range(nb)]
-        ev_enc = [torch.cuda.Event() for _ in range(nb)]
-        ev_out = [None] * nb
-        # ---- store: upload raw, encode, download containers
-        for b in range(nb):
-            slot = b & 1
-            if b >= 2:
-                s_in.wait_event(ev_enc[b - 2])            # input slot free again
-            N.check(lib.b200kv_copy_async(dev_in[slot].data_ptr(), host_raw.host_ptr + b * per_batch_bytes,
-                                          per_batch_bytes, s_in.cuda_stream))
-            ev_in[b].record(s_in)
-            h2d += per_batch_bytes
-            cur.wait_event(ev_in[b])
-            if b >= 2 and ev_out[b - 2] is not None:
-                cur.wait_event(ev_out[b - 2])              # container slot drained
-            ntok = min(batch_tok, T - b * batch_tok)
-            batch = codec.encode(KvView.from_blob(dev_in[slot], "vllm"), 0, ntok, cs, out=dev_cont[slot])
-            ev_enc[b].record(cur)
-            s_out.wait_event(ev_enc[b])
-            for j, sz in enumerate(batch.sizes):
-                cj = b * B + j
-                sizes_all[cj] = sz
-                N.check(lib.b200kv_copy_async(host_cont.host_ptr + cj * stride, dev_cont[slot].data_ptr() + j * stride,
-                                              sz, s_out.cuda_stream))
-                d2h += sz
-            ev_out[b] = torch.cuda.Event()
-            ev_out[b].record(s_out)
-        # ---- retrieve: upload containers, decode into the KV blob.  No host sync in between: the upload of batch b
-        # waits (on the copy stream) for its containers' download and for the store side to be done with the slot.
-        ev_up = [torch.cuda.Event() for _ in range(nb)]
-        ev_dec = [torch.cuda.Event() for _ in range(nb)]
-        for b in range(nb):
-            slot = b & 1
-            s_in.wait_event(ev_out[b])                    # containers of batch b are in host memory
-            if b >= 2:
-                s_in.wait_event(ev_dec[b - 2])
-            else:
-                last = nb - 1 if ((nb - 1) & 1) == slot else nb - 2          # last store batch that used this slot
-                if last >= 0:
-                    s_in.wait_event(ev_out[last])
-            k = min(B, n_chunks - b * B)
-            for j in range(k):
-                cj = b * B + j
-                N.check(lib.b200kv_copy_async(dev_cont[slot].data_ptr() + j * stride, host_cont.host_ptr + cj * stride,
-                                              sizes_all[cj], s_in.cuda_stream))
-                h2d += sizes_all[cj]
-            ev_up[b].record(s_in)
-            cur.wait_event(ev_up[b])
-            codec.decode_raw(dev_cont[slot].data_ptr(), dev_cont[slot].numel(), [j * stride for j in range(k)],
-                             [sizes_all[b * B + j] for j in range(k)],
-                             [min(cs, T - (b * B + j) * cs) for j in range(k)], out_view,
-                             [(b * B + j) * cs for j in range(k)], N.DT_BF16, codec.coder)
-            ev_dec[b].record(cur)
-        N.check(lib.b200kv_copy_async(host_digest.host_ptr, out.data_ptr(), 4096, cur.cuda_stream))
-        d2h += 4096
+    def one_step(upload_from=None):
+        if upload_from is not None:                       # round-1 definition: raw KV arrives from page-locked host memory
+            N.check(lib.b200kv_copy_async(kv.data_ptr(), upload_from.host_ptr, raw_bytes, cur.cuda_stream))
+        t0 = time.perf_counter()
+        engine.store(tokens, kv_tuple, skip_existing=False, blocking=True)
+        t1 = time.perf_counter()
+        ret, mask = engine.retrieve(tokens)
+        N.check(lib.b200kv_copy_async(digest.host_ptr, ret[0][0].data_ptr(), 4096, cur.cuda_stream))
         cur.synchronize()
-        return h2d, d2h
+        t2 = time.perf_counter()
+        assert int(mask.sum()) == T
+        return t1 - t0, t2 - t1
 
     for _ in range(2):
         one_step()
+    host_bytes = backend.host_bytes()
+    cont_bytes = sum(e.nbytes for e in backend.dict.values() if e.blk is not None)
     barrier()
-    t0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(cur)
     steps = max(2, min(args.steps, 3))
-    for _ in range(steps):
-        h2d, d2h = one_step()
-    ev1.record(cur)
+    t0 = time.perf_counter()
+    parts = [one_step() for _ in range(steps)]
     barrier()
     wall = (time.perf_counter() - t0) / steps
-    from lmcache_b200.dist_util import max_over_ranks
     sec = max_over_ranks(wall, dev)
-    host_raw.close(); host_cont.close(); host_digest.close()
-    return {"value": round(world * raw_bytes / sec / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": round(sec * 1e3, 2), "steps": steps,
-            "path": "pinned host raw KV -> H2D -> b200kv_encode_chunks -> containers D2H -> H2D -> "
-                    "b200kv_decode_chunks -> digest D2H (wall clock incl. all copies, 4-chunk batches, 3 streams)"}
+    ring = backend._pipe.ring
+    res = {"value": round(world * raw_bytes / sec / 1e9, 2), "unit": "GB/s",
+           "h2d_bytes_per_step": cont_bytes, "d2h_bytes_per_step": cont_bytes + 2 * 32 * n_chunks + 4096,
+           "ms_per_step": round(sec * 1e3, 2), "steps": steps,
+           "store_ms": round(1e3 * sum(p[0] for p in parts) / steps, 2),
+           "retrieve_ms": round(1e3 * sum(p[1] for p in parts) / steps, 2),
+           "first_store_s": round(first_store_s, 2),
+           "host_tier_bytes": host_bytes, "slab_segments": backend.slab.stats()[0],
+           "device_scratch_bytes": {"encode_ring": ring.scratch_bytes() if ring else None,
+                                    "wave_chunks": ring.wave if ring else None},
+           "path": "LMCacheEngine.store(tokens, kv_tuple, blocking=True) [sha256 chain -> waves: b200kv_encode_chunks on the "
+                   "caller's stream || device->host of the previous wave's containers into the page-locked slab] then "
+                   "LMCacheEngine.retrieve(tokens) [sha256 chain -> waves: host->device of containers || "
+                   "b200kv_decode_chunks into one blob]; KV starts and ends on the GPU (retrieve returns CUDA tensors, "
+                   "4 KiB of the result is read back); wall clock incl. every copy and host-side step"}
+    # the round-1 variant: the raw KV is first uploaded from page-locked host memory (not part of store(); PCIe-bound)
+    if world == 1 and raw_bytes <= (8 << 30):
+        host_raw = PinnedBuffer(raw_bytes)
+        N.check(lib.b200kv_copy_async(host_raw.host_ptr, kv.data_ptr(), raw_bytes, cur.cuda_stream))
+        cur.synchronize()
+        one_step(host_raw)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            one_step(host_raw)
+        w2 = (time.perf_counter() - t0) / 2
+        host_raw.close()
+        res["raw_upload_variant"] = {"value": round(raw_bytes / w2 / 1e9, 2), "unit": "GB/s", "ms_per_step": round(w2 * 1e3, 2),
+                                     "h2d_bytes_per_step": raw_bytes + cont_bytes,
+                                     "note": "same engine calls preceded by an upload of the raw KV from page-locked host "
+                                             "memory (round 1's e2e definition); that copy dominates and is not part of "
+                                             "the product path"}
+    engine.close()
+    digest.close()
+    return res
 
 
 if __name__ == "__main__":

@@ -111,7 +111,7 @@ int64_t b200kv_decode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t c
  * last one, which holds last_chunk_tokens (1..chunk_tokens).  Its container is written at
  * out + j*out_stride (device memory, out_stride >= layout.max_total_bytes or the call fails with
  * the header status set if the payload does not fit).  sizes_out[j] (device or mapped-host memory)
- * receives total_bytes of chunk j.
+ * receives total_bytes of chunk j, or 0 when the chunk's header carries a nonzero status.
  * key_bins / value_bins: HOST float arrays of length L (make_key_bins / make_value_bins, :339-350).
  * coder: B200KV_CODER_* -- which entropy coder fills the bytestreams (and hence header.version).
  */

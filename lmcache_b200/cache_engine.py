@@ -329,17 +329,24 @@ class LMCacheEngine:
         keys = [self._make_key(h, fmt) for h in chunk_hashes]
         geom = self._kv_geometry()
         if geom is None:
-            # shapes unknown (nothing stored through this engine yet): learn them from the first chunk
-            first = self.engine_.get(keys[0])
-            if first is None:
+            # shapes unknown (nothing stored through this engine yet -- the normal case for a retrieve-only replica):
+            # read them from the first chunk's container header / stored blob; only backends without that door pay
+            # for a full get of chunk 0
+            peek = getattr(self.engine_, "peek_geometry", None)
+            if peek is not None:
+                geom = peek(keys[0], fmt)
+            else:
+                first = self.engine_.get(keys[0])
+                if first is not None:
+                    geom = ((first.shape[0], first.shape[3], first.shape[4]) if fmt == "vllm" else
+                            (first.shape[0], first.shape[2], first.shape[4])) + (first.dtype,)
+            if geom is None:
                 logger.info("Retrieved 0 chunks")
                 ret_mask[:] = False
                 return (), ret_mask
-            L, H, D = (first.shape[0], first.shape[3], first.shape[4]) if fmt == "vllm" else \
-                (first.shape[0], first.shape[2], first.shape[4])
-            self._geom = geom = (L, H, D, first.dtype)
+            self._geom = geom
         L, H, D, dtype = geom
-        od = getattr(getattr(self.engine_, "deserializer", None), "out_dtype", None)
+        od = getattr(self.engine_, "out_dtype", None) or getattr(getattr(self.engine_, "deserializer", None), "out_dtype", None)
         if od is not None:
             dtype = od()
         n_tok_max = len(tokens) - num_skip_chunk * self.chunk_size

@@ -235,6 +235,29 @@ class EncodedBatch:
         return self.buf[j * self.stride: j * self.stride + self.sizes[j]]
 
 
+@dataclass
+class EncodeTicket:
+    """An encode in flight (CacheGenCodec.encode_async).  `wait()` blocks the calling host thread -- not the stream --
+    until the kernels are done and returns the batch with its sizes."""
+    buf: torch.Tensor
+    stride: int
+    n_chunks: int
+    sizes_buf: "PinnedBuffer"
+    event: torch.cuda.Event
+    max_dtype: int
+    coder: int
+    keep: object = None          # keeps the source view (and through it the KV tensors) alive until the kernels ran
+
+    def wait(self) -> EncodedBatch:
+        self.event.synchronize()
+        self.keep = None
+        sizes = list((ctypes.c_uint64 * self.n_chunks).from_address(self.sizes_buf.host_ptr))
+        for j, s in enumerate(sizes):
+            if s < N.HEADER_BYTES or s > self.stride:
+                raise N.NativeError(f"encoder produced an invalid container size {s} for chunk {j}")
+        return EncodedBatch(self.buf, self.stride, [int(s) for s in sizes], self.max_dtype, self.coder)
+
+
 class CacheGenCodec:
     """Batched CacheGen encode / decode on the current CUDA device.
 
@@ -258,8 +281,9 @@ class CacheGenCodec:
         self.nlayers = len(kb)
         self._kb = N.float_array(kb)
         self._vb = N.float_array(vb)
-        self._enc_lock = threading.Lock()
+        self._enc_lock = threading.RLock()
         self._dec_lock = threading.Lock()
+        self._enc_event: Optional[torch.cuda.Event] = None
         self._enc_ws: Optional[torch.Tensor] = None
         self._dec_ws: Optional[torch.Tensor] = None
         self._enc_out: Optional[torch.Tensor] = None
@@ -289,10 +313,15 @@ class CacheGenCodec:
         return lo.max_total_bytes
 
     # ------------------------------------------------------------------ encode
-    def encode(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
-               stream: Optional[torch.cuda.Stream] = None, out: Optional[torch.Tensor] = None) -> EncodedBatch:
-        """Encode tokens [tok_begin, tok_begin + n_tokens) of `view` as ceil(n_tokens / chunk_size) containers.
-        Blocks until the containers' sizes are known (one event wait); payloads stay on the device."""
+    def encode_async(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
+                     stream: Optional[torch.cuda.Stream] = None, out: Optional[torch.Tensor] = None,
+                     sizes: Optional[PinnedBuffer] = None) -> "EncodeTicket":
+        """Enqueue the encode of tokens [tok_begin, tok_begin + n_tokens) of `view` as ceil(n_tokens / chunk_size)
+        containers on `stream` and return at once: no host synchronisation.  The containers land in `out` (device,
+        `out_stride` apart; the codec's own staging when None) and their sizes in `sizes` (mapped page-locked memory,
+        8 bytes per chunk; the codec's own when None) -- both are valid once the ticket's event has completed.
+        The KV is read in stream order, so the caller may reuse it for later work on the same stream (this is the
+        snapshot a non-blocking store needs; reference cache_engine.py:274-275 materialises chunk copies instead)."""
         if n_tokens <= 0:
             raise ValueError("n_tokens must be positive")
         if view.L > self.nlayers:
@@ -302,48 +331,53 @@ class CacheGenCodec:
         stride = self.out_stride(view.L, view.H, view.D, chunk_size)
         lib = N.lib()
         with self._enc_lock, torch.cuda.device(view.device):
+            tstream = stream if stream is not None else torch.cuda.current_stream()
             ws_bytes = lib.b200kv_encode_workspace_bytes(view.L, view.H, view.D, chunk_size, n_chunks, self.coder)
+            own_out, own_sizes = out is None, sizes is None
+            need_out = stride * n_chunks + N.READ_SLACK if own_out else 0
+            # the workspace (and the codec's own staging) are shared by consecutive calls: order after the previous
+            # encode on whatever stream it ran; never free a buffer a kernel may still be using
+            if self._enc_event is not None:
+                grow = (self._enc_ws is None or self._enc_ws.numel() < ws_bytes or self._enc_ws.device != view.device or
+                        (own_out and (self._enc_out is None or self._enc_out.numel() < need_out)))
+                if grow:
+                    self._enc_event.synchronize()
+                else:
+                    tstream.wait_event(self._enc_event)
             self._enc_ws = self._grow(self._enc_ws, ws_bytes, view.device)
-            if out is None:
-                self._enc_out = self._grow(self._enc_out, stride * n_chunks + N.READ_SLACK, view.device)
+            if own_out:
+                self._enc_out = self._grow(self._enc_out, need_out, view.device)
                 out = self._enc_out
             elif out.numel() < stride * n_chunks:
                 raise ValueError("encode output buffer too small")
-            if self._sizes is None or self._sizes.nbytes < 8 * n_chunks:
-                self._sizes = PinnedBuffer(max(4096, 8 * n_chunks))
-            sp = _stream_ptr(stream)
+            if own_sizes:
+                if self._sizes is None or self._sizes.nbytes < 8 * n_chunks:
+                    self._sizes = PinnedBuffer(max(4096, 8 * n_chunks))
+                sizes = self._sizes
+            elif sizes.nbytes < 8 * n_chunks:
+                raise ValueError("sizes buffer too small")
             N.check(lib.b200kv_encode_chunks(ctypes.byref(view.desc), tok_begin, n_chunks, chunk_size, last,
-                                             self._kb, self._vb, self.coder, out.data_ptr(), stride, self._sizes.dev_ptr,
-                                             self._enc_ws.data_ptr(), self._enc_ws.numel(), sp), "encode_chunks")
-            N.check(lib.b200kv_stream_sync(sp), "stream_sync")
-            sizes = list((ctypes.c_uint64 * n_chunks).from_address(self._sizes.host_ptr))
-            # header status is checked on the device copy lazily by consumers; check it here via sizes sanity
-            for j, s in enumerate(sizes):
-                if s < N.HEADER_BYTES or s > stride:
-                    raise N.NativeError(f"encoder produced an invalid container size {s} for chunk {j}")
-            return EncodedBatch(out, stride, [int(s) for s in sizes], int(view.desc.dtype), self.coder)
+                                             self._kb, self._vb, self.coder, out.data_ptr(), stride, sizes.dev_ptr,
+                                             self._enc_ws.data_ptr(), self._enc_ws.numel(), tstream.cuda_stream),
+                    "encode_chunks")
+            ev = torch.cuda.Event()
+            ev.record(tstream)
+            self._enc_event = ev
+            return EncodeTicket(out, stride, n_chunks, sizes, ev, int(view.desc.dtype), self.coder, view)
+
+    def encode(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
+               stream: Optional[torch.cuda.Stream] = None, out: Optional[torch.Tensor] = None) -> EncodedBatch:
+        """encode_async + one event wait: blocks until the containers' sizes are known; payloads stay on the device.
+        With out=None the batch aliases the codec's staging, which the next encode call overwrites."""
+        return self.encode_async(view, tok_begin, n_tokens, chunk_size, stream, out).wait()
 
     def encode_to_host(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
                        stream: Optional[torch.cuda.Stream] = None) -> List[bytes]:
-        """encode + one device->host copy per container into pinned memory, returned as immutable bytes."""
-        batch = self.encode(view, tok_begin, n_tokens, chunk_size, stream)
-        total = sum((s + 15) & ~15 for s in batch.sizes)
-        pin = PinnedBuffer(total)
-        lib = N.lib()
-        sp = _stream_ptr(stream)
-        offs, o = [], 0
-        with torch.cuda.device(view.device):
-            for j, s in enumerate(batch.sizes):
-                N.check(lib.b200kv_copy_async(pin.host_ptr + o, batch.buf.data_ptr() + j * batch.stride, s, sp), "copy")
-                offs.append(o)
-                o += (s + 15) & ~15
-            N.check(lib.b200kv_stream_sync(sp), "stream_sync")
-        outs = [bytes(pin.view(offs[j], batch.sizes[j])) for j in range(len(offs))]
-        for b in outs:
-            hd = parse_header(b)   # raises on encoder error status
-            del hd
-        pin.close()
-        return outs
+        """encode + one device->host copy per container through the codec's page-locked slab, returned as immutable
+        bytes (the Serializer.to_bytes contract, serde.py:12-27).  The encoder lock is held until the copies are done:
+        the staging the batch aliases cannot be overwritten by a concurrent encode."""
+        with self._enc_lock, self.encode_to_pinned(view, tok_begin, n_tokens, chunk_size, stream) as views:
+            return [bytes(v) for v in views]
 
     @contextlib.contextmanager
     def encode_to_pinned(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
@@ -351,9 +385,9 @@ class CacheGenCodec:
         """encode + one device->host copy per container into the codec's page-locked slab (kept across calls, grown on
         demand); yields one writable memoryview per container.  The views -- e.g. handed to a socket send -- are valid
         inside the `with` block only: the slab is reused by the next call (serialised by a lock)."""
-        batch = self.encode(view, tok_begin, n_tokens, chunk_size, stream)
-        total = sum((s + 15) & ~15 for s in batch.sizes)
-        with self._pin_lock:
+        with self._enc_lock, self._pin_lock:
+            batch = self.encode(view, tok_begin, n_tokens, chunk_size, stream)
+            total = sum((s + 15) & ~15 for s in batch.sizes)
             if self._pin_out is None or self._pin_out.nbytes < total:
                 if self._pin_out is not None:
                     self._pin_out.close()

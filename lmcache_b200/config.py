@@ -29,18 +29,30 @@ class LMCacheEngineConfig:
     remote_serde: Optional[str]   # "torch" | "cachegen" | ...
     pipelined_backend: bool
     save_decode_cache: bool
+    # not in the reference: how the LOCAL host tier keeps chunks.  None = raw blobs, as the reference does
+    # (local_backend.py:95-100); "cachegen" = CacheGen containers in page-locked memory (LMCLocalCompressedBackend).
+    # The environment variable LMCACHE_B200_LOCAL_SERDE sets the default for configurations that do not name it.
+    local_serde: Optional[str] = None
+
+    def __post_init__(self):
+        if self.local_serde is None:
+            import os
+            self.local_serde = os.environ.get("LMCACHE_B200_LOCAL_SERDE") or None
+        if self.local_serde not in (None, "cachegen"):
+            raise ValueError(f"Invalid local serde: {self.local_serde}")
 
     @staticmethod
     def from_defaults(chunk_size: int = 256, local_device: str = "cuda",
                       remote_url: str = "redis://localhost:6379", remote_serde: str = "torch",
-                      pipelined_backend: bool = False, save_decode_cache: bool = False) -> "LMCacheEngineConfig":
+                      pipelined_backend: bool = False, save_decode_cache: bool = False,
+                      local_serde: Optional[str] = None) -> "LMCacheEngineConfig":
         return LMCacheEngineConfig(chunk_size, local_device, remote_url, remote_serde, pipelined_backend,
-                                   save_decode_cache)
+                                   save_decode_cache, local_serde)
 
     @staticmethod
     def from_legacy(chunk_size: int = 256, backend: str = "cuda", persist_path: Optional[str] = None,
                     remote_serde: Optional[str] = "torch", pipelined_backend: bool = False,
-                    save_decode_cache: bool = False) -> "LMCacheEngineConfig":
+                    save_decode_cache: bool = False, local_serde: Optional[str] = None) -> "LMCacheEngineConfig":
         """backend: "cpu" | "cuda" | "file://<dir>/" | "<scheme>://<host>:<port>" (config.py:51-82)."""
         local_device: Optional[str] = None
         remote_url: Optional[str] = None
@@ -51,7 +63,7 @@ class LMCacheEngineConfig:
         elif _URL_RE.match(backend):
             remote_url = backend
         return LMCacheEngineConfig(chunk_size, local_device, remote_url, remote_serde, pipelined_backend,
-                                   save_decode_cache)
+                                   save_decode_cache, local_serde)
 
     @staticmethod
     def from_file(file_path: str) -> "LMCacheEngineConfig":
@@ -64,6 +76,7 @@ class LMCacheEngineConfig:
         remote_serde = cfg.get("remote_serde", "torch")
         pipelined_backend = cfg.get("pipelined_backend", False)
         save_decode_cache = cfg.get("save_decode_cache", False)
+        local_serde = cfg.get("local_serde", None)
 
         if local_device in ("cpu", "cuda", None):
             pass
@@ -76,7 +89,7 @@ class LMCacheEngineConfig:
             raise ValueError(f"Invalid remote storage url: {remote_url}")
 
         return LMCacheEngineConfig(chunk_size, local_device, remote_url, remote_serde, pipelined_backend,
-                                   save_decode_cache)
+                                   save_decode_cache, local_serde)
 
 
 class GlobalConfig:

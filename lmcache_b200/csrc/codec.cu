@@ -737,7 +737,7 @@ __global__ void finalize_kernel(EncParams P) {
     hd->total_bytes = (uint64_t)lo.off_payload + P.totals[j];
     hd->status = P.err[j];
     hd->reserved[0] = hd->reserved[1] = hd->reserved[2] = 0u;
-    if (P.sizes_out) P.sizes_out[j] = hd->total_bytes;
+    if (P.sizes_out) P.sizes_out[j] = hd->status ? 0ull : hd->total_bytes;     // 0 = this chunk failed (see header.status)
 }
 
 // ------------------------------------------------------------------------------------------ decode

@@ -9,6 +9,9 @@ def CreateStorageBackend(config: LMCacheEngineConfig, metadata: LMCacheEngineMet
         from lmcache_b200.storage_backend.remote_backend import LMCPipelinedRemoteBackend, LMCRemoteBackend
         return (LMCPipelinedRemoteBackend if config.pipelined_backend else LMCRemoteBackend)(config, metadata)
     if isinstance(local, str) and remote is None:
+        if local == "cpu" and config.local_serde == "cachegen":
+            from lmcache_b200.storage_backend.local_backend import LMCLocalCompressedBackend
+            return LMCLocalCompressedBackend(config, metadata)
         if local in ("cpu", "cuda"):
             from lmcache_b200.storage_backend.local_backend import LMCLocalBackend
             return LMCLocalBackend(config)

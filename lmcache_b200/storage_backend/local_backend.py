@@ -113,6 +113,17 @@ class LMCLocalBackend(LMCBackendInterface):
     def supports_kv_view(self) -> bool:
         return True
 
+    def peek_geometry(self, key, fmt: str = "vllm"):
+        """(L, H, D, dtype) of a stored chunk blob, from its shape (no copy): [L,2,t,H,D] (vllm) / [L,2,H,t,D] (hf)."""
+        val = self.dict.get(key, None)
+        if val is None:
+            return None
+        t = val.host if isinstance(val, _HostEntry) else val
+        if t.dim() != 5:
+            return None
+        return (t.shape[0], t.shape[2], t.shape[4], t.dtype) if fmt == "huggingface" else \
+            (t.shape[0], t.shape[3], t.shape[4], t.dtype)
+
     def put_kv_chunks(self, keys, view, tok_begin: int, chunk_size: int, blocking: bool = True) -> int:
         """Store tokens [tok_begin, T) of `view` as len(keys) chunk blobs: ONE gather kernel (b200kv_pack_chunks)
         builds every chunk blob; for the host tier ONE device->host DMA moves them all into a page-locked slab."""
@@ -236,4 +247,236 @@ class LMCLocalBackend(LMCBackendInterface):
         try:
             self.close()
         except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------- compressed host tier
+class _CEntry:
+    """One CacheGen container in the page-locked slab."""
+    __slots__ = ("blk", "nbytes", "ntokens", "L", "H", "D", "max_dtype", "coder", "ready", "error", "last_read")
+
+    def __init__(self):
+        self.blk = None
+        self.nbytes = 0
+        self.ntokens = 0
+        self.L = self.H = self.D = 0
+        self.max_dtype = 0
+        self.coder = 0
+        self.ready = threading.Event()       # set by the store worker once the container is in host memory
+        self.error: Optional[BaseException] = None
+        self.last_read: Optional[torch.cuda.Event] = None   # most recent upload out of the block
+
+
+class LMCLocalCompressedBackend(LMCBackendInterface):
+    """local_device="cpu" + local_serde="cachegen": the host tier keeps CacheGen containers instead of raw blobs.
+
+    Replaces LMCLocalBackend("cpu") (lmcache/storage_backend/local_backend.py:28-153) for BASELINE configs[2]: the
+    bytes crossing PCIe and sitting in host memory shrink by the codec's ratio (5.9x on the SURVEY 8d data), and both
+    directions are pipelined (lmcache_b200/pipeline.py):
+      store     waves of chunks are encoded on the caller's stream (enqueue only) while a worker thread moves the
+                previous wave's containers -- exactly their bytes -- into the page-locked slab on a copy stream;
+      retrieve  the containers of wave i+1 are uploaded on a copy stream while wave i is decoded straight into the
+                destination; slot reuse is ordered by events, the host never waits.
+    Every container lives in one PinnedSlab (one cudaHostAlloc per GiB, not one per put)."""
+
+    def __init__(self, config: LMCacheEngineConfig, metadata):
+        super().__init__()
+        from lmcache_b200.codec import CacheGenCodec
+        from lmcache_b200.pipeline import EncodePipeline, UploadRing
+        from lmcache_b200.slab import PinnedSlab
+        N.require_cuda()
+        self.chunk_size = config.chunk_size
+        self.fmt = metadata.fmt
+        if self.fmt not in ("vllm", "huggingface"):
+            raise ValueError(f"Invalid format: {self.fmt}")
+        self.codec = CacheGenCodec(metadata.model_name)      # ValueError for models outside the bin table
+        self.slab = PinnedSlab()
+        self.dict: Dict[CacheEngineKey, _CEntry] = {}
+        self.update_lock = threading.Lock()
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._pipe = EncodePipeline(self.codec, self._sink)
+        self._upload: Optional[UploadRing] = None
+        self._retired = []                                    # (event, block): overwritten entries still being read
+        self._closed = False
+
+    # ------------------------------------------------------------------ store
+    def _sink(self, slot, batch, c0, entries) -> None:
+        """worker thread: the wave's containers -> slab (one async copy each, exactly `size` bytes), then publish"""
+        dev = slot.dev.device
+        with torch.cuda.device(dev):
+            if self._copy_stream is None or self._copy_stream.device != dev:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            cs = self._copy_stream
+            try:
+                blocks = []
+                for j, size in enumerate(batch.sizes):
+                    blk = self.slab.alloc(size)
+                    blocks.append(blk)
+                    N.check(N.lib().b200kv_copy_async(ctypes.c_void_p(blk.host_ptr),
+                                                      ctypes.c_void_p(slot.dev.data_ptr() + j * batch.stride), size,
+                                                      cs.cuda_stream), "copy_async")
+                cs.synchronize()
+                from lmcache_b200.codec import parse_header
+                for e, blk in zip(entries, blocks):
+                    hd = parse_header(blk.view())              # raises on a nonzero encoder status
+                    e.blk, e.nbytes, e.ntokens = blk, blk.nbytes, int(hd.ntokens)
+                    e.L, e.H, e.D, e.max_dtype, e.coder = int(hd.L), int(hd.H), int(hd.D), int(hd.max_dtype), int(hd.version) - 1
+            except BaseException as err:     # noqa: BLE001
+                for e in entries:
+                    e.error = err
+                raise
+            finally:
+                for e in entries:
+                    e.ready.set()
+
+    def _retire(self, e: _CEntry) -> None:
+        if e.blk is None:
+            return
+        if e.last_read is not None and not e.last_read.query():
+            self._retired.append((e.last_read, e.blk))
+        else:
+            e.blk.free()
+        e.blk = None
+
+    def _sweep(self) -> None:
+        keep = []
+        for ev, blk in self._retired:
+            if ev.query():
+                blk.free()
+            else:
+                keep.append((ev, blk))
+        self._retired = keep
+
+    def put_kv_chunks(self, keys, view, tok_begin: int, chunk_size: int, blocking: bool = True) -> int:
+        entries = [_CEntry() for _ in keys]
+        old = []
+        with self.update_lock:                      # visible at once: contains() is true, readers wait on `ready`
+            for k, e in zip(keys, entries):
+                prev = self.dict.get(k)
+                if prev is not None:
+                    old.append(prev)
+                self.dict[k] = e
+        job = self._pipe.submit(view, tok_begin, chunk_size, entries)
+        for prev in old:                            # an overwritten container leaves once nobody reads it any more
+            prev.ready.wait()
+            self._retire(prev)
+        self._sweep()
+        if blocking:
+            job.wait()
+        return len(keys)
+
+    @_lmcache_nvtx_annotate
+    def put(self, key: CacheEngineKey, kv_chunk: torch.Tensor, blocking: bool = True) -> None:
+        from lmcache_b200.codec import KvView
+        if not kv_chunk.is_cuda:
+            kv_chunk = kv_chunk.cuda()              # reference: tensor.cuda() in the serializer (cachegen_encoder.py:383)
+        view = KvView.from_blob(kv_chunk, self.fmt)
+        self.put_kv_chunks([key], view, 0, view.ntokens, blocking=blocking)
+
+    # ------------------------------------------------------------------ lookup
+    def contains(self, key: CacheEngineKey) -> bool:
+        e = self.dict.get(key)
+        if e is None:
+            return False
+        if e.ready.is_set() and e.error is not None:
+            return False
+        return True
+
+    def _ready_entry(self, key) -> Optional[_CEntry]:
+        e = self.dict.get(key)
+        if e is None:
+            return None
+        e.ready.wait()
+        return None if e.error is not None or e.blk is None else e
+
+    def peek_geometry(self, key, fmt: str = "vllm"):
+        """(L, H, D, output dtype) of the stored chunks, read from a container header (no decode)."""
+        e = self._ready_entry(key)
+        return None if e is None else (e.L, e.H, e.D, self.out_dtype())
+
+    def out_dtype(self) -> torch.dtype:
+        # the reference's decoder casts by format, ignoring metadata.dtype (cachegen_decoder.py:189-200)
+        return torch.bfloat16 if self.fmt == "vllm" else torch.float16
+
+    # ------------------------------------------------------------------ retrieve
+    def supports_kv_view(self) -> bool:
+        return True
+
+    def get_kv_into(self, keys, dst, dst_tok0: int, chunk_size: int) -> int:
+        """Upload + decode consecutive chunks (until the first miss) straight into `dst`; chunk i lands at token
+        dst_tok0 + i * chunk_size.  Everything is enqueued: copies on the copy stream, decodes on the current stream."""
+        from lmcache_b200.pipeline import UploadRing, wave_chunks_default
+        hits = []
+        for i, key in enumerate(keys):
+            e = self._ready_entry(key)
+            if e is None or (e.L, e.H, e.D) != (dst.L, dst.H, dst.D):
+                break
+            tok = dst_tok0 + i * chunk_size
+            if tok + e.ntokens > dst.ntokens:
+                break
+            if hits and (e.max_dtype, e.coder) != (hits[0].max_dtype, hits[0].coder):
+                break
+            hits.append(e)
+        if not hits:
+            return 0
+        W = wave_chunks_default()
+        lib = N.lib()
+        with torch.cuda.device(dst.device):
+            if self._upload is None or self._upload.device != dst.device:
+                self._upload = UploadRing(dst.device)
+            up = self._upload
+            cur = torch.cuda.current_stream()
+            for w0 in range(0, len(hits), W):
+                wave = hits[w0:w0 + W]
+                offs, o = [], 0
+                for e in wave:
+                    offs.append(o)
+                    o += (e.nbytes + 15) & ~15
+                slot, buf = up.next_slot(o)
+                for e, off in zip(wave, offs):
+                    N.check(lib.b200kv_copy_async(ctypes.c_void_p(buf.data_ptr() + off), ctypes.c_void_p(e.blk.host_ptr),
+                                                  e.nbytes, up.copy_stream.cuda_stream), "copy_async")
+                ev = torch.cuda.Event()
+                ev.record(up.copy_stream)
+                for e in wave:
+                    e.last_read = ev
+                cur.wait_event(ev)
+                self.codec.decode_raw(buf.data_ptr(), buf.numel(), offs, [e.nbytes for e in wave],
+                                      [e.ntokens for e in wave], dst,
+                                      [dst_tok0 + (w0 + j) * chunk_size for j in range(len(wave))],
+                                      wave[0].max_dtype, wave[0].coder, cur)
+                up.mark_read(slot, cur)
+        return len(hits)
+
+    @_lmcache_nvtx_annotate
+    def get(self, key: CacheEngineKey) -> Optional[torch.Tensor]:
+        from lmcache_b200.codec import KvView
+        e = self._ready_entry(key)
+        if e is None:
+            return None
+        shape = (e.L, 2, e.ntokens, e.H, e.D) if self.fmt == "vllm" else (e.L, 2, e.H, e.ntokens, e.D)
+        out = torch.empty(shape, dtype=self.out_dtype(), device=torch.device("cuda", torch.cuda.current_device()))
+        if self.get_kv_into([key], KvView.from_blob(out, self.fmt), 0, e.ntokens) != 1:
+            return None
+        return out
+
+    def host_bytes(self) -> int:
+        """bytes of containers currently held (for reports)"""
+        return self.slab.stats()[2]
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        self._pipe.close()
+        try:
+            torch.cuda.synchronize()
+        except Exception:       # noqa: BLE001 -- interpreter shutdown
+            pass
+        self.slab.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001
             pass

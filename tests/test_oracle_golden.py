@@ -99,3 +99,33 @@ def test_sha256_against_hashlib():
     for n in [1, 7, 55, 56, 63, 64, 65, 119, 120, 1000]:
         toks = rng.integers(0, 256, n, dtype=np.uint8)
         assert O.sha256_chain(toks, 1 << 20)[0] == hashlib.sha256(toks.tobytes()).hexdigest()
+
+
+def test_ref_torch_helper_pinned_to_goldens(golden, golden_names):
+    """tests/ref_torch.py (the torch restatement the full-size GPU parity tests and bench.py's spot check lean on) against
+    the vectors generated from the reference's own torch_quant_vectorized / do_dequantize (tests/golden/make_golden.py)."""
+    import sys
+    import os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_torch
+    kb, vb = torch.from_numpy(golden["key_bins"]), torch.from_numpy(golden["value_bins"])
+    for n in golden_names:
+        x = golden[f"{n}/x"]
+        dt = torch.bfloat16 if int(golden[f"{n}/dtype"][0]) == 0 else torch.float16
+        blob = torch.from_numpy(x.view(np.int16).copy()).view(dt)
+        L, _, t, H, D = blob.shape
+        sym, mk, mv = ref_torch.quantize(blob, kb, vb)
+        assert np.array_equal(sym.numpy(), golden[f"{n}/sym"]), n
+        assert np.array_equal(mk.view(torch.int16).numpy().view(np.uint16).reshape(L, t), golden[f"{n}/max_k"].reshape(L, t)), n
+        assert np.array_equal(mv.view(torch.int16).numpy().view(np.uint16).reshape(L, t), golden[f"{n}/max_v"].reshape(L, t)), n
+        for fmt, key in (("vllm", "deq_vllm_bf16"), ("huggingface", "deq_hf_fp16")):
+            out = ref_torch.roundtrip(blob, kb, vb, fmt)
+            got = out.contiguous().view(torch.int16).numpy().view(np.uint16)
+            want = golden[f"{n}/{key}"]
+            fa = got.astype(np.uint32) << 16 if fmt == "vllm" else None
+            same = got == want.reshape(got.shape)
+            if not same.all():                      # NaN payloads may differ; nothing else may
+                g = (got.astype(np.uint32) << 16).view(np.float32) if fmt == "vllm" else got.view(np.float16)
+                w = (want.reshape(got.shape).astype(np.uint32) << 16).view(np.float32) if fmt == "vllm" else want.reshape(got.shape).view(np.float16)
+                assert (same | (np.isnan(g) & np.isnan(w))).all(), (n, fmt)
