@@ -555,6 +555,7 @@ def run_e2e(args, kv, dev, world, rank, barrier):
     t_first = time.perf_counter()
     engine.store(tokens, kv_tuple, skip_existing=False, blocking=True)   # also pays the slab's cudaHostAlloc
     first_store_s = time.perf_counter() - t_first
+    backend.reserve_host(3 * backend.host_bytes())       # overwriting stores hold the old and the new containers for a moment
 
     def one_step(upload_from=None):
         if upload_from is not None:                       # round-1 definition: raw KV arrives from page-locked host memory

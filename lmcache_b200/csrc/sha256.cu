@@ -16,6 +16,8 @@
 //      streams the precomputed (W + K) blocks through 64 fully unrolled rounds with register renaming.
 //      Independent sequences (batched requests, RAG chunk mixes) occupy the other lanes / warps.
 #include <cuda_runtime.h>
+
+#include <mutex>
 #include <stdint.h>
 
 #include "common.cuh"
@@ -246,14 +248,40 @@ extern "C" int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const 
     const int64_t n_blocks = nchunks * bpc;
     const size_t tab_bytes = sizeof(int64_t) * 3 * (size_t)(n_seq + 1);
     const size_t tab_pad = (tab_bytes + 255) & ~(size_t)255;
-    uint8_t* dmem = nullptr;
-    cudaError_t e = cudaMallocAsync(&dmem, tab_pad + (size_t)n_blocks * 256, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dmem, tab, tab_bytes, cudaMemcpyHostToDevice, stream);   // staged before return
-    free(tab);
-    if (e != cudaSuccess) {
-        if (dmem) cudaFreeAsync(dmem, stream);
-        B2_CHECK_CUDA(e);
+    // Scratch comes from a grow-only per-device buffer owned by the library, not from cudaMallocAsync: the default memory
+    // pool hands its memory back to the driver at every synchronisation point (release threshold 0), so a per-call pool
+    // allocation turned into a real allocation -- 3 to 90 ms once the process has gigabytes of mapped page-locked memory
+    // (measured, round 2) -- on the critical path of every store() and retrieve().  Calls are ordered through an event, so
+    // two streams can share the buffer.
+    static std::mutex mu;
+    static uint8_t* g_buf[64] = {nullptr};
+    static size_t g_cap[64] = {0};
+    static cudaEvent_t g_ev[64] = {nullptr};
+    int devi = 0;
+    B2_CHECK_CUDA(cudaGetDevice(&devi));
+    if (devi < 0 || devi >= 64) devi = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    const size_t need = tab_pad + (size_t)n_blocks * 256;
+    if (g_ev[devi] == nullptr) {
+        cudaError_t ee = cudaEventCreateWithFlags(&g_ev[devi], cudaEventDisableTiming);
+        if (ee != cudaSuccess) { free(tab); B2_CHECK_CUDA(ee); }
+    } else {
+        cudaError_t ee = g_cap[devi] < need ? cudaEventSynchronize(g_ev[devi]) : cudaStreamWaitEvent(stream, g_ev[devi], 0);
+        if (ee != cudaSuccess) { free(tab); B2_CHECK_CUDA(ee); }
     }
+    if (g_cap[devi] < need) {
+        if (g_buf[devi]) cudaFree(g_buf[devi]);
+        g_buf[devi] = nullptr;
+        g_cap[devi] = 0;
+        const size_t cap = need < ((size_t)1 << 20) ? ((size_t)1 << 20) : need * 2;
+        cudaError_t ee = cudaMalloc(&g_buf[devi], cap);
+        if (ee != cudaSuccess) { free(tab); B2_CHECK_CUDA(ee); }
+        g_cap[devi] = cap;
+    }
+    uint8_t* dmem = g_buf[devi];
+    cudaError_t e = cudaMemcpyAsync(dmem, tab, tab_bytes, cudaMemcpyHostToDevice, stream);   // pageable: staged before return
+    free(tab);
+    B2_CHECK_CUDA(e);
     ShaParams P;
     P.tokens = static_cast<const uint8_t*>(tokens);
     P.seq_offsets = reinterpret_cast<const int64_t*>(dmem);
@@ -270,7 +298,7 @@ extern "C" int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const 
         sha256_chain_kernel<<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
         e = cudaGetLastError();
     }
-    cudaFreeAsync(dmem, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(g_ev[devi], stream);
     B2_CHECK_CUDA(e);
     return 0;
 }

@@ -460,6 +460,11 @@ class LMCLocalCompressedBackend(LMCBackendInterface):
             return None
         return out
 
+    def reserve_host(self, nbytes: int) -> None:
+        """Page-lock at least nbytes of slab up front (a cudaHostAlloc of 1 GiB takes ~0.3 s: better at start-up than
+        inside a store)."""
+        self.slab.reserve(int(nbytes))
+
     def host_bytes(self) -> int:
         """bytes of containers currently held (for reports)"""
         return self.slab.stats()[2]

@@ -1,9 +1,19 @@
 """LMCRemoteBackend -- serde + connector (lmcache/storage_backend/remote_backend.py:24-180) and the pipelined
 variant (:183-275).  This is the caller of the serde plugins: put = to_bytes -> connection.set,
-get = connection.get -> from_bytes.  Non-blocking puts keep the reference's single worker thread, so at most
-one encode runs at a time per backend (the codec owns per-direction buffers under that assumption)."""
+get = connection.get -> from_bytes.  The generic per-chunk path keeps the reference's single put worker thread.
+
+Engine fast paths (CacheGen serde + a connector with get_into), both pipelined and striped over several connections:
+  put   waves of chunks are encoded on the caller's stream (enqueue only -- this is also the snapshot a non-blocking
+        store needs, the caller may reuse its KV buffers in stream order); a worker moves each finished wave's containers
+        to a page-locked slab and sends them over k connections in parallel;
+  get   the containers of all requested chunks are fetched by k connections into the slab while the main thread uploads
+        and decodes the waves that are already complete (network || H2D || decode: what remote_backend.py:183-275 does
+        with a network thread and a deserialize thread, here also on the engine's one-blob path).
+LMCACHE_B200_REMOTE_CONNS sets k (default 4; one TCP stream tops out at 2-4 GB/s)."""
+import os
 import queue
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import Iterable, Iterator, List, Optional, Set, Tuple, Union
 
 import torch
@@ -39,6 +49,19 @@ class LMCRemoteBackend(LMCBackendInterface):
             queue.Queue()
         self.put_thread = threading.Thread(target=self.put_worker, args=(), daemon=True)
         self.put_thread.start()
+        # fast-path machinery, built on first use
+        self._url = config.remote_url
+        self._nconn = max(1, int(os.environ.get("LMCACHE_B200_REMOTE_CONNS", "4")))
+        self._pool: Optional[ThreadPoolExecutor] = None
+        self._tls = threading.local()
+        self._conns: List = []
+        self._conns_lock = threading.Lock()
+        self._slab = None
+        self._pipe = None
+        self._upload = None
+        self._copy_stream = None
+        self._inflight = []          # (event, [slab blocks]) of uploads still reading host memory
+        self._peek = None            # (key, block, nbytes): the container peek_geometry fetched, reused by get_kv_into
 
     @_lmcache_nvtx_annotate
     def put_worker(self):
@@ -105,6 +128,77 @@ class LMCRemoteBackend(LMCBackendInterface):
         """True when the serde plugin can encode / decode straight from / into the engine's KV tensors."""
         return hasattr(self.serializer, "view_to_bytes_batch") and hasattr(self.deserializer, "decode_into")
 
+    def _striped(self) -> bool:
+        return hasattr(self.connection, "get_into") and hasattr(self.serializer, "codec") and \
+            hasattr(self.deserializer, "container_bound")
+
+    # k connections, one per pool thread (a connection serialises whole request / response exchanges)
+    def _conn(self):
+        c = getattr(self._tls, "conn", None)
+        if c is None:
+            c = CreateConnector(self._url)
+            self._tls.conn = c
+            with self._conns_lock:
+                self._conns.append(c)
+        return c
+
+    def _executor(self) -> ThreadPoolExecutor:
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=self._nconn, thread_name_prefix="b200kv-net")
+        return self._pool
+
+    def _host_slab(self):
+        if self._slab is None:
+            from lmcache_b200.slab import PinnedSlab
+            self._slab = PinnedSlab()
+        return self._slab
+
+    def _sweep(self, wait: bool = False) -> None:
+        keep = []
+        for ev, blocks in self._inflight:
+            if wait:
+                ev.synchronize()
+            if wait or ev.query():
+                for b in blocks:
+                    b.free()
+            else:
+                keep.append((ev, blocks))
+        self._inflight = keep
+
+    # ---- put
+    def _sink(self, slot, batch, c0, keys) -> None:
+        """store worker: one wave's containers -> page-locked slab (async copies on a copy stream), then k-way send"""
+        import ctypes
+
+        import torch as _t
+
+        from lmcache_b200 import _native as N
+        from lmcache_b200.codec import parse_header
+        dev = slot.dev.device
+        slab = self._host_slab()
+        with _t.cuda.device(dev):
+            if self._copy_stream is None or self._copy_stream.device != dev:
+                self._copy_stream = _t.cuda.Stream(device=dev)
+            cs = self._copy_stream
+            blocks = [slab.alloc(sz) for sz in batch.sizes]
+            try:
+                for j, (blk, sz) in enumerate(zip(blocks, batch.sizes)):
+                    N.check(N.lib().b200kv_copy_async(ctypes.c_void_p(blk.host_ptr),
+                                                      ctypes.c_void_p(slot.dev.data_ptr() + j * batch.stride), sz,
+                                                      cs.cuda_stream), "copy_async")
+                cs.synchronize()
+                for blk in blocks:
+                    parse_header(blk.view())          # raises on a nonzero encoder status: nothing corrupt leaves the host
+
+                def send(key, blk):
+                    self._conn().set(self._combine_key(key), blk.view())
+                    return key
+                for key in self._executor().map(send, keys, blocks):
+                    self.existing_keys.add(key)
+            finally:
+                for blk in blocks:
+                    blk.free()
+
     def _put_view_blocking(self, keys, view, tok_begin: int, chunk_size: int) -> None:
         n_tokens = view.ntokens - tok_begin
         if hasattr(self.serializer, "view_to_pinned_batch"):
@@ -123,32 +217,83 @@ class LMCRemoteBackend(LMCBackendInterface):
 
     def put_kv_chunks(self, keys: List[CacheEngineKey], view, tok_begin: int, chunk_size: int,
                       blocking: bool = True) -> int:
-        """Store tokens [tok_begin, T) of `view` as len(keys) chunks: one batched encode (all chunks in one kernel
-        launch sequence), then one set() per chunk.  Replaces the engine's blob pack + per-chunk to_bytes."""
-        if blocking:
+        """Store tokens [tok_begin, T) of `view` as len(keys) chunks.  Striped path: every wave is encoded on the caller's
+        stream before this returns (so a non-blocking store has consumed the caller's KV in stream order -- paged caches
+        included -- like the reference's materialised chunk list, cache_engine.py:274-275); D2H and the sends happen on
+        the pipeline's worker.  Other serdes: one batched encode, then one set() per chunk."""
+        if self._striped():
+            if self._pipe is None:
+                from lmcache_b200.pipeline import EncodePipeline
+                self._pipe = EncodePipeline(self.serializer.codec, self._sink, name="b200kv-remote-store")
+            job = self._pipe.submit(view, tok_begin, chunk_size, list(keys))
+            if blocking:
+                job.wait()
+                self.flush()
+            return len(keys)
+        if blocking or getattr(view.desc, "slot_map", None):
+            # a paged view aliases vLLM's live cache: never queue it for a later encode
             self._put_view_blocking(keys, view, tok_begin, chunk_size)
         else:
             self.put_queue.put(("view", list(keys), view, tok_begin, chunk_size))
         return len(keys)
 
+    def flush(self) -> None:
+        """PUT carries no acknowledgement (lmcache/server/__main__.py:46-48), but a connection is served in order: one
+        EXIST round trip per connection means the server has processed every PUT sent before it.  A blocking store ends
+        with this, so another engine's retrieve that starts afterwards finds the chunks."""
+        with self._conns_lock:
+            conns = list(self._conns)
+        for c in conns:
+            try:
+                c.exists("b200kv-flush")
+            except Exception:       # noqa: BLE001
+                pass
+
+    def drain(self) -> None:
+        """Wait until every queued / in-flight put of this backend has reached the server."""
+        self.put_queue.join()
+        if self._pipe is not None and self._pipe.ring is not None:
+            self._pipe.ring.drain()
+        self.flush()
+
+    # ---- get
+    def _fetch(self, key: CacheEngineKey, bound: int):
+        """pool thread: one GET into a fresh slab block -> (block, nbytes) or None on a miss"""
+        blk = self._host_slab().alloc(bound)
+        try:
+            n = self._conn().get_into(self._combine_key(key), blk.host_ptr, bound)
+        except Exception:      # noqa: BLE001 -- a broken connection is a miss
+            n = None
+        if not n:
+            blk.free()
+            return None
+        return blk, int(n)
+
+    def peek_geometry(self, key: CacheEngineKey, fmt: str = "vllm"):
+        """(L, H, D, output dtype) from the header of the first chunk's container.  The fetched container is kept for the
+        get_kv_into call that follows, so a retrieve-only replica neither decodes nor fetches chunk 0 twice."""
+        if not (self._striped() and hasattr(self.deserializer, "out_dtype")):
+            return None
+        from lmcache_b200.codec import parse_header
+        blk = self._host_slab().alloc(256 << 20)          # the geometry is what we are asking for: be generous
+        try:
+            n = self.connection.get_into(self._combine_key(key), blk.host_ptr, blk.cap)
+            hd = parse_header(blk.view()[:n]) if n else None
+        except Exception:       # noqa: BLE001 -- broken connection / damaged container: a miss
+            hd = None
+        if hd is None:
+            blk.free()
+            return None
+        if self._peek is not None:
+            self._peek[1].free()
+        self._peek = (key, blk, int(n))
+        return (int(hd.L), int(hd.H), int(hd.D), self.deserializer.out_dtype())
+
     def get_kv_into(self, keys: List[CacheEngineKey], dst, dst_tok0: int, chunk_size: int) -> int:
-        """Fetch consecutive chunks until the first miss and decode them with ONE batched launch straight into `dst`
-        (chunk i lands at token dst_tok0 + i * chunk_size).  Returns (number of chunks, tokens written)."""
-        if hasattr(self.connection, "get_into") and hasattr(self.deserializer, "pinned_staging"):
-            # receive straight into a page-locked slab and upload from there (true async copies, no bytearrays)
-            bound = (self.deserializer.container_bound(dst.L, dst.H, dst.D, chunk_size) + 63) & ~63
-            with self.deserializer.pinned_staging(bound * len(keys)) as pin:
-                blobs = []
-                for i, key in enumerate(keys):
-                    if not self.contains(key):
-                        break
-                    n = self.connection.get_into(self._combine_key(key), pin.host_ptr + i * bound, bound)
-                    if n is None or n == 0:
-                        break
-                    blobs.append(pin.view(i * bound, n))
-                if blobs:
-                    self.deserializer.decode_into(blobs, dst, [dst_tok0 + i * chunk_size for i in range(len(blobs))])
-                return len(blobs)
+        """Fetch consecutive chunks until the first miss and decode them straight into `dst` (chunk i lands at token
+        dst_tok0 + i * chunk_size).  Returns the number of chunks."""
+        if self._striped() and hasattr(self.deserializer, "codec"):
+            return self._get_striped(list(keys), dst, dst_tok0, chunk_size)
         blobs = []
         for key in keys:
             if not self.contains(key):
@@ -161,10 +306,120 @@ class LMCRemoteBackend(LMCBackendInterface):
             self.deserializer.decode_into(blobs, dst, [dst_tok0 + i * chunk_size for i in range(len(blobs))])
         return len(blobs)
 
+    def _get_striped(self, keys, dst, dst_tok0: int, chunk_size: int) -> int:
+        import ctypes
+
+        import torch as _t
+
+        from lmcache_b200 import _native as N
+        from lmcache_b200.codec import parse_header
+        from lmcache_b200.pipeline import UploadRing, wave_chunks_default
+        self._sweep()
+        codec = self.deserializer.codec
+        bound = (self.deserializer.container_bound(dst.L, dst.H, dst.D, chunk_size) + 255) & ~255
+        ex = self._executor()
+        window = max(2 * self._nconn, 2 * wave_chunks_default())       # fetches in flight ahead of the consumer
+        futs = {}
+        peek, self._peek = self._peek, None
+
+        def want(i):
+            if i < len(keys) and i not in futs:
+                if peek is not None and i == 0 and peek[0] == keys[0]:
+                    futs[i] = None                                    # already in host memory
+                else:
+                    futs[i] = ex.submit(self._fetch, keys[i], bound)
+        for i in range(min(window, len(keys))):
+            want(i)
+        W = wave_chunks_default()
+        n_done = 0
+        lib = N.lib()
+        with _t.cuda.device(dst.device):
+            if self._upload is None or self._upload.device != dst.device:
+                self._upload = UploadRing(dst.device)
+            up = self._upload
+            cur = _t.cuda.current_stream()
+            wave = []                   # (block, nbytes, header, chunk index)
+
+            def flush():
+                if not wave:
+                    return
+                offs, o = [], 0
+                for _, n, _, _ in wave:
+                    offs.append(o)
+                    o += (n + 15) & ~15
+                slot, buf = up.next_slot(o)
+                for (blk, n, _, _), off in zip(wave, offs):
+                    N.check(lib.b200kv_copy_async(ctypes.c_void_p(buf.data_ptr() + off), ctypes.c_void_p(blk.host_ptr), n,
+                                                  up.copy_stream.cuda_stream), "copy_async")
+                ev = _t.cuda.Event()
+                ev.record(up.copy_stream)
+                self._inflight.append((ev, [w[0] for w in wave]))
+                cur.wait_event(ev)
+                h0 = wave[0][2]
+                codec.decode_raw(buf.data_ptr(), buf.numel(), offs, [w[1] for w in wave], [int(w[2].ntokens) for w in wave],
+                                 dst, [dst_tok0 + w[3] * chunk_size for w in wave], int(h0.max_dtype), int(h0.version) - 1, cur)
+                up.mark_read(slot, cur)
+                wave.clear()
+
+            miss = False
+            for i in range(len(keys)):
+                want(i + window)
+                f = futs.pop(i)
+                got = (peek[1], peek[2]) if f is None else f.result()
+                if got is None:
+                    miss = True
+                    break
+                blk, n = got
+                try:
+                    hd = parse_header(blk.view()[:n])
+                    ok = (hd.L, hd.H, hd.D) == (dst.L, dst.H, dst.D) and \
+                        dst_tok0 + i * chunk_size + hd.ntokens <= dst.ntokens and \
+                        (not wave or (hd.max_dtype, hd.version) == (wave[0][2].max_dtype, wave[0][2].version))
+                except ValueError:
+                    ok = False                      # damaged container: a miss, not an error
+                if not ok:
+                    blk.free()
+                    miss = True
+                    break
+                wave.append((blk, n, hd, i))
+                n_done += 1
+                if len(wave) == W:
+                    flush()
+            flush()
+        for f in futs.values():                      # fetches past the first miss: let them finish, drop their blocks
+            if f is not None:
+                r = f.result()
+                if r is not None:
+                    r[0].free()
+        if peek is not None and (n_done == 0 or peek[0] != keys[0]):
+            peek[1].free()
+        del miss
+        return n_done
+
     def close(self):
         if self.put_thread is not None and self.put_thread.is_alive():
             self.put_queue.put(RemoteBackendEndSignal())
             self.put_thread.join()
+        if getattr(self, "_pipe", None) is not None:
+            self._pipe.close()
+            self._pipe = None
+        if getattr(self, "_pool", None) is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        if getattr(self, "_inflight", None):
+            self._sweep(wait=True)
+        if getattr(self, "_peek", None) is not None:
+            self._peek[1].free()
+            self._peek = None
+        for c in getattr(self, "_conns", []):
+            try:
+                c.close()
+            except Exception:       # noqa: BLE001
+                pass
+        self._conns = []
+        if getattr(self, "_slab", None) is not None:
+            self._slab.close()
+            self._slab = None
         if self.connection is not None:
             self.connection.close()
             self.connection = None

@@ -366,7 +366,7 @@ def test_remote_cachegen_matches_reference_chain(fmt, pipelined, lmserver, autor
     assert engine._fast_path() == (engine_path == "fast")
     engine.store(tokens, kv, blocking=not pipelined)
     if pipelined:
-        engine.engine_.put_queue.join()     # non-blocking store: wait for the put worker to drain
+        engine.engine_.drain()              # non-blocking store: wait until the server holds every chunk
     r, m = engine.retrieve(tokens)
     assert torch.sum(m) == T
     kb, vb = (torch.tensor(b) for b in O.make_bins(model))
