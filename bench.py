@@ -354,9 +354,15 @@ def main():
                              N.DT_BF16, codec.coder)
 
     def measure_sizes():
+        """container sizes of the resident block; also picks the decoder's table layout the way the product does from
+        the headers (b200kv_decode_chunks: transposed above 3.6 payload bits per symbol) -- the timed step hands the
+        decoder slot bounds instead of sizes, so it is told through the library's measurement knob"""
         sizes = []
+        os.environ.pop("B200KV_DECODE_TABLE", None)
         step_device(lambda ticket, c0, k: sizes.extend(ticket.wait().sizes))
         torch.cuda.synchronize()
+        bps = 8.0 * (sum(sizes) - n_chunks * N.container_layout(L, H, D, cs).fixed_bytes) / (raw_bytes / 2)
+        os.environ["B200KV_DECODE_TABLE"] = "transposed" if bps > 3.6 else "rows"
         return sizes
 
     def profile_kernels(steps):

@@ -102,7 +102,7 @@ def main(args):
 
     c4 = args.config == "c4"
     T = 16384 if c4 else 4096
-    n_seq = (2 if c4 else 16)
+    n_seq = (4 if c4 else 16)
     if args.tokens not in (8192, T):
         T = args.tokens                         # smaller shapes for smoke runs
     raw_seq = L * 2 * T * C * 2
@@ -121,12 +121,13 @@ def main(args):
     writer = (rank == 0) if c4 else True
     reader = (rank == (1 if world > 1 else 0)) if c4 else True
     store_s = retr_lat = None
-    wire = 0
     eng_w = engine(0 if c4 else rank) if writer else None
-    # warm the pipelines (page-locked slabs, rings) outside the timed regions, on keys nobody reads
+    # warm the pipelines (page-locked slab segments, rings, upload slots) outside the timed regions: one full-length
+    # sequence that is stored and read back before anything is timed
+    gw = torch.Generator(device=dev).manual_seed(31337 + (0 if c4 else rank))
+    warm = torch.randint(0, 32000, (T,), device=dev, generator=gw)
     if writer:
-        warm = torch.randint(0, 32000, (min(T, 4 * cs),), device=dev, generator=g)
-        eng_w.store(warm, tuple((k[:warm.numel()], v[:warm.numel()]) for k, v in tuples[0]))
+        eng_w.store(warm, tuples[0])
     barrier()
     if writer:
         t0 = time.perf_counter()
@@ -139,6 +140,10 @@ def main(args):
     if reader:
         # c4: a replica that never stored anything (its geometry comes from a container header); c5: the storing engine
         eng_r = engine(0) if c4 else eng_w
+        wr, wm = eng_r.retrieve(warm)
+        torch.cuda.synchronize()
+        assert int(wm.sum()) == T
+        del wr
         import random
         order = list(range(n_seq)) if c4 else random.Random(7 + rank).sample(range(n_seq), n_seq // 2)
         retr_lat = []

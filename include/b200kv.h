@@ -35,6 +35,10 @@ extern "C" {
 #define B200KV_CODER_AC 0          /* payload = torchac-lineage arithmetic coder; container version 1 */
 #define B200KV_CODER_RANS 1        /* payload = rANS, 32-bit state / 16-bit renormalisation; container version 2 */
 #define B200KV_CONTAINER_VERSION(coder) ((coder) + 1) /* "B2KV" wire container version (b200kv_header.version) */
+#define B200KV_ENCODE_HINT_HIGH_ENTROPY 0x100 /* OR into `coder` of b200kv_encode_chunks: the caller expects more than ~2.7
+                                               * payload bits per symbol (e.g. the previous call's sizes said so); selects the
+                                               * TMA-staged encode kernel whose time does not grow with entropy.  Output bytes
+                                               * are identical either way. */
 #define B200KV_LP 33            /* CDF entries per stream (cachegen_encoder.py:287-289: int(bins.max()) + 1) */
 #define B200KV_GROUP_TOKENS 256 /* CACHEGEN_GPU_MAX_TOKENS_PER_CHUNK (cachegen_basics.py:13) */
 #define B200KV_MAX_PLANES 128   /* 2 * nlayers upper bound */

@@ -19,6 +19,7 @@ DT_FP16 = 1
 CODER_AC = 0       # container version 1: arithmetic coder
 CODER_RANS = 1     # container version 2: rANS
 CODERS = {"ac": CODER_AC, "rans": CODER_RANS}
+ENCODE_HINT_HIGH_ENTROPY = 0x100   # B200KV_ENCODE_HINT_HIGH_ENTROPY
 LP = 33
 GROUP_TOKENS = 256
 MAX_PLANES = 128

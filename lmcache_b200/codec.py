@@ -247,6 +247,8 @@ class EncodeTicket:
     max_dtype: int
     coder: int
     keep: object = None          # keeps the source view (and through it the KV tensors) alive until the kernels ran
+    codec: object = None         # told the measured bits per symbol (picks the next call's kernel variant)
+    stats: tuple = (0, 0.0)      # (fixed bytes per container, symbols in this call)
 
     def wait(self) -> EncodedBatch:
         self.event.synchronize()
@@ -255,6 +257,9 @@ class EncodeTicket:
         for j, s in enumerate(sizes):
             if s < N.HEADER_BYTES or s > self.stride:
                 raise N.NativeError(f"encoder produced an invalid container size {s} for chunk {j}")
+        if self.codec is not None and self.stats[1] > 0:
+            self.codec._last_bits_per_symbol = 8.0 * (sum(sizes) - self.n_chunks * self.stats[0]) / self.stats[1]
+            self.codec = None
         return EncodedBatch(self.buf, self.stride, [int(s) for s in sizes], self.max_dtype, self.coder)
 
 
@@ -284,6 +289,7 @@ class CacheGenCodec:
         self._enc_lock = threading.RLock()
         self._dec_lock = threading.Lock()
         self._enc_event: Optional[torch.cuda.Event] = None
+        self._last_bits_per_symbol = 0.0        # payload bits per symbol of the most recent encode whose sizes were read
         self._enc_ws: Optional[torch.Tensor] = None
         self._dec_ws: Optional[torch.Tensor] = None
         self._enc_out: Optional[torch.Tensor] = None
@@ -356,14 +362,19 @@ class CacheGenCodec:
                 sizes = self._sizes
             elif sizes.nbytes < 8 * n_chunks:
                 raise ValueError("sizes buffer too small")
+            # KV statistics of one model are stable from call to call: the previous call's measured entropy picks the
+            # encode kernel variant for this one (byte-identical output either way)
+            flags = self.coder | (N.ENCODE_HINT_HIGH_ENTROPY if self._last_bits_per_symbol > 2.7 else 0)
             N.check(lib.b200kv_encode_chunks(ctypes.byref(view.desc), tok_begin, n_chunks, chunk_size, last,
-                                             self._kb, self._vb, self.coder, out.data_ptr(), stride, sizes.dev_ptr,
+                                             self._kb, self._vb, flags, out.data_ptr(), stride, sizes.dev_ptr,
                                              self._enc_ws.data_ptr(), self._enc_ws.numel(), tstream.cuda_stream),
                     "encode_chunks")
             ev = torch.cuda.Event()
             ev.record(tstream)
             self._enc_event = ev
-            return EncodeTicket(out, stride, n_chunks, sizes, ev, int(view.desc.dtype), self.coder, view)
+            fixed = N.container_layout(view.L, view.H, view.D, chunk_size).fixed_bytes
+            return EncodeTicket(out, stride, n_chunks, sizes, ev, int(view.desc.dtype), self.coder, view, self,
+                                (fixed, 2.0 * view.L * view.H * view.D * n_tokens))
 
     def encode(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
                stream: Optional[torch.cuda.Stream] = None, out: Optional[torch.Tensor] = None) -> EncodedBatch:

@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ac_core.cuh"
 #include "common.cuh"
@@ -497,6 +498,218 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
     if (tid == 0) P.tile_tot[(int64_t)j * P.tiles_full + id.tile_in_chunk] = tile_total;
 }
 
+// ------------------------------------------------------------------------------------------ encode, TMA-staged
+// The fused rANS encoder again, rebuilt around three facts the profiles of the kernel above showed (profiles/r2b_*):
+// it is bound by instruction issue (85 % at 0.6 bits/symbol) and, at high entropy, by shared-memory bank conflicts (9.9
+// extra wavefronts per warp-symbol at 4.1 bits); its per-thread LDG.U16 loads with their address arithmetic cost 4.4
+// instructions per symbol; and packing symbols into shared-memory rows only to unpack them again costs another 4.
+//   * Input tiles arrive through the TMA unit: `cp.async.bulk` copies of the tile's token rows (128 channels = 256
+//     contiguous bytes each; any row pitch, paged slots included) into a 3-stage ring of 16-token boxes, completion on
+//     mbarriers.  A symbol's load is then one LDS.U16 at an immediate offset.
+//   * No symbol rows: pass 2 streams the tile through the ring a second time (last box first: rANS codes a stream back
+//     to front) and re-quantises -- 4 instructions, fewer than store + load + unpack, and 22 KB of shared memory less.
+//     The second read is served by L2 or DRAM; the kernel sits at a fifth of the HBM roofline, the bytes are there.
+//   * One TRANSPOSED table [32 entries][128 streams] of 32-bit words serves as histogram (pass 1: one red.shared.add
+//     per symbol) and then as the coder's (start | freq << 16) table (pass 2: one LDS per symbol): a lane never leaves
+//     its own bank, so neither pass has bank conflicts at any entropy; the columns are thread-private, so the passes
+//     need no CTA-wide barrier between them.
+// Eligibility (host side): rANS, chunk <= 256 tokens, tiles of exactly 128 channels that are contiguous in every
+// token row, 16-byte aligned rows.  Everything else takes encode_kernel above.
+constexpr int BOXT = 16;                 // tokens per ring box: 16 x 256 B = 4 KB
+constexpr int RSTAGES = 3;
+constexpr int kEncTmaSmem = 32 * CT * 4 + (kGroup + 16) * 4 + (kGroup + 8) * 4 + RSTAGES * BOXT * CT * 2 + 64;
+
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tLAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra LAB_DONE;\n\tbra LAB_WAIT;\n\tLAB_DONE:\n\t}" ::"r"(a), "r"(parity), "r"(20000u) : "memory");
+}
+// one row of a box: global -> shared through the TMA unit, completion (bytes) on the stage's mbarrier
+__device__ __forceinline__ void bulk_row_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+template <int DT, bool PAGED>
+__global__ void __launch_bounds__(CT, 7) encode_tma_kernel(EncParams P) {
+    extern __shared__ __align__(128) uint8_t smem8[];
+    uint32_t* tbl = reinterpret_cast<uint32_t*>(smem8);                                   // [32][CT]: counts, then (start | freq << 16)
+    float* fac = reinterpret_cast<float*>(smem8 + 32 * CT * 4);                          // [kGroup + 16]
+    float* ntab = fac + (kGroup + 16);                                                    // fl32(n / t), n = 0..t
+    uint8_t* ring = smem8 + 32 * CT * 4 + (kGroup + 16) * 4 + (kGroup + 8) * 4;          // RSTAGES boxes of BOXT x 256 B
+    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t bar_a = ring_a + RSTAGES * BOXT * CT * 2;                              // full[RSTAGES], empty[RSTAGES]
+    __shared__ uint32_t s_warp[CT / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    TileId id;
+    if (!decode_tile(P, blockIdx.x, &id)) return;
+    const int NL = 2 * P.L;
+    const int j = id.j, nl = id.nl, ct = id.ct, t = id.t, gt = id.gt;
+    const int c = ct * CT + tid;
+    uint8_t* cont = P.out + (int64_t)j * P.out_stride;
+    const Layout lo = make_layout(P.L, P.C, t);
+    const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + id.tok0;
+    const float maxq = P.pt.maxq[nl];
+    const int64_t tokabs = P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0;
+    // channel 0 of this tile in row 0 of the plane; the tile's 128 channels are contiguous in every row (host checked)
+    const uint16_t* tile0 = P.pt.p[nl] + (int64_t)((ct * CT) / P.D) * P.sH + ((ct * CT) % P.D);
+    const int NB = (gt + BOXT - 1) / BOXT;               // boxes per pass
+    const int NQ = 2 * NB;                               // pass 1 forwards, pass 2 backwards
+
+    // ---- prologue: factors, n/t table, zeroed counters, barriers
+    for (int i = tid; i < kGroup + 16; i += CT)
+        fac[i] = i < gt ? quant_factor_safe(maxq, half_to_float(maxes[i], DT)) : 0.0f;
+    {
+        const float tf = (float)t;
+        for (int n = tid; n <= t; n += CT) ntab[n] = fdiv((float)n, tf);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tbl[i * CT + tid] = 0u;
+    if (tid == 0) {
+        for (int s = 0; s < RSTAGES; ++s) {
+            mbar_init(bar_a + 8 * s, 1);                          // full: the producer's expect_tx arrival (+ the bytes)
+            mbar_init(bar_a + 8 * (RSTAGES + s), CT / 32);        // empty: one arrival per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // box q of the 2 NB box sequence: pass 1 walks boxes 0..NB-1, pass 2 walks NB-1..0
+    auto issue = [&](int q) {                                      // warp 0, all lanes
+        const int b = q < NB ? q : NQ - 1 - q;
+        const int rows = min(BOXT, gt - b * BOXT);
+        const int stage = q % RSTAGES;
+        const uint32_t full = bar_a + 8 * stage;
+        if (lane == 0) mbar_expect_tx(full, (uint32_t)rows * CT * 2);
+        __syncwarp();
+        if (lane < rows) {
+            const int64_t row = tok_row<PAGED>(P.slot_map, tokabs + b * BOXT + lane);
+            bulk_row_g2s(ring_a + (uint32_t)(stage * BOXT + lane) * CT * 2, tile0 + row * P.sT, CT * 2, full);
+        }
+    };
+    if (warp == 0)
+        for (int q = 0; q < min(RSTAGES, NQ); ++q) issue(q);
+
+    uint32_t* const mycol = tbl + tid;
+    const uint32_t mycol_a = (uint32_t)__cvta_generic_to_shared(mycol);
+    auto consume_done = [&](int q) {                               // every thread, after its last read of box q
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a + 8 * (RSTAGES + q % RSTAGES));
+        if (warp == 0 && q + RSTAGES < NQ) {                       // the stage is free once all four warps have arrived
+            mbar_wait(bar_a + 8 * (RSTAGES + q % RSTAGES), (uint32_t)(q / RSTAGES) & 1u);
+            issue(q + RSTAGES);
+        }
+    };
+    auto load_box = [&](int q, uint16_t (&x)[BOXT]) {
+        const int stage = q % RSTAGES;
+        mbar_wait(bar_a + 8 * stage, (uint32_t)(q / RSTAGES) & 1u);
+        const uint16_t* colp = reinterpret_cast<const uint16_t*>(ring) + stage * (BOXT * CT) + tid;
+#pragma unroll
+        for (int k = 0; k < BOXT; ++k) x[k] = colp[k * CT];        // LDS.U16 at immediate offsets
+    };
+
+    // ---- pass 1: histogram (one shared-memory reduction per symbol, conflict-free by layout)
+    auto count = [&](uint16_t xv, float f) {
+        const uint32_t sym = quant_symbol_nc(half_to_float(xv, DT), f, maxq);
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(mycol_a + sym * (CT * 4)) : "memory");
+    };
+    for (int q = 0; q < NB; ++q) {
+        uint16_t x[BOXT];
+        load_box(q, x);
+        const int tk0 = q * BOXT;
+        const int rows = min(BOXT, gt - tk0);
+        if (rows == BOXT) {                                         // all boxes but (at most) the last: no per-token test
+#pragma unroll
+            for (int k = 0; k < BOXT; ++k) count(x[k], fac[tk0 + k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < BOXT; ++k)
+                if (k < rows) count(x[k], fac[tk0 + k]);
+        }
+        consume_done(q);
+    }
+
+    // ---- CDF from the thread's own column, written back as (start | freq << 16) over the counts
+    uint32_t c32;
+    {
+        uint32_t cnt[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cnt[i] = mycol[i * CT];
+        CdfAccum acc;
+        acc.init(t);
+        uint32_t c0 = acc.next_p(0u, ntab[cnt[0]]);
+#pragma unroll
+        for (uint32_t i = 0; i < 31u; ++i) {
+            const uint32_t c1 = acc.next_p(i + 1u, ntab[cnt[i + 1]]);
+            mycol[i * CT] = c0 | ((c1 - c0) << 16);                 // symbols are <= 30: entry 31 is never coded
+            c0 = c1;
+        }
+        c32 = acc.next_p(32u, 0.0f);
+        mycol[31 * CT] = c0 | (c32 << 16);                          // keeps cdf[31] and cdf[32] for the container's CDF row
+    }
+
+    // ---- pass 2: rANS, last token first
+    uint32_t x_state = kRansLow;
+    uint32_t* trow = P.temp + ((int64_t)blockIdx.x * CT + tid) * P.tempw;
+    const uint16_t* const wend = reinterpret_cast<const uint16_t*>(trow) + 2 * TEMPW_FUSED_RANS;
+    int32_t nk = 0;
+    auto code = [&](uint16_t xv, float f) {
+        // the same symbol as pass 1 without the XU pipe (F2I there, reciprocal + F2I in rans_put here): adding
+        // 1.5 * 2^23 rounds v to an integer half-to-even exactly like F2I.RN and leaves it in the low mantissa bits;
+        // fmaxf turns the NaN of a "safe factor" row into the bias itself, i.e. symbol 0, as F2I does
+        const float v = fadd(fmul(half_to_float(xv, DT), f), maxq);
+        const uint32_t sym = __float_as_uint(fmaxf(__fadd_rn(v, 12582912.0f), 12582912.0f)) & 31u;
+        uint32_t pk;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pk) : "r"(mycol_a + sym * (CT * 4)));
+        rans_put(x_state, nk, wend, pk & 0xffffu, pk >> 16);
+    };
+    for (int q = NB; q < NQ; ++q) {
+        uint16_t x[BOXT];
+        load_box(q, x);
+        const int b = NQ - 1 - q;
+        const int tk0 = b * BOXT;
+        const int rows = min(BOXT, gt - tk0);
+        if (rows == BOXT) {
+#pragma unroll
+            for (int k = BOXT - 1; k >= 0; --k) code(x[k], fac[tk0 + k]);
+        } else {
+#pragma unroll
+            for (int k = BOXT - 1; k >= 0; --k)
+                if (k < rows) code(x[k], fac[tk0 + k]);
+        }
+        consume_done(q);
+    }
+    P.rstate[(int64_t)blockIdx.x * CT + tid] = x_state;
+    const uint32_t len = 4u - 2u * (uint32_t)nk;
+
+    // ---- stream lengths, tile total, CDF rows (staged through the now idle ring: stream-major u16[33] rows,
+    //      contiguous in the container -> one coalesced copy)
+    reinterpret_cast<int32_t*>(cont + lo.off_lengths)[((int64_t)id.g * NL + nl) * P.C + c] = (int32_t)len;
+    uint32_t tile_total;
+    (void)block_excl_scan(len, s_warp, &tile_total);               // has a __syncthreads: every thread is done with the ring
+    if (tid == 0) P.tile_tot[(int64_t)j * P.tiles_full + id.tile_in_chunk] = tile_total;
+    if (id.g == 0) {                                                // the CDF belongs to the chunk; its first group writes it
+        uint16_t* stg = reinterpret_cast<uint16_t*>(ring);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[tid * kLp + i] = (uint16_t)mycol[i * CT];
+        stg[tid * kLp + 32] = (uint16_t)c32;
+        __syncthreads();
+        uint16_t* dstc = reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
+        for (int e = tid; e < CT * kLp; e += CT) dstc[e] = stg[e];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ cdf (chunks > 256 tokens)
 template <int DT, bool PAGED>
 __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
@@ -901,12 +1114,22 @@ __device__ __forceinline__ void decode_stream(const uint8_t* cont, uint32_t my_o
     }
 }
 
+// one lower-bound step through a stream's table whose entries are PITCH bytes apart: a += ROWS entries iff the entry ROWS
+// further is <= key.  The add is an IMAD with an opaque multiplier (FMA pipe; see rans_decode_stream).
+template <uint32_t ROWS, uint32_t PITCH>
+__device__ __forceinline__ void rans_search_step(uint32_t& a, uint32_t key, uint32_t one) {
+    uint32_t ev;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(ev) : "r"(a), "n"(ROWS * PITCH));
+    asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+        : "+r"(a) : "r"(ev), "r"(key), "r"(one), "n"(ROWS * PITCH));
+}
+
 // rANS decode loop (container version 2): one stream, gt symbols, straight to the destination layout.
 // Per symbol: key = (x << 16) | 0xffff; lower-bound search over the stream's packed table pk[i] = (cdf[i] << 16) | freq(i)
 // -- the two top levels sit in registers, the rest are LDS off a running shared-memory address --; the winning entry
 // carries start and freq, so the state update is one multiply-add; at most one 16-bit renormalisation (a PRMT out of the
 // two-word window, a predicated aligned load when the window moves on).  Returns the final state (2^16 when intact).
-template <int OUT_DT, int NSTEPS, bool PAGED>
+template <int OUT_DT, int NSTEPS, bool PAGED, bool TR>
 __device__ __forceinline__ uint32_t rans_decode_stream(const uint8_t* cont, uint32_t my_off, const uint32_t* pk,
                                                        const float* lut, const float* mx, uint16_t* dst, uint32_t sT, int gt,
                                                        const int64_t* slots, uint32_t one) {
@@ -921,15 +1144,24 @@ __device__ __forceinline__ uint32_t rans_decode_stream(const uint8_t* cont, uint
     RansDec st;
     rans_dec_init(st, src, (my_off >> 1) & 1u);
     constexpr uint32_t H = 1u << (NSTEPS - 1);
+    // `pk` points at this stream's entry 0.  Two table layouts (decode_kernel builds either):
+    //   TR = false  rows of 33 words per stream (odd pitch: lanes that read the SAME entry never collide; lanes that read
+    //               different entries sometimes do -- 2.7 extra wavefronts per warp-symbol at 0.6 bits/symbol, 7.4 at 4.1)
+    //   TR = true   transposed, entry i of every stream in one 512-byte row: a lane never leaves its own bank, at the
+    //               price of two more instructions per symbol for the LUT address and a two-step table build
+    // The host picks by the containers' measured bits per symbol (b200kv_decode_chunks).
+    constexpr uint32_t kPitch = TR ? CT * 4u : 4u;
+    constexpr uint32_t kIdx = TR ? CT : 1u;
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(pk);
-    const uint32_t a0h = a0 + 4u * H;
-    const uint32_t r_mid = pk[H], r_lo = pk[H / 2], r_hi = pk[H + H / 2];
-    const uint32_t lut_rel = (uint32_t)__cvta_generic_to_shared(lut) - a0;     // lut[s] lives at (a0 + 4 s) + lut_rel
+    const uint32_t a0h = a0 + kPitch * H;
+    const uint32_t r_mid = pk[kIdx * H], r_lo = pk[kIdx * (H / 2)], r_hi = pk[kIdx * (H + H / 2)];
+    const uint32_t lut_a = (uint32_t)__cvta_generic_to_shared(lut);            // TR: lut[s] = lut_a + ((a - a0) >> 7)
+    const uint32_t lut_rel = lut_a - a0;                                       // !TR: lut[s] = a + lut_rel
     uint32_t off = 0u;                                                         // element offset of the current token row
     // The integer ALU pipe (ISETP / SEL / PRMT / LOP3, one warp instruction per 2 cycles) is what bounds this loop, the
     // FMA pipe idles: additions and shifts are therefore written as IMADs whose multiplier ptxas cannot fold (`one` is
     // 1 but comes from a kernel parameter), which pins them to the FMA pipe.
-    const uint32_t c64k = one << 16, mone = 0u - one, two = one + one;
+    const uint32_t c64k = one << 16, mone = 0u - one, two = one + one, c25 = one << 25;
     auto step = [&](float row_max, int i) {
         uint32_t key, xh;
         asm("mad.lo.u32 %0, %1, %2, 65535;" : "=r"(key) : "r"(st.x), "r"(c64k));      // (x << 16) | 0xffff
@@ -938,20 +1170,16 @@ __device__ __forceinline__ uint32_t rans_decode_stream(const uint8_t* cont, uint
         uint32_t a = p1 ? a0h : a0;
         const uint32_t m = p1 ? r_hi : r_lo;
         asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
-            : "+r"(a) : "r"(m), "r"(key), "r"(one), "n"(2 * H));
-#pragma unroll
-        for (uint32_t st4 = H; st4 >= 4u; st4 >>= 1) {                           // byte steps H, H/2, .., 4 = entries H/4 .. 1
-            uint32_t ev;
-            if (st4 == 16u) asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(ev) : "r"(a));
-            else if (st4 == 8u) asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(ev) : "r"(a));
-            else asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(ev) : "r"(a));
-            asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
-                : "+r"(a) : "r"(ev), "r"(key), "r"(one), "r"(st4));
-        }
-        uint32_t e;
+            : "+r"(a) : "r"(m), "r"(key), "r"(one), "n"(kPitch * (H / 2)));
+        if constexpr (H >= 16) rans_search_step<4, kPitch>(a, key, one);         // entries H/4 .. 1 further on
+        rans_search_step<2, kPitch>(a, key, one);
+        rans_search_step<1, kPitch>(a, key, one);
+        uint32_t e, la;
         float lv;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lv) : "r"(a + lut_rel));
+        if constexpr (TR) asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(la) : "r"(a - a0), "r"(c25), "r"(lut_a));   // lut_a + 4 * symbol
+        else la = a + lut_rel;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lv) : "r"(la));
         // x = freq * (x >> 16) + slot - start
         uint32_t dl;
         asm("mul.hi.u32 %0, %1, %2;" : "=r"(dl) : "r"(key - e), "r"(c64k));
@@ -980,10 +1208,12 @@ __device__ __forceinline__ uint32_t rans_decode_stream(const uint8_t* cont, uint
         }
     };
     int i = 0;
-    for (; i + 4 <= gt; i += 4) {
-        const float4 m4 = *reinterpret_cast<const float4*>(mx + i);            // four row maxima per LDS.128
-        step(m4.x, i); step(m4.y, i + 1); step(m4.z, i + 2); step(m4.w, i + 3);
+#pragma unroll 1
+    for (; i + 4 <= gt; i += 4) {                                               // 4 symbols per trip: the body is ~150
+        const float4 m4 = *reinterpret_cast<const float4*>(mx + i);            // instructions, it must stay in the
+        step(m4.x, i); step(m4.y, i + 1); step(m4.z, i + 2); step(m4.w, i + 3);   // instruction cache next to its twin
     }
+#pragma unroll 1
     for (; i < gt; ++i) step(mx[i], i);
     return st.x;
 }
@@ -993,7 +1223,7 @@ __device__ __forceinline__ uint32_t rans_decode_stream(const uint8_t* cont, uint
 // dequantisation LUT live in shared memory (~18 KB per CTA), so many CTAs stay resident and hide the serial latency of
 // each stream's coder.  Symbols are dequantised and stored straight into the destination layout (no uint8 / fp32
 // intermediates in HBM).  CODER selects the payload format (container version 1: arithmetic coder, 2: rANS).
-template <int OUT_DT, bool PAGED, int CODER>
+template <int OUT_DT, bool PAGED, int CODER, bool TR>
 __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* tab = smem;                                                            // CT * 33 words (rows of 33, odd)
@@ -1030,21 +1260,57 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
 
     // stage the per-stream tables (one contiguous run of ncols * 33 halfwords in the container), row maxima, LUT
     const uint16_t* cdf_src = reinterpret_cast<const uint16_t*>(dc.base + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
-    for (int e = tid; e < ncols * kLp; e += CT) {
-        const uint32_t i = (uint32_t)e % (uint32_t)kLp;
-        const uint32_t c0 = __ldg(cdf_src + e);
-        if constexpr (CODER == CODER_RANS) {
-            // (cdf[i] << 16) | freq(i); cdf[32] is stored as 0 and stands for 65536; entry 32 is never searched
-            const uint32_t c1 = i < 31u ? (uint32_t)__ldg(cdf_src + e + 1) : 0x10000u;
-            tab[e] = i < 32u ? rans_table_entry(c0, c1) : 0xFFFFFFFFu;
-        } else {
-            tab[e] = dec_table_entry(i, c0);
-        }
-    }
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(dc.base + lo.off_maxes) + (int64_t)nl * dc.t + tok0;
-    for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
     const float cq = P.pt.maxq[nl];
-    if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
+    if constexpr (CODER == CODER_RANS && TR) {
+        // TRANSPOSED table: entry i of stream tid at tab[i * CT + tid], entry = (cdf[i] << 16) | freq(i).  Built in two
+        // steps through a staging copy of the raw CDF rows that lives in the table's own upper half (bytes 8448..16895):
+        // coalesced global -> staging; every thread turns ITS row (33 halfwords, stride 33: conflict-free) into column
+        // entries 0..15 (bytes 0..8191, clear of the staging); entries 16..31 -- needed by 32-bin planes only -- go
+        // through registers so that they may overwrite the staging once everybody has read it.
+        uint16_t* stg = reinterpret_cast<uint16_t*>(smem) + (CT * kLp);            // second half of the CT*kLp words
+        for (int e = tid; e < ncols * kLp; e += CT) stg[e] = __ldg(cdf_src + e);
+        for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
+        if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
+        __syncthreads();
+        const uint16_t* my = stg + tid * kLp;
+        if (active) {
+            uint32_t c0 = my[0];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t c1 = my[i + 1];
+                tab[i * CT + tid] = rans_table_entry(c0, c1);
+                c0 = c1;
+            }
+        }
+        if (cq > 7.0f) {                                                            // uniform per CTA
+            uint32_t cv[17];
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cv[i] = my[16 + i];
+                cv[16] = 0x10000u;                                                   // cdf[32] is stored as 0 and means 65536
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tab[(16 + i) * CT + tid] = rans_table_entry(cv[i], cv[i + 1]);
+            }
+        }
+    } else {
+        for (int e = tid; e < ncols * kLp; e += CT) {
+            const uint32_t i = (uint32_t)e % (uint32_t)kLp;
+            const uint32_t c0 = __ldg(cdf_src + e);
+            if constexpr (CODER == CODER_RANS) {
+                // (cdf[i] << 16) | freq(i); cdf[32] is stored as 0 and stands for 65536; entry 32 is never searched
+                const uint32_t c1 = i < 31u ? (uint32_t)__ldg(cdf_src + e + 1) : 0x10000u;
+                tab[e] = i < 32u ? rans_table_entry(c0, c1) : 0xFFFFFFFFu;
+            } else {
+                tab[e] = dec_table_entry(i, c0);
+            }
+        }
+        for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
+        if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
+    }
     __syncthreads();
 
     if (!active) return;
@@ -1057,8 +1323,9 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     if constexpr (CODER == CODER_RANS) {
         uint32_t xf;
         const uint32_t one = min((uint32_t)P.n_chunks, 1u);      // 1, but opaque to the compiler (see rans_decode_stream)
-        if (cq <= 7.0f) xf = rans_decode_stream<OUT_DT, 4, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots, one);
-        else xf = rans_decode_stream<OUT_DT, 5, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots, one);
+        const uint32_t* pk = TR ? tab + tid : tab + tid * kLp;
+        if (cq <= 7.0f) xf = rans_decode_stream<OUT_DT, 4, PAGED, TR>(dc.base, my_off, pk, lut, mx, dst, (uint32_t)P.sT, gt, slots, one);
+        else xf = rans_decode_stream<OUT_DT, 5, PAGED, TR>(dc.base, my_off, pk, lut, mx, dst, (uint32_t)P.sT, gt, slots, one);
         bad |= xf != kRansLow ? 1u : 0u;
     } else {
         if (cq <= 7.0f) decode_stream<OUT_DT, 4, PAGED>(dc.base, my_off, erow, lut, mx, dst, (uint32_t)P.sT, gt, slots);   // <= 16 bins: symbols 0..14
@@ -1161,6 +1428,7 @@ int b200kv_container_layout(int32_t L, int32_t H, int32_t D, int32_t ntokens, b2
 int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks,
                                       int32_t coder) {
     if (L <= 0 || H <= 0 || D <= 0 || chunk_tokens <= 0 || n_chunks <= 0) return -2;
+    coder &= 0xff;
     if (coder != CODER_AC && coder != CODER_RANS) return -2;
     const int64_t G = (chunk_tokens + kGroup - 1) / kGroup;
     const int64_t n_tiles = (int64_t)n_chunks * G * 2 * L * tiles_per_plane(H * D);
@@ -1183,6 +1451,8 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     EncParams P;
     B2_REQUIRE(key_bins && value_bins, "bins are NULL");
+    const bool hint_tma = (coder & B200KV_ENCODE_HINT_HIGH_ENTROPY) != 0;
+    coder &= 0xff;
     B2_REQUIRE(coder == CODER_AC || coder == CODER_RANS, "coder must be B200KV_CODER_AC or B200KV_CODER_RANS");
     P.coder = coder;
     if (int rc = make_plane_table(kv, key_bins, value_bins, &P.pt)) return rc;
@@ -1258,7 +1528,29 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
         if (P.dtype == B200KV_DT_BF16) { if (paged) B2_LAUNCH_ENC(FUSED, 0, true, SMEM); else B2_LAUNCH_ENC(FUSED, 0, false, SMEM); } \
         else { if (paged) B2_LAUNCH_ENC(FUSED, 1, true, SMEM); else B2_LAUNCH_ENC(FUSED, 1, false, SMEM); } \
     } while (0)
-    if (fused) {
+    // TMA-staged kernel (encode_tma_kernel): rANS, fused mode, tiles of exactly CT channels that are contiguous in every
+    // token row and 16-byte aligned.  B200KV_ENCODE_PATH=legacy forces the kernel above (A/B measurements).
+    // Measured (profiles/r2_encode_variants.json): the TMA-staged kernel is flat in the data's entropy (4.4 .. 5.2 ms per
+    // 8192-token block), the register-staged one is faster below ~2.7 payload bits per symbol (3.75 ms at 0.6) and slower
+    // above (6.2 ms at 4.1): the caller says which regime it expects (B200KV_ENCODE_HINT_HIGH_ENTROPY, e.g. from the
+    // sizes of the previous call).  B200KV_ENCODE_PATH=legacy|tma overrides (A/B measurements).
+    bool tma = hint_tma;
+    if (const char* e = getenv("B200KV_ENCODE_PATH")) tma = e[0] == 't';
+    tma = tma && fused && coder == CODER_RANS && P.C % CT == 0 && (kv->sH == kv->D || kv->D % CT == 0) &&
+          kv->sT % 8 == 0 && kv->sH % 8 == 0;
+    for (int nl = 0; nl < 2 * P.L && tma; ++nl) tma = (reinterpret_cast<uintptr_t>(P.pt.p[nl]) & 15) == 0;
+    if (tma) {
+        ProfScope prof(kProfEncode, stream);
+#define B2_LAUNCH_TMA(DT, PAGED)                                                                                       \
+    do {                                                                                                               \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(encode_tma_kernel<DT, PAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           kEncTmaSmem));                                                              \
+        encode_tma_kernel<DT, PAGED><<<(unsigned)n_tiles, CT, kEncTmaSmem, stream>>>(P);                               \
+    } while (0)
+        if (P.dtype == B200KV_DT_BF16) { if (paged) B2_LAUNCH_TMA(0, true); else B2_LAUNCH_TMA(0, false); }
+        else { if (paged) B2_LAUNCH_TMA(1, true); else B2_LAUNCH_TMA(1, false); }
+#undef B2_LAUNCH_TMA
+    } else if (fused) {
         ProfScope prof(kProfEncode, stream);
         B2_LAUNCH_ENC2(true, smem_fused);
     } else {
@@ -1330,6 +1622,20 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
     const int64_t Gmax = (tmax + kGroup - 1) / kGroup;
     const int64_t tiles_max = Gmax * 2 * P.L * P.tpp;
     B2_REQUIRE(tiles_max < (1ll << 31) && n_chunks <= 65535, "too many tiles / chunks in one call");
+    // table layout of the rANS decoder: the conflict-free (transposed) one pays off above ~3.6 payload bits per symbol
+    // (measured: 3.28 / 3.60 ms at 0.6 bits, 4.04 / 3.72 ms at 4.1 bits, row-major / transposed); the containers say how
+    // many bits they hold.  B200KV_DECODE_TABLE=rows|transposed overrides (measurement knob).
+    bool transposed = false;
+    {
+        double bits = 0.0, syms = 0.0;
+        for (int j = 0; j < n_chunks; ++j) {
+            const Layout lj = make_layout(P.L, P.C, ntokens[j]);
+            bits += 8.0 * (double)(total_bytes[j] - lj.off_payload);
+            syms += 2.0 * P.L * (double)P.C * ntokens[j];
+        }
+        transposed = bits > 3.6 * syms && bits < 6.0 * syms;       // a slot bound instead of a size says nothing: rows
+        if (const char* e = getenv("B200KV_DECODE_TABLE")) transposed = e[0] == 't';
+    }
     P.tiles_max = (int32_t)tiles_max;
     size_t off_tb;
     const size_t need = dec_ws_layout(tiles_max, n_chunks, &off_tb);
@@ -1372,16 +1678,17 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
     const size_t smem = (size_t)(CT * kLp + kGroup + 32) * 4;
     dim3 grid((unsigned)tiles_max, (unsigned)n_chunks);
     ProfScope prof(kProfDecode, stream);
-#define B2_LAUNCH_DEC1(DT, PAGED, CODER)                                                                               \
+#define B2_LAUNCH_DEC1(DT, PAGED, CODER, TR)                                                                           \
     do {                                                                                                               \
-        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<DT, PAGED, CODER>,                                            \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<DT, PAGED, CODER, TR>,                                        \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
-        decode_kernel<DT, PAGED, CODER><<<grid, CT, smem, stream>>>(P);                                                \
+        decode_kernel<DT, PAGED, CODER, TR><<<grid, CT, smem, stream>>>(P);                                            \
     } while (0)
 #define B2_LAUNCH_DEC(DT, PAGED)                                                                                       \
     do {                                                                                                               \
-        if (coder == CODER_RANS) B2_LAUNCH_DEC1(DT, PAGED, CODER_RANS);                                                \
-        else B2_LAUNCH_DEC1(DT, PAGED, CODER_AC);                                                                      \
+        if (coder == CODER_RANS && transposed) B2_LAUNCH_DEC1(DT, PAGED, CODER_RANS, true);                            \
+        else if (coder == CODER_RANS) B2_LAUNCH_DEC1(DT, PAGED, CODER_RANS, false);                                    \
+        else B2_LAUNCH_DEC1(DT, PAGED, CODER_AC, false);                                                               \
     } while (0)
     if (P.out_dtype == B200KV_DT_BF16) { if (P.slot_map) B2_LAUNCH_DEC(0, true); else B2_LAUNCH_DEC(0, false); }
     else { if (P.slot_map) B2_LAUNCH_DEC(1, true); else B2_LAUNCH_DEC(1, false); }

@@ -485,3 +485,39 @@ def test_torch_serde_gpu_lossless():
     t = torch.randn(4, 2, 256, 4, 64, device="cuda").to(torch.bfloat16)     # BASELINE config 1 shape
     back = TorchDeserializer().from_bytes(TorchSerializer().to_bytes(t))
     assert back.device.type == "cpu" and torch.equal(back, t.cpu())
+
+
+@pytest.mark.parametrize("kind", ["peaked", "uniform"])
+def test_kernel_variants_agree(kind, monkeypatch):
+    """the library's measurement knobs select kernel variants that must be interchangeable: the TMA-staged and the
+    register-staged fused encoder produce byte-identical containers, the row-major and the transposed decoder table
+    produce identical KV (the product picks by eligibility / by the containers' bits per symbol)"""
+    from lmcache_b200.codec import CacheGenCodec, KvView
+    L, H, D, T, cs = 8, 4, 128, 700, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    if kind == "peaked":
+        kv = (torch.randn((L, 2, T, H, D), device="cuda", generator=g) * 0.05)
+        kv[:, :, :, :, 0] = 4.0                                        # one loud channel pins every row's maximum
+    else:
+        kv = torch.rand((L, 2, T, H, D), device="cuda", generator=g) * 2 - 1
+    kv = kv.to(torch.bfloat16)
+    codec = CacheGenCodec(MODEL, coder="rans")
+    view = KvView.from_blob(kv, "vllm")
+    outs, decs = {}, {}
+    for path in ("tma", "legacy"):
+        monkeypatch.setenv("B200KV_ENCODE_PATH", path)
+        outs[path] = [bytes(b) for b in codec.encode_to_host(view, 0, T, cs)]
+    assert outs["tma"] == outs["legacy"]
+    for table in ("rows", "transposed"):
+        monkeypatch.setenv("B200KV_DECODE_TABLE", table)
+        out = torch.zeros_like(kv)
+        codec.decode(outs["tma"], KvView.from_blob(out, "vllm"), [j * cs for j in range(len(outs["tma"]))])
+        torch.cuda.synchronize()
+        assert codec.decode_status() == [0] * len(outs["tma"])
+        decs[table] = out
+    assert torch.equal(decs["rows"].view(torch.int16), decs["transposed"].view(torch.int16))
+    kb, vb = O.make_bins(MODEL)
+    bits = _tensor_bits(kv).reshape(L, 2, T, H * D)
+    want = np.concatenate([O.decode_chunk(O.encode_chunk(bits[:, :, j * cs:min(T, (j + 1) * cs)], 0, kb, vb, O.CODER_RANS), 0, kb, vb, 0)
+                           for j in range(len(outs["tma"]))], axis=2)
+    assert np.array_equal(_tensor_bits(decs["rows"]).reshape(L, 2, T, H * D), want)
