@@ -124,6 +124,15 @@ class LMCacheEngine:
             chunks.append(buf[j * stride_elems: j * stride_elems + per_tok * t].view(self._chunk_shape(view, t, fmt)))
         return chunks
 
+    def _pack_chunks_torch(self, kv: KVCache, tok_begin: int, fmt: str) -> List[torch.Tensor]:
+        """_tuple_kv_to_blob + _slice_kv_at with torch ops (cache_engine.py:98-161), for dtypes the kernels do not move"""
+        k = torch.stack([x[0] for x in kv])
+        v = torch.stack([x[1] for x in kv])
+        blob = torch.stack((k, v)).permute(1, 0, 2, 3, 4)
+        tdim = 2 if fmt == "vllm" else 3
+        blob = blob.narrow(tdim, tok_begin, blob.shape[tdim] - tok_begin)
+        return [c.contiguous() for c in torch.split(blob, self.chunk_size, dim=tdim)]
+
     @staticmethod
     def _as_cuda_kv(kv_tensors_raw: KVCache) -> KVCache:
         if kv_tensors_raw[0][0].is_cuda:
@@ -158,9 +167,19 @@ class LMCacheEngine:
                     break
         n_chunks = 0
         if start_chunk_idx < len(chunk_hashes):
-            view = KvView.from_tuple(self._as_cuda_kv(kv_tensors_raw), fmt)
-            self._geom = (view.L, view.H, view.D, view.dtype)
             keys = [self._make_key(h, fmt) for h in chunk_hashes[start_chunk_idx:]]
+            kv_cuda = self._as_cuda_kv(kv_tensors_raw)
+            if kv_cuda[0][0].dtype not in (torch.bfloat16, torch.float16):
+                # the native pack / codec kernels move 16-bit KV; any other dtype (the reference's local and torch-serde
+                # paths accept every dtype) takes the reference's own blob ops on the GPU (cache_engine.py:98-161)
+                chunks = self._pack_chunks_torch(kv_cuda, start_chunk_idx * self.chunk_size, fmt)
+                end_make_chunks = time.perf_counter()
+                n_chunks = self.engine_.batched_put(zip(keys, chunks), blocking=blocking)
+                logger.info(f"Stored/updated {n_chunks} chunks, total time {time.perf_counter() - start_time:.2f}s, "
+                            f"make chunks time {end_make_chunks - start_time:.2f}s")
+                return
+            view = KvView.from_tuple(kv_cuda, fmt)
+            self._geom = (view.L, view.H, view.D, view.dtype)
             if self._fast_path():
                 # B200-native path: the backend consumes the caller's 2L tensors directly (batched encode / one gather)
                 end_make_chunks = time.perf_counter()
@@ -195,8 +214,11 @@ class LMCacheEngine:
         if fmt not in ("vllm", "huggingface"):
             raise ValueError(f"Invalid format: {fmt}")
         chunk_hashes = self._prefix_hash(tokens, num_skip_chunk)
-        if self._fast_path() and len(chunk_hashes) > 0:
-            return self._retrieve_into_blob(tokens, chunk_hashes, num_skip_tok, num_skip_chunk, ret_mask, fmt, st)
+        if self._fast_path() and len(chunk_hashes) > 0 and not getattr(self, "_wide_dtype", False):
+            try:
+                return self._retrieve_into_blob(tokens, chunk_hashes, num_skip_tok, num_skip_chunk, ret_mask, fmt, st)
+            except TypeError:
+                self._wide_dtype = True      # chunks of a dtype the kernels do not move: per-chunk path from now on
         retrieved: List[torch.Tensor] = []
         for chunk in self.engine_.batched_get(self._make_key(h, fmt) for h in chunk_hashes):
             if chunk is None:
@@ -347,7 +369,7 @@ class LMCacheEngine:
             self._geom = geom
         L, H, D, dtype = geom
         od = getattr(self.engine_, "out_dtype", None) or getattr(getattr(self.engine_, "deserializer", None), "out_dtype", None)
-        if od is not None:
+        if od is not None and od() is not None:
             dtype = od()
         n_tok_max = len(tokens) - num_skip_chunk * self.chunk_size
         shape = (L, 2, n_tok_max, H, D) if fmt == "vllm" else (L, 2, H, n_tok_max, D)

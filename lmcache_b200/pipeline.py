@@ -222,3 +222,77 @@ class UploadRing:
         ev = torch.cuda.Event()
         ev.record(stream)
         self._busy[i] = ev
+
+
+def fetch_decode(codec: CacheGenCodec, upload: UploadRing, futures: Sequence, dst: KvView, dst_tok0: int, chunk_size: int,
+                 inflight: list, on_more: Optional[Callable[[int], None]] = None, wave: Optional[int] = None) -> int:
+    """Consume container fetches IN ORDER -- futures[i].result() is (slab block, nbytes) or None for a miss; an entry may
+    also be such a tuple directly -- and, wave by wave, upload the containers on the copy stream and decode them into
+    `dst` on the current stream (chunk i lands at token dst_tok0 + i * chunk_size).  Fetches of later chunks keep running
+    in their pool while earlier waves upload and decode: network / disk || H2D || decode.  Stops at the first miss or
+    damaged / mismatching container; everything fetched past that point is released.  Blocks of uploaded waves are
+    appended to `inflight` as (event, [blocks]) for the caller to free once the event has completed.
+    `on_more(i)` is called before chunk i is awaited (lets the caller keep a window of fetches in flight)."""
+    import ctypes
+
+    from lmcache_b200.codec import parse_header
+    W = wave or wave_chunks_default()
+    lib = N.lib()
+    n_done = 0
+    wave_items: list = []                  # (block, nbytes, header, chunk index)
+    with torch.cuda.device(dst.device):
+        cur = torch.cuda.current_stream()
+
+        def flush():
+            if not wave_items:
+                return
+            offs, o = [], 0
+            for _, n, _, _ in wave_items:
+                offs.append(o)
+                o += (n + 15) & ~15
+            slot, buf = upload.next_slot(o)
+            for (blk, n, _, _), off in zip(wave_items, offs):
+                N.check(lib.b200kv_copy_async(ctypes.c_void_p(buf.data_ptr() + off), ctypes.c_void_p(blk.host_ptr), n,
+                                              upload.copy_stream.cuda_stream), "copy_async")
+            ev = torch.cuda.Event()
+            ev.record(upload.copy_stream)
+            inflight.append((ev, [w[0] for w in wave_items]))
+            cur.wait_event(ev)
+            h0 = wave_items[0][2]
+            codec.decode_raw(buf.data_ptr(), buf.numel(), offs, [w[1] for w in wave_items],
+                             [int(w[2].ntokens) for w in wave_items], dst,
+                             [dst_tok0 + w[3] * chunk_size for w in wave_items], int(h0.max_dtype), int(h0.version) - 1, cur)
+            upload.mark_read(slot, cur)
+            wave_items.clear()
+
+        stop_at = len(futures)
+        for i in range(len(futures)):
+            if on_more is not None:
+                on_more(i)
+            f = futures[i]
+            got = f.result() if hasattr(f, "result") else f
+            if got is None:
+                stop_at = i
+                break
+            blk, n = got
+            try:
+                hd = parse_header(blk.view()[:n])
+                ok = (hd.L, hd.H, hd.D) == (dst.L, dst.H, dst.D) and \
+                    dst_tok0 + i * chunk_size + hd.ntokens <= dst.ntokens and \
+                    (not wave_items or (hd.max_dtype, hd.version) == (wave_items[0][2].max_dtype, wave_items[0][2].version))
+            except ValueError:
+                ok = False                      # damaged container: a miss, not an error
+            if not ok:
+                blk.free()
+                stop_at = i
+                break
+            wave_items.append((blk, n, hd, i))
+            n_done += 1
+            if len(wave_items) == W:
+                flush()
+        flush()
+    for f in futures[stop_at + 1:]:              # fetches past the first miss: let them finish, drop their blocks
+        r = f.result() if hasattr(f, "result") else f
+        if r is not None:
+            r[0].free()
+    return n_done

@@ -15,11 +15,12 @@ def CreateStorageBackend(config: LMCacheEngineConfig, metadata: LMCacheEngineMet
         if local in ("cpu", "cuda"):
             from lmcache_b200.storage_backend.local_backend import LMCLocalBackend
             return LMCLocalBackend(config)
-        # disk tier (LMCLocalDiskBackend, local_backend.py:163-310) is file I/O, not GPU path: SURVEY 8(f) "next" row 4
-        raise ValueError(f"Invalid configuration: local disk backend '{local}' is not provided by lmcache_b200")
+        # a directory: the disk tier (LMCLocalDiskBackend, local_backend.py:163-310), here with CacheGen containers
+        from lmcache_b200.storage_backend.local_backend import LMCLocalDiskBackend
+        return LMCLocalDiskBackend(config, metadata)
     if isinstance(local, str) and isinstance(remote, str):
-        # hybrid = write-through composition of local + remote (hybrid_backend.py): outside the rebuilt hot path
-        raise ValueError("Invalid configuration: hybrid (local + remote) backend is not provided by lmcache_b200")
+        from lmcache_b200.storage_backend.hybrid_backend import LMCHybridBackend
+        return LMCHybridBackend(config, metadata)
     raise ValueError(f"Invalid configuration: {config}")
 
 

@@ -32,6 +32,21 @@ class RemoteBackendEndSignal:
     pass
 
 
+class _LazyFutures:
+    """list view over futures that are submitted on demand: entries past `issued` do not exist yet"""
+
+    def __init__(self, futs, issued):
+        self.futs, self.issued = futs, issued
+
+    def __len__(self):
+        return len(self.futs)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [f for f in self.futs[i] if f is not None]
+        return self.futs[i]
+
+
 class LMCRemoteBackend(LMCBackendInterface):
 
     def __init__(self, config: LMCacheEngineConfig, metadata: LMCacheEngineMetadata):
@@ -307,94 +322,35 @@ class LMCRemoteBackend(LMCBackendInterface):
         return len(blobs)
 
     def _get_striped(self, keys, dst, dst_tok0: int, chunk_size: int) -> int:
-        import ctypes
-
         import torch as _t
 
-        from lmcache_b200 import _native as N
-        from lmcache_b200.codec import parse_header
-        from lmcache_b200.pipeline import UploadRing, wave_chunks_default
+        from lmcache_b200.pipeline import UploadRing, fetch_decode, wave_chunks_default
         self._sweep()
-        codec = self.deserializer.codec
         bound = (self.deserializer.container_bound(dst.L, dst.H, dst.D, chunk_size) + 255) & ~255
         ex = self._executor()
         window = max(2 * self._nconn, 2 * wave_chunks_default())       # fetches in flight ahead of the consumer
-        futs = {}
         peek, self._peek = self._peek, None
+        futs: list = [None] * len(keys)
+        issued = [0]
 
-        def want(i):
-            if i < len(keys) and i not in futs:
-                if peek is not None and i == 0 and peek[0] == keys[0]:
-                    futs[i] = None                                    # already in host memory
+        def on_more(i):
+            while issued[0] < min(len(keys), i + window):
+                k = issued[0]
+                if peek is not None and k == 0 and peek[0] == keys[0]:
+                    futs[0] = (peek[1], peek[2])                       # already in host memory (peek_geometry)
                 else:
-                    futs[i] = ex.submit(self._fetch, keys[i], bound)
-        for i in range(min(window, len(keys))):
-            want(i)
-        W = wave_chunks_default()
-        n_done = 0
-        lib = N.lib()
+                    futs[k] = ex.submit(self._fetch, keys[k], bound)
+                issued[0] += 1
+        on_more(0)
+        if peek is not None and not (keys and peek[0] == keys[0]):
+            peek[1].free()
         with _t.cuda.device(dst.device):
             if self._upload is None or self._upload.device != dst.device:
                 self._upload = UploadRing(dst.device)
-            up = self._upload
-            cur = _t.cuda.current_stream()
-            wave = []                   # (block, nbytes, header, chunk index)
-
-            def flush():
-                if not wave:
-                    return
-                offs, o = [], 0
-                for _, n, _, _ in wave:
-                    offs.append(o)
-                    o += (n + 15) & ~15
-                slot, buf = up.next_slot(o)
-                for (blk, n, _, _), off in zip(wave, offs):
-                    N.check(lib.b200kv_copy_async(ctypes.c_void_p(buf.data_ptr() + off), ctypes.c_void_p(blk.host_ptr), n,
-                                                  up.copy_stream.cuda_stream), "copy_async")
-                ev = _t.cuda.Event()
-                ev.record(up.copy_stream)
-                self._inflight.append((ev, [w[0] for w in wave]))
-                cur.wait_event(ev)
-                h0 = wave[0][2]
-                codec.decode_raw(buf.data_ptr(), buf.numel(), offs, [w[1] for w in wave], [int(w[2].ntokens) for w in wave],
-                                 dst, [dst_tok0 + w[3] * chunk_size for w in wave], int(h0.max_dtype), int(h0.version) - 1, cur)
-                up.mark_read(slot, cur)
-                wave.clear()
-
-            miss = False
-            for i in range(len(keys)):
-                want(i + window)
-                f = futs.pop(i)
-                got = (peek[1], peek[2]) if f is None else f.result()
-                if got is None:
-                    miss = True
-                    break
-                blk, n = got
-                try:
-                    hd = parse_header(blk.view()[:n])
-                    ok = (hd.L, hd.H, hd.D) == (dst.L, dst.H, dst.D) and \
-                        dst_tok0 + i * chunk_size + hd.ntokens <= dst.ntokens and \
-                        (not wave or (hd.max_dtype, hd.version) == (wave[0][2].max_dtype, wave[0][2].version))
-                except ValueError:
-                    ok = False                      # damaged container: a miss, not an error
-                if not ok:
-                    blk.free()
-                    miss = True
-                    break
-                wave.append((blk, n, hd, i))
-                n_done += 1
-                if len(wave) == W:
-                    flush()
-            flush()
-        for f in futs.values():                      # fetches past the first miss: let them finish, drop their blocks
-            if f is not None:
-                r = f.result()
-                if r is not None:
-                    r[0].free()
-        if peek is not None and (n_done == 0 or peek[0] != keys[0]):
-            peek[1].free()
-        del miss
-        return n_done
+        # only what has been submitted can be awaited: hand fetch_decode the live list, it asks for more as it goes
+        n = fetch_decode(self.deserializer.codec, self._upload, _LazyFutures(futs, issued), dst, dst_tok0, chunk_size,
+                         self._inflight, on_more)
+        return n
 
     def close(self):
         if self.put_thread is not None and self.put_thread.is_alive():

@@ -469,3 +469,52 @@ def test_engine_paged_store_and_retrieve(backend, lmserver, autorelease):
     # total miss
     m4 = eng.retrieve_paged(generate_tokens(T, "cuda") + 20000, caches3, slots)
     assert int(torch.sum(m4)) == 0
+
+
+# ---------------------------------------------------------------- hybrid backend, wide dtypes
+@pytest.mark.parametrize("serde", ["torch", "cachegen"])
+def test_hybrid_backend_write_through_and_fall_through(serde, lmserver, autorelease):
+    """local + remote (lmcache/storage_backend/hybrid_backend.py): a store lands in both tiers; a second engine whose
+    local tier is empty is served by the remote tier; the first engine is served locally (its remote connection can go)"""
+    import ref_torch
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    from lmcache_b200.storage_backend.hybrid_backend import LMCHybridBackend
+    model = "mistralai/Mistral-7B-Instruct-v0.2"
+    T = 700
+    tokens = generate_tokens(T, "cuda")
+    kv = generate_kv_cache(T, "vllm", "cuda", 8, 2, 128)
+    cfg = LMCacheEngineConfig(256, "cuda", lmserver, serde, False, False)
+    e1 = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", model + serde)))
+    assert isinstance(e1.engine_, LMCHybridBackend)
+    e1.store(tokens, kv)
+    r1, m1 = e1.retrieve(tokens)                                   # local tier: raw, lossless
+    assert int(m1.sum()) == T
+    check_kv_cache_equal(r1, kv, T, "vllm")
+    e2 = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", model + serde)))
+    r2, m2 = e2.retrieve(tokens)                                   # empty local tier: the remote tier answers
+    assert int(m2.sum()) == T
+    if serde == "torch":
+        check_kv_cache_equal(r2, kv, T, "vllm")
+    else:
+        kb, vb = (torch.tensor(b) for b in O.make_bins(model))
+        blob = torch.stack((torch.stack([k for k, _ in kv]), torch.stack([v for _, v in kv]))).permute(1, 0, 2, 3, 4)
+        want = torch.cat([ref_torch.roundtrip(c.contiguous(), kb, vb, "vllm") for c in torch.split(blob, 256, dim=2)], dim=2)
+        got = torch.stack([torch.stack(p) for p in r2])
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
+@pytest.mark.parametrize("backend", ["cuda", "cpu"])
+def test_fp32_kv_takes_the_generic_path(backend, autorelease):
+    """the reference's local tiers accept any dtype (local_backend.py:95-100); the 16-bit kernels do not, so such KV goes
+    through torch's blob ops on the GPU and the per-chunk plugin interface -- still lossless"""
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    T = 600
+    tokens = generate_tokens(T, "cuda")
+    kv = tuple((torch.rand(T, 2, 16, device="cuda"), torch.rand(T, 2, 16, device="cuda")) for _ in range(3))
+    engine = autorelease(LMCacheEngine(LMCacheEngineConfig.from_legacy(chunk_size=256, backend=backend), dumb_metadata()))
+    engine.store(tokens, kv)
+    r, m = engine.retrieve(torch.cat([tokens, generate_tokens(50, "cuda")]))
+    assert int(m.sum()) == 512 and r[0][0].dtype == torch.float32
+    check_kv_cache_equal(r, kv, 512, "vllm")

@@ -184,3 +184,50 @@ def test_compressed_tier_concurrent_store_and_retrieve(autorelease):
         assert torch.equal(_blob_of(ret).view(torch.int16), want0.view(torch.int16))
     th.join()
     assert not errs
+
+
+def test_disk_tier_store_restart_retrieve(tmp_path, autorelease):
+    """local_device = file://<dir>/ : chunks are B2KV container files; a second engine started on the same directory (a
+    restart) rebuilds the index from the file headers and serves the chunks; damaged and foreign files are ignored."""
+    import os
+
+    from lmcache_b200.cache_engine import LMCacheEngine
+    from lmcache_b200.config import LMCacheEngineConfig
+    from lmcache_b200.storage_backend.local_backend import LMCLocalDiskBackend
+    cs, T = 256, 1400
+    d = str(tmp_path / "kvdisk") + "/"
+    cfg = LMCacheEngineConfig.from_legacy(chunk_size=cs, backend="file://" + d)
+    assert cfg.local_device == d
+    tokens = torch.randint(0, 32000, (T,), device="cuda")
+    kv = _kv(T, "vllm", seed=8)
+    want = _want(kv, "vllm", cs, T)
+    engine = LMCacheEngine(cfg, _meta())
+    assert isinstance(engine.engine_, LMCLocalDiskBackend)
+    engine.store(tokens, kv, blocking=False)
+    ret, mask = engine.retrieve(tokens)                       # read-your-writes: waits for the files
+    assert int(mask.sum()) == T
+    assert torch.equal(_blob_of(ret).view(torch.int16), want.view(torch.int16))
+    files = sorted(f for f in os.listdir(d) if f.endswith(".b2kv"))
+    assert len(files) == 6 and not [f for f in os.listdir(d) if f.endswith(".tmp")]
+    raw = sum(k.numel() * 2 * 2 for k, _ in kv)
+    assert sum(os.path.getsize(d + f) for f in files) < 0.75 * raw          # containers, not raw blobs
+    engine.close()
+    # restart: damage one file (truncate), drop a foreign file in
+    victim = d + files[3]
+    with open(victim, "r+b") as f:
+        f.truncate(os.path.getsize(victim) // 2)
+    open(d + "notes.b2kv", "wb").write(b"not a container")
+    engine2 = autorelease(LMCacheEngine(cfg, _meta()))
+    assert len(engine2.engine_.dict) == 5
+    ret, mask = engine2.retrieve(tokens)
+    torch.cuda.synchronize()
+    # chunks are matched front to back: everything before the damaged chunk comes back, nothing after it
+    hashes = engine2._prefix_hash(tokens)
+    bad = [i for i, h in enumerate(hashes) if engine2.engine_._key_to_path(engine2._make_key(h, "vllm")) == victim][0]
+    assert int(mask.sum()) == bad * cs
+    assert torch.equal(_blob_of(ret).view(torch.int16), want[:, :, :bad * cs].contiguous().view(torch.int16))
+    # storing again repairs the cache (skip_existing stops at the damaged chunk and rewrites from there)
+    engine2.store(tokens, kv)
+    ret, mask = engine2.retrieve(tokens)
+    assert int(mask.sum()) == T
+    assert torch.equal(_blob_of(ret).view(torch.int16), want.view(torch.int16))
