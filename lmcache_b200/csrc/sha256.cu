@@ -112,38 +112,23 @@ __global__ void __launch_bounds__(128) sha256_expand_kernel(ShaParams P) {
 }
 
 // 64 rounds over precomputed (W + K); state in registers, variables renamed instead of rotated.
-// One chain is one thread, and every instruction of a round -- three funnel shifts + one LOP3 per Sigma, Ch, Maj, four
-// adds -- is an integer-ALU-pipe instruction (one warp instruction per 2 cycles per SM sub-partition): 13 of them put a
-// floor of 26 cycles under a round whatever the dependencies do (measured in round 1: 42).  Half of the rotations are
-// therefore taken off that pipe: x * 2^(32-n) as a 64-bit product is (x >> n) : (x << (32-n)), the two halves of
-// rotr(x, n), and since they do not overlap their SUM is the rotation -- one IMAD.WIDE and one IMAD.IADD, both FMA-pipe
-// instructions.  The multipliers come from a kernel parameter (`one`), otherwise ptxas turns the products back into
-// shifts.  Per round: 3 rotations stay funnel shifts, 3 are multiplied; with the adds split likewise that is ~9 ALU and
-// ~8 FMA instructions, i.e. a floor of ~18 cycles per round instead of 26.
-struct RotK {
-    uint32_t k7, k19, k10;       // 2^(32-25); 2^(32-13), 2^(32-22)
-};
-__device__ __forceinline__ uint32_t rotr_mul(uint32_t x, uint32_t k) {
-    uint32_t r;
-    asm("{\n\t.reg .b64 p;\n\t.reg .b32 lo, hi;\n\tmul.wide.u32 p, %1, %2;\n\tmov.b64 {lo, hi}, p;\n\tmad.lo.u32 %0, lo, 1, hi;\n\t}"
-        : "=r"(r) : "r"(x), "r"(k));
-    return r;
-}
-__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
+// One chain is one thread.  Every instruction of a round -- three funnel shifts + one LOP3 per Sigma, Ch, Maj, four adds --
+// is an integer-ALU-pipe instruction (one warp instruction per 2 cycles per SM sub-partition): 13 of them put a floor of
+// 26 cycles under a round; measured 42 (a single warp cannot hide its own dependency stalls).  Round 2 tried to take half
+// of the rotations off that pipe -- x * 2^(32-n) as a 64-bit product is (x >> n) : (x << (32-n)), whose halves sum to
+// rotr(x, n): one IMAD.WIDE + one IMAD.IADD on the FMA pipe -- and measured it SLOWER (1.74 ms vs 1.50 ms for 8192 tokens):
+// with one warp the round is bound by the latency of its dependency chain, and the multiply path is longer than a funnel
+// shift.  Kept: the plain form below.
 #define B2_SHA_ROUND(a, b, c, d, e, f, g, h, wk)                                              \
     {                                                                                          \
-        const uint32_t t1_ = (h) + xor3(rotr(e, 6), rotr(e, 11), rotr_mul(e, rk.k7)) + (((e) & (f)) ^ (~(e) & (g))) + (wk); \
-        const uint32_t t2_ = xor3(rotr(a, 2), rotr_mul(a, rk.k19), rotr_mul(a, rk.k10)) + (((a) & (b)) ^ ((a) & (c)) ^ ((b) & (c))); \
+        const uint32_t t1_ = (h) + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + (((e) & (f)) ^ (~(e) & (g))) + (wk); \
+        const uint32_t t2_ = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + (((a) & (b)) ^ ((a) & (c)) ^ ((b) & (c))); \
         (d) += t1_;                                                                            \
         (h) = t1_ + t2_;                                                                       \
     }
 
 // 64 rounds over a block's (W + K) held in registers
-__device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q)[16], const RotK& rk) {
+__device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q)[16]) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
@@ -174,8 +159,6 @@ __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
     int64_t gb = P.seq_block0[s];
     uint32_t dig[8];
     bool first = true;
-    const uint32_t one = P.n_seq > 0 ? 1u : 0u;          // 1, but not a constant ptxas can see through
-    const RotK rk{one << 7, one << 19, one << 10};
     for (int64_t tb = t0; tb < t1; tb += P.chunk_size, ++slot) {
         const int64_t cnt = (t1 - tb) < P.chunk_size ? (t1 - tb) : P.chunk_size;
         const uint32_t ntail = ((uint32_t)(cnt * P.elem_size) + 9u + 63u) / 64u;
@@ -209,7 +192,7 @@ __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
             for (int i = 0; i < 16; ++i)
                 q[i] = make_uint4(w[4 * i] + kK[4 * i], w[4 * i + 1] + kK[4 * i + 1], w[4 * i + 2] + kK[4 * i + 2],
                                   w[4 * i + 3] + kK[4 * i + 3]);
-            compress_regs(st, q, rk);
+            compress_regs(st, q);
         }
         // stream the precomputed blocks: the next block's 16 loads are in flight while this block's rounds run
         const uint4* wk4 = reinterpret_cast<const uint4*>(P.scratch + gb * 64);
@@ -217,7 +200,7 @@ __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
         load_block(cur, wk4);
         for (uint32_t k = 0; k < ntail; ++k) {
             if (k + 1 < ntail) load_block(nxt, wk4 + 16 * (k + 1));
-            compress_regs(st, cur, rk);
+            compress_regs(st, cur);
 #pragma unroll
             for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }

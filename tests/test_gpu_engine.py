@@ -485,13 +485,13 @@ def test_hybrid_backend_write_through_and_fall_through(serde, lmserver, autorele
     tokens = generate_tokens(T, "cuda")
     kv = generate_kv_cache(T, "vllm", "cuda", 8, 2, 128)
     cfg = LMCacheEngineConfig(256, "cuda", lmserver, serde, False, False)
-    e1 = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", model + serde)))
+    e1 = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", model)))
     assert isinstance(e1.engine_, LMCHybridBackend)
     e1.store(tokens, kv)
     r1, m1 = e1.retrieve(tokens)                                   # local tier: raw, lossless
     assert int(m1.sum()) == T
     check_kv_cache_equal(r1, kv, T, "vllm")
-    e2 = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", model + serde)))
+    e2 = autorelease(LMCacheEngine(cfg, dumb_metadata("vllm", model)))
     r2, m2 = e2.retrieve(tokens)                                   # empty local tier: the remote tier answers
     assert int(m2.sum()) == T
     if serde == "torch":
