@@ -55,7 +55,8 @@ def parse_args():
     ap.add_argument("--wave", type=int, default=8, help="chunks per wave of the device-timed step")
     ap.add_argument("--no-sweep", action="store_true", help="skip config.entropy_sweep")
     ap.add_argument("--data", default="kv8d", choices=list(DATA_KINDS), help="synthetic KV distribution (kv8d = SURVEY 8d, the headline)")
-    ap.add_argument("--coder", default="rans", choices=["rans", "ac"], help="payload coder: rans = container v2 (default), ac = v1")
+    ap.add_argument("--coder", default="rans_compact", choices=["rans_compact", "rans", "ac"],
+                    help="container: rans_compact = v3 (default: rANS + symbol counts), rans = v2 (rANS + CDF rows), ac = v1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -334,7 +335,7 @@ def main():
     W = max(1, min(args.wave, n_chunks))
     staging = torch.empty(stride * W + N.READ_SLACK, dtype=torch.uint8, device=dev)      # ONE wave, reused in stream order
     stream = torch.cuda.current_stream()
-    ws_enc = lib.b200kv_encode_workspace_bytes(L, H, D, cs, W, codec.coder)
+    ws_enc = lib.b200kv_encode_workspace_bytes(L, H, D, cs, W, codec.coder_for(cs))
     ws_dec = lib.b200kv_decode_workspace_bytes(L, H, D, cs, W)
 
     def waves():
@@ -351,7 +352,7 @@ def main():
                 collect(ticket, c0, k)
             codec.decode_raw(staging.data_ptr(), staging.numel(), [j * stride for j in range(k)], [stride] * k,
                              [min(cs, T - (c0 + j) * cs) for j in range(k)], out_view, [(c0 + j) * cs for j in range(k)],
-                             N.DT_BF16, codec.coder)
+                             N.DT_BF16, codec.coder_for(cs))
 
     def measure_sizes():
         """container sizes of the resident block; also picks the decoder's table layout the way the product does from
@@ -361,7 +362,7 @@ def main():
         os.environ.pop("B200KV_DECODE_TABLE", None)
         step_device(lambda ticket, c0, k: sizes.extend(ticket.wait().sizes))
         torch.cuda.synchronize()
-        bps = 8.0 * (sum(sizes) - n_chunks * N.container_layout(L, H, D, cs).fixed_bytes) / (raw_bytes / 2)
+        bps = 8.0 * (sum(sizes) - n_chunks * codec.layout(L, H, D, cs).fixed_bytes) / (raw_bytes / 2)
         os.environ["B200KV_DECODE_TABLE"] = "transposed" if bps > 3.6 else "rows"
         return sizes
 
@@ -375,7 +376,7 @@ def main():
                 ticket = codec.encode_async(view, c0 * cs, nt, cs, out=staging)
                 codec.decode_raw(staging.data_ptr(), staging.numel(), [j * stride for j in range(k)], [stride] * k,
                                  [min(cs, T - (c0 + j) * cs) for j in range(k)], out_view,
-                                 [(c0 + j) * cs for j in range(k)], N.DT_BF16, codec.coder)
+                                 [(c0 + j) * cs for j in range(k)], N.DT_BF16, codec.coder_for(cs))
                 buf = (ctypes.c_float * 8)()
                 N.check(lib.b200kv_profile_last(buf, 8))
                 for i, name in enumerate(N.PROFILE_SLOTS):
@@ -401,7 +402,7 @@ def main():
         step_device()
     sizes = measure_sizes()
     container_bytes = sum(sizes)
-    fixed = N.container_layout(L, H, D, cs).fixed_bytes
+    fixed = codec.layout(L, H, D, cs).fixed_bytes
     payload_bytes = container_bytes - n_chunks * fixed
     parity = parity_spot_check(kv, out, cs)
     status_words = codec.decode_status()
@@ -511,7 +512,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"CacheGen encode+decode, {L}L/{H}H/{D}D {T}-token bf16 KV block per GPU, "
                                    f"chunk_size {cs} -> {n_chunks} chunks" + (" (BASELINE configs[1])" if (H, T) == (32, 8192) else " (BASELINE configs[2] shape: 65536-token offload + reload; e2e is that config's metric)" if (H, T) == (32, 65536) else " (side measurement, not a BASELINE shape)"),
-                       "data_kind": args.data, "coder": args.coder + (" (B2KV container v2)" if args.coder == "rans" else " (B2KV container v1)"),
+                       "data_kind": args.data, "coder": args.coder + f" (B2KV container v{codec.coder_for(cs) + 1})",
                        "raw_bytes_per_gpu": raw_bytes, "container_bytes": container_bytes,
                        "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
                        "wave_chunks": W, "device_scratch_bytes": {"staging": staging_bytes(stride, W, N), "encode_workspace": int(ws_enc),

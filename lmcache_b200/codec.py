@@ -194,30 +194,51 @@ def parse_header(buf) -> N.Header:
     hd = N.Header.from_buffer_copy(bytes(mv[:N.HEADER_BYTES]))
     if hd.magic != N.MAGIC:
         raise ValueError("not a B2KV container (bad magic)")
-    if hd.version not in (1, 2):
+    if hd.version not in (1, 2, 3):
         raise ValueError(f"unsupported B2KV version {hd.version}")
     if hd.total_bytes > mv.nbytes:
         raise ValueError("truncated B2KV container")
     if hd.status != 0:
         raise ValueError(f"B2KV container carries encoder error status {hd.status}")
-    check_header(hd)
+    nb = None
+    if hd.version == 3:
+        if not 0 < hd.L <= N.MAX_PLANES // 2 or mv.nbytes < N.HEADER_BYTES + 2 * hd.L:
+            raise ValueError("B2KV header carries an impossible shape")
+        nb = list(bytes(mv[N.HEADER_BYTES:N.HEADER_BYTES + 2 * hd.L]))
+    check_header(hd, nb)
     return hd
 
 
-def check_header(hd: "N.Header") -> None:
+def container_layout_of(hd: "N.Header") -> "N.Layout":
+    """Section offsets of a parsed container (version 3: from the nb map parse_header / check_header attached)."""
+    if hd.version == 3:
+        return N.container_layout(hd.L, hd.H, hd.D, hd.ntokens, N.CODER_RANS_COMPACT, hd.nb[:hd.L], hd.nb[hd.L:])
+    return N.container_layout(hd.L, hd.H, hd.D, hd.ntokens)
+
+
+def check_header(hd: "N.Header", nb: Optional[Sequence[int]] = None) -> None:
     """Structural checks that make a damaged blob a miss (ValueError) instead of bad device addresses: the section
-    offsets follow from (L, H, D, ntokens), so total_bytes must be exactly fixed sections + payload."""
+    offsets follow from (L, H, D, ntokens) -- and, for the compact container (version 3), from its nb map, the 2L bytes
+    after the header, passed as `nb` and attached to the header as `hd.nb` -- so total_bytes must be exactly fixed
+    sections + payload."""
     if not (0 < hd.L <= N.MAX_PLANES // 2 and hd.H > 0 and hd.D > 0 and hd.ntokens > 0):
         raise ValueError("B2KV header carries an impossible shape")
     if hd.max_dtype not in (N.DT_BF16, N.DT_FP16):
         raise ValueError("B2KV header carries an unknown max_dtype")
-    lo = N.container_layout(hd.L, hd.H, hd.D, hd.ntokens)
+    hd.nb = None
+    if hd.version == 3:
+        if nb is None or len(nb) != 2 * hd.L or any(v < 4 or v > 32 or v % 2 for v in nb):
+            raise ValueError("B2KV v3 header: bad nb map")
+        if hd.ntokens > N.GROUP_TOKENS:
+            raise ValueError("B2KV v3 header: more than 256 tokens")
+        hd.nb = [int(v) for v in nb]
+    lo = container_layout_of(hd)
     if hd.ngroups != (hd.ntokens + N.GROUP_TOKENS - 1) // N.GROUP_TOKENS:
         raise ValueError("B2KV header: ngroups does not match ntokens")
     if hd.total_bytes != lo.off_payload + hd.payload_bytes:
         raise ValueError("B2KV header: total_bytes != fixed sections + payload_bytes (truncated or corrupt)")
     nstreams = 2 * hd.L * hd.H * hd.D * hd.ngroups
-    per_stream = 4 if hd.version == 2 else 1          # rANS streams are >= 4 bytes, arithmetic-coder streams >= 1
+    per_stream = 1 if hd.version == 1 else 4          # rANS streams are >= 4 bytes, arithmetic-coder streams >= 1
     if hd.payload_bytes < per_stream * nstreams or hd.payload_bytes > lo.max_total_bytes:
         raise ValueError("B2KV header: payload_bytes impossible for this shape")
 
@@ -272,12 +293,14 @@ class CacheGenCodec:
     """
 
     def __init__(self, model_name: str, coder: Optional[str] = None):
-        """coder: "rans" (container version 2, the default) or "ac" (version 1, the torchac-lineage arithmetic coder);
-        the environment variable LMCACHE_B200_CODER overrides the default.  Decoding accepts both."""
+        """coder: "rans_compact" (container version 3, the default: rANS payload + symbol counts instead of CDF rows;
+        chunks of more than 256 tokens fall back to version 2), "rans" (version 2) or "ac" (version 1, the
+        torchac-lineage arithmetic coder); the environment variable LMCACHE_B200_CODER overrides the default.
+        Decoding accepts all three."""
         import os
         from lmcache_b200.storage_backend.serde.cachegen_basics import CacheGenConfig
         N.require_cuda()
-        name = (coder or os.environ.get("LMCACHE_B200_CODER", "rans")).lower()
+        name = (coder or os.environ.get("LMCACHE_B200_CODER", "rans_compact")).lower()
         if name not in N.CODERS:
             raise ValueError(f"unknown coder {name!r} (expected one of {sorted(N.CODERS)})")
         self.coder = N.CODERS[name]
@@ -286,6 +309,7 @@ class CacheGenCodec:
         self.nlayers = len(kb)
         self._kb = N.float_array(kb)
         self._vb = N.float_array(vb)
+        self._nb = (N.nb_map(kb, vb, len(kb)))          # keys then values, all layers of the model
         self._enc_lock = threading.RLock()
         self._dec_lock = threading.Lock()
         self._enc_event: Optional[torch.cuda.Event] = None
@@ -310,10 +334,34 @@ class CacheGenCodec:
             t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
         return t
 
+    def coder_for(self, chunk_tokens: int) -> int:
+        """The container this codec writes for chunks of `chunk_tokens`: the compact one holds <= 256 tokens."""
+        if self.coder == N.CODER_RANS_COMPACT and chunk_tokens > N.GROUP_TOKENS:
+            return N.CODER_RANS
+        return self.coder
+
+    def layout(self, L: int, H: int, D: int, chunk_tokens: int) -> "N.Layout":
+        return N.container_layout(L, H, D, chunk_tokens, self.coder_for(chunk_tokens), self._kb, self._vb)
+
+    def accepts(self, hd: "N.Header") -> bool:
+        """Can this codec decode the container?  A compact container must have been written with this model's bins."""
+        if hd.version != 3:
+            return True
+        n = self.nlayers
+        return hd.L <= n and hd.nb == self._nb[:hd.L] + self._nb[n:n + hd.L]
+
+    def max_container_bytes(self, L: int, H: int, D: int, chunk_tokens: int) -> int:
+        """Upper bound of a container of ANY version this codec can decode (what a receive slab must reserve when the
+        writer may have been configured differently): version 2's sections are the largest."""
+        lo = N.container_layout(L, H, D, chunk_tokens)
+        if chunk_tokens <= N.GROUP_TOKENS:
+            return (lo.fixed_bytes + 2 * L * H * D * (chunk_tokens + 4) + 16 + 15) & ~15
+        return lo.max_total_bytes
+
     def out_stride(self, L: int, H: int, D: int, chunk_tokens: int) -> int:
         """Bytes reserved per container.  Chunks of <= 256 tokens are coded with their own empirical CDF,
         so a stream costs <= 8 bits/symbol (+ flush); larger chunks may reach 16 bits/symbol."""
-        lo = N.container_layout(L, H, D, chunk_tokens)
+        lo = self.layout(L, H, D, chunk_tokens)
         if chunk_tokens <= N.GROUP_TOKENS:
             return (lo.fixed_bytes + 2 * L * H * D * (chunk_tokens + 4) + 16 + 15) & ~15
         return lo.max_total_bytes
@@ -338,7 +386,8 @@ class CacheGenCodec:
         lib = N.lib()
         with self._enc_lock, torch.cuda.device(view.device):
             tstream = stream if stream is not None else torch.cuda.current_stream()
-            ws_bytes = lib.b200kv_encode_workspace_bytes(view.L, view.H, view.D, chunk_size, n_chunks, self.coder)
+            coder = self.coder_for(chunk_size)
+            ws_bytes = lib.b200kv_encode_workspace_bytes(view.L, view.H, view.D, chunk_size, n_chunks, coder)
             own_out, own_sizes = out is None, sizes is None
             need_out = stride * n_chunks + N.READ_SLACK if own_out else 0
             # the workspace (and the codec's own staging) are shared by consecutive calls: order after the previous
@@ -364,7 +413,7 @@ class CacheGenCodec:
                 raise ValueError("sizes buffer too small")
             # KV statistics of one model are stable from call to call: the previous call's measured entropy picks the
             # encode kernel variant for this one (byte-identical output either way)
-            flags = self.coder | (N.ENCODE_HINT_HIGH_ENTROPY if self._last_bits_per_symbol > 2.7 else 0)
+            flags = coder | (N.ENCODE_HINT_HIGH_ENTROPY if self._last_bits_per_symbol > 2.7 else 0)
             N.check(lib.b200kv_encode_chunks(ctypes.byref(view.desc), tok_begin, n_chunks, chunk_size, last,
                                              self._kb, self._vb, flags, out.data_ptr(), stride, sizes.dev_ptr,
                                              self._enc_ws.data_ptr(), self._enc_ws.numel(), tstream.cuda_stream),
@@ -372,8 +421,8 @@ class CacheGenCodec:
             ev = torch.cuda.Event()
             ev.record(tstream)
             self._enc_event = ev
-            fixed = N.container_layout(view.L, view.H, view.D, chunk_size).fixed_bytes
-            return EncodeTicket(out, stride, n_chunks, sizes, ev, int(view.desc.dtype), self.coder, view, self,
+            fixed = self.layout(view.L, view.H, view.D, chunk_size).fixed_bytes
+            return EncodeTicket(out, stride, n_chunks, sizes, ev, int(view.desc.dtype), coder, view, self,
                                 (fixed, 2.0 * view.L * view.H * view.D * n_tokens))
 
     def encode(self, view: KvView, tok_begin: int, n_tokens: int, chunk_size: int,
@@ -518,13 +567,15 @@ class CacheGenCodec:
         heads = []
         for c in containers:
             if isinstance(c, torch.Tensor):
-                hb = c[:N.HEADER_BYTES].cpu().numpy().tobytes()
-                hd = N.Header.from_buffer_copy(hb)
-                if hd.magic != N.MAGIC or hd.version not in (1, 2) or hd.status != 0 or hd.total_bytes > c.numel():
+                hb = c[:N.HEADER_BYTES + N.MAX_PLANES].cpu().numpy().tobytes()
+                hd = N.Header.from_buffer_copy(hb[:N.HEADER_BYTES])
+                if hd.magic != N.MAGIC or hd.version not in (1, 2, 3) or hd.status != 0 or hd.total_bytes > c.numel():
                     raise ValueError("bad B2KV container tensor")
-                check_header(hd)
+                check_header(hd, list(hb[N.HEADER_BYTES:N.HEADER_BYTES + 2 * hd.L]) if hd.version == 3 else None)
             else:
                 hd = parse_header(c)
+            if not self.accepts(hd):
+                raise ValueError("compact container written with another model's bins")
             if (hd.L, hd.H, hd.D) != (dst.L, dst.H, dst.D):
                 raise ValueError(f"container shape L/H/D={hd.L}/{hd.H}/{hd.D} does not match destination "
                                  f"{dst.L}/{dst.H}/{dst.D}")

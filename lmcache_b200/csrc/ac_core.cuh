@@ -773,15 +773,31 @@ struct Layout {
     int32_t ngroups;
 };
 
-B2_HD Layout make_layout(int L, int C, int t) {
+// Containers of version 1 / 2 (nbsum == 0):  header | cdf i16[2L][C][33] | maxes | lengths i32[G][2L][C] | payload.
+// Compact container, version 3 (nbsum = sum over the 2L planes of nb(plane) = 2 * (bins // 2), chunks of <= 256 tokens):
+//   header | nb u8[2L] | counts u8[plane][C][nb(plane)] | maxes | half-lengths u8[2L][C] | payload
+// i.e. the per-stream CDF is replaced by the symbol histogram it is a function of (CdfAccum: cdf = f(counts, t)), and
+// a stream's byte length L (even, <= 194) by L / 2.  off_cdf is the first byte after the header in both (the nb map in
+// version 3); counts start at off_cdf + align16(2L).
+B2_HD Layout make_layout(int L, int C, int t, int nbsum = 0) {
     Layout lo;
     const int64_t NL = 2 * (int64_t)L;
     lo.ngroups = (t + kGroup - 1) / kGroup;
     lo.off_cdf = 64;
-    lo.off_maxes = align16(lo.off_cdf + NL * C * kLp * 2);
-    lo.off_lengths = align16(lo.off_maxes + NL * t * 2);
-    lo.off_payload = align16(lo.off_lengths + (int64_t)lo.ngroups * NL * C * 4);
+    if (nbsum > 0) {
+        lo.off_maxes = align16(lo.off_cdf + align16(NL) + (int64_t)C * nbsum);
+        lo.off_lengths = align16(lo.off_maxes + NL * t * 2);
+        lo.off_payload = align16(lo.off_lengths + (int64_t)lo.ngroups * NL * C);
+    } else {
+        lo.off_maxes = align16(lo.off_cdf + NL * C * kLp * 2);
+        lo.off_lengths = align16(lo.off_maxes + NL * t * 2);
+        lo.off_payload = align16(lo.off_lengths + (int64_t)lo.ngroups * NL * C * 4);
+    }
     return lo;
 }
+
+// compact container: a symbol count as stored (256 -- a stream of one repeated symbol in a full chunk -- is stored as
+// 255 and recognised by the stream's counts summing to t - 1)
+B2_HD uint32_t count_to_byte(uint32_t n) { return n < 255u ? n : 255u; }
 
 }  // namespace b200kv

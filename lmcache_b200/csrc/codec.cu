@@ -33,7 +33,8 @@ constexpr int TEMPW_SPLIT = 132;   // foreign CDF (chunk > 256 tokens): <= 16 bi
 constexpr int TEMPW_FUSED_RANS = 48;   // rANS, own-CDF streams: <= 95 renormalisation halfwords for ANY symbol order
                                        //   (ideal <= 1268.5 bits, < 1 bit of overshoot per step); the 32-bit
                                        //   final state goes to its own array.  Split mode: <= 1 halfword per symbol = 128 words
-constexpr int CODER_AC = 0, CODER_RANS = 1;   // B2KV container version = coder + 1
+constexpr int CODER_AC = 0, CODER_RANS = 1;   // payload coder; B2KV container version = coder + 1 ...
+constexpr int CODER_RANS_COMPACT = 2;         // ... 3 = rANS payload + compact side information (ac_core.cuh, make_layout)
 
 struct EncParams {
     PlaneTable pt;
@@ -43,7 +44,8 @@ struct EncParams {
     int32_t n_chunks, chunk_tokens, last_chunk_tokens, tpp;   // tpp = tiles per plane
     int32_t tiles_full, tempw;                                 // tiles per full chunk; words per temp row
     int32_t stage_bytes;                                       // compact_kernel: bytes of shared-memory stage per CTA
-    int32_t coder;                                             // CODER_AC | CODER_RANS
+    int32_t coder;                                             // CODER_AC | CODER_RANS (the payload coder)
+    int32_t compact;                                           // 1 = container version 3 (counts instead of CDF rows, u8 half-lengths)
     uint8_t* out;
     int64_t out_stride;
     uint64_t* sizes_out;
@@ -53,6 +55,76 @@ struct EncParams {
     unsigned long long* totals;      // [n_chunks] payload bytes
     unsigned int* err;               // [n_chunks]
 };
+
+// section offsets of a container of this call (encode and decode parameter blocks alike)
+template <class Prm>
+__device__ __forceinline__ Layout layout_of(const Prm& P, int t) {
+    return make_layout(P.L, P.C, t, P.compact ? P.pt.nbsum : 0);
+}
+
+// stream lengths section: int32 bytes (versions 1, 2) or u8 bytes / 2 (version 3: rANS streams are even and <= 194 bytes)
+__device__ __forceinline__ uint32_t load_len(const uint8_t* sec, int64_t idx, bool compact) {
+    return compact ? 2u * (uint32_t)sec[idx] : (uint32_t)reinterpret_cast<const int32_t*>(sec)[idx];
+}
+__device__ __forceinline__ void store_len(uint8_t* sec, int64_t idx, uint32_t len, bool compact) {
+    if (compact) sec[idx] = (uint8_t)(len >> 1);
+    else reinterpret_cast<int32_t*>(sec)[idx] = (int32_t)len;
+}
+
+// compact container: where stream c of plane nl keeps its nb = 2 * (maxq + 1) symbol counts, and whether the records of
+// this plane can be moved with 16-byte accesses (uniform per CTA)
+struct CountRec {
+    int64_t off;     // from the container's first byte
+    int nb;
+    bool vec;
+};
+template <class Prm>
+__device__ __forceinline__ CountRec count_rec(const Prm& P, const Layout& lo, int nl, int c) {
+    CountRec r;
+    r.nb = 2 * ((int)P.pt.maxq[nl] + 1);
+    const int64_t plane = (int64_t)P.C * P.pt.nbpre[nl];
+    r.off = lo.off_cdf + align16(2 * (int64_t)P.L) + plane + (int64_t)c * r.nb;
+    r.vec = (r.nb & 15) == 0 && (plane & 15) == 0;
+    return r;
+}
+__device__ __forceinline__ void store_counts(uint8_t* rec, const uint32_t (&cnt)[32], int nb, bool vec) {
+    if (vec) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (16 * q < nb) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 16 * q + 4 * k;
+                    w[k] = count_to_byte(cnt[i]) | (count_to_byte(cnt[i + 1]) << 8) | (count_to_byte(cnt[i + 2]) << 16) |
+                           (count_to_byte(cnt[i + 3]) << 24);
+                }
+                *reinterpret_cast<uint4*>(rec + 16 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nb) rec[i] = (uint8_t)count_to_byte(cnt[i]);
+    }
+}
+// the record back as 8 words of 4 counts (little-endian, zero beyond nb)
+__device__ __forceinline__ void load_counts(const uint8_t* rec, int nb, bool vec, uint32_t (&w)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = 0u;
+    if (vec) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(rec));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        if (nb > 16) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(rec + 16));
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nb) w[i >> 2] |= (uint32_t)__ldg(rec + i) << (8 * (i & 3));
+    }
+}
 
 __device__ __forceinline__ int chunk_tokens_of(const EncParams& P, int j) {
     return j == P.n_chunks - 1 ? P.last_chunk_tokens : P.chunk_tokens;
@@ -103,7 +175,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_
     if (lane == 0) {
         const int j = (int)(T / P.chunk_tokens);
         const int tj = chunk_tokens_of(P, j);
-        const Layout lo = make_layout(P.L, P.C, tj);
+        const Layout lo = layout_of(P, tj);
         uint16_t* maxes = reinterpret_cast<uint16_t*>(P.out + (int64_t)j * P.out_stride + lo.off_maxes);
         maxes[(int64_t)nl * tj + (T - (int64_t)j * P.chunk_tokens)] = (uint16_t)m;
     }
@@ -276,7 +348,7 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
     const int ncols = min(CT, P.C - ct * CT);
 
     uint8_t* cont = P.out + (int64_t)j * P.out_stride;
-    const Layout lo = make_layout(P.L, P.C, t);
+    const Layout lo = layout_of(P, t);
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + id.tok0;
     const float maxq = P.pt.maxq[nl];
     const int64_t s1 = P.sT;
@@ -390,9 +462,13 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
 #pragma unroll
             for (uint32_t i = 0; i < 32u; ++i) crow[i] = acc.next_p(i, fac[cnt[i]]);
             crow[32] = acc.next_p(32u, 0.0f);
+            if (P.compact) {   // version 3 keeps the counts (the CDF is a function of them): 16 or 32 bytes per stream
+                const CountRec cr = count_rec(P, lo, nl, c);
+                store_counts(cont + cr.off, cnt, cr.nb, cr.vec);
+            }
         }
         __syncthreads();
-        {   // the tile's 33-entry rows are contiguous in smem and in the container: straight coalesced copy
+        if (!P.compact) {   // the tile's 33-entry rows are contiguous in smem and in the container: straight coalesced copy
             uint16_t* dstc = reinterpret_cast<uint16_t*>(cont + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
             for (int e = tid; e < ncols * kLp; e += CT) dstc[e] = cdfr[e];
         }
@@ -489,10 +565,7 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
     }
 
     // ---- stream lengths to the container, tile total for the compaction scan
-    if (active) {
-        int32_t* lengths = reinterpret_cast<int32_t*>(cont + lo.off_lengths) + ((int64_t)id.g * NL + nl) * P.C;
-        lengths[c] = (int32_t)len;
-    }
+    if (active) store_len(cont + lo.off_lengths, ((int64_t)id.g * NL + nl) * P.C + c, len, P.compact != 0);
     uint32_t tile_total;
     (void)block_excl_scan(len, s_warp, &tile_total);
     if (tid == 0) P.tile_tot[(int64_t)j * P.tiles_full + id.tile_in_chunk] = tile_total;
@@ -558,7 +631,7 @@ __global__ void __launch_bounds__(CT, 7) encode_tma_kernel(EncParams P) {
     const int j = id.j, nl = id.nl, ct = id.ct, t = id.t, gt = id.gt;
     const int c = ct * CT + tid;
     uint8_t* cont = P.out + (int64_t)j * P.out_stride;
-    const Layout lo = make_layout(P.L, P.C, t);
+    const Layout lo = layout_of(P, t);
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t + id.tok0;
     const float maxq = P.pt.maxq[nl];
     const int64_t tokabs = P.tok_begin + (int64_t)j * P.chunk_tokens + id.tok0;
@@ -648,6 +721,10 @@ __global__ void __launch_bounds__(CT, 7) encode_tma_kernel(EncParams P) {
         for (int i = 0; i < 32; ++i) cnt[i] = mycol[i * CT];
         CdfAccum acc;
         acc.init(t);
+        if (P.compact) {
+            const CountRec cr = count_rec(P, lo, nl, c);
+            store_counts(cont + cr.off, cnt, cr.nb, cr.vec);
+        }
         uint32_t c0 = acc.next_p(0u, ntab[cnt[0]]);
 #pragma unroll
         for (uint32_t i = 0; i < 31u; ++i) {
@@ -695,11 +772,11 @@ __global__ void __launch_bounds__(CT, 7) encode_tma_kernel(EncParams P) {
 
     // ---- stream lengths, tile total, CDF rows (staged through the now idle ring: stream-major u16[33] rows,
     //      contiguous in the container -> one coalesced copy)
-    reinterpret_cast<int32_t*>(cont + lo.off_lengths)[((int64_t)id.g * NL + nl) * P.C + c] = (int32_t)len;
+    store_len(cont + lo.off_lengths, ((int64_t)id.g * NL + nl) * P.C + c, len, P.compact != 0);
     uint32_t tile_total;
     (void)block_excl_scan(len, s_warp, &tile_total);               // has a __syncthreads: every thread is done with the ring
     if (tid == 0) P.tile_tot[(int64_t)j * P.tiles_full + id.tile_in_chunk] = tile_total;
-    if (id.g == 0) {                                                // the CDF belongs to the chunk; its first group writes it
+    if (id.g == 0 && !P.compact) {                                  // the CDF belongs to the chunk; its first group writes it
         uint16_t* stg = reinterpret_cast<uint16_t*>(ring);
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg[tid * kLp + i] = (uint16_t)mycol[i * CT];
@@ -728,7 +805,7 @@ __global__ void __launch_bounds__(CT) cdf_kernel(EncParams P) {
     const bool active = c < P.C;
     const int ncols = min(CT, P.C - ct * CT);
     uint8_t* cont = P.out + (int64_t)j * P.out_stride;
-    const Layout lo = make_layout(P.L, P.C, t);
+    const Layout lo = layout_of(P, t);
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(cont + lo.off_maxes) + (int64_t)nl * t;
     const float maxq = P.pt.maxq[nl];
     uint32_t* prow = cnts + tid * PAIRW;
@@ -885,11 +962,11 @@ __global__ void __launch_bounds__(CT, 9) compact_kernel(EncParams P) {
     const int NL = 2 * P.L;
     const int c = id.ct * CT + tid;
     uint8_t* cont = P.out + (int64_t)id.j * P.out_stride;
-    const Layout lo = make_layout(P.L, P.C, id.t);
-    const int32_t* lengths = reinterpret_cast<const int32_t*>(cont + lo.off_lengths) + ((int64_t)id.g * NL + id.nl) * P.C;
+    const Layout lo = layout_of(P, id.t);
     const bool rans = P.coder == CODER_RANS;
     const uint32_t rowbytes = (uint32_t)P.tempw * 4u;
-    const uint32_t len = c < P.C ? min((uint32_t)lengths[c], rowbytes + (rans ? 4u : 0u)) : 0u;
+    const uint32_t len = c < P.C ? min(load_len(cont + lo.off_lengths, ((int64_t)id.g * NL + id.nl) * P.C + c, P.compact != 0),
+                                       rowbytes + (rans ? 4u : 0u)) : 0u;
     uint32_t tile_total;
     const uint32_t my_off = block_excl_scan(len, s_warp, &tile_total);
     const uint64_t base = P.tile_tot[(int64_t)id.j * P.tiles_full + id.tile_in_chunk];
@@ -938,10 +1015,10 @@ __global__ void finalize_kernel(EncParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n_chunks) return;
     const int t = chunk_tokens_of(P, j);
-    const Layout lo = make_layout(P.L, P.C, t);
+    const Layout lo = layout_of(P, t);
     b200kv_header* hd = reinterpret_cast<b200kv_header*>(P.out + (int64_t)j * P.out_stride);
     hd->magic = B200KV_MAGIC;
-    hd->version = (uint32_t)P.coder + 1u;          // 1: arithmetic coder, 2: rANS
+    hd->version = P.compact ? 3u : (uint32_t)P.coder + 1u;    // 1: arithmetic coder, 2: rANS, 3: rANS + compact sections
     hd->L = P.L; hd->H = P.H; hd->D = P.D;
     hd->ntokens = t;
     hd->ngroups = lo.ngroups;
@@ -951,6 +1028,11 @@ __global__ void finalize_kernel(EncParams P) {
     hd->status = P.err[j];
     hd->reserved[0] = hd->reserved[1] = hd->reserved[2] = 0u;
     if (P.sizes_out) P.sizes_out[j] = hd->status ? 0ull : hd->total_bytes;     // 0 = this chunk failed (see header.status)
+    if (P.compact) {                               // counts per stream of every plane: makes the container self-describing
+        uint8_t* nbmap = reinterpret_cast<uint8_t*>(hd) + lo.off_cdf;
+        const int NL = 2 * P.L;
+        for (int nl = 0; nl < (int)align16(NL); ++nl) nbmap[nl] = nl < NL ? (uint8_t)(2 * ((int)P.pt.maxq[nl] + 1)) : (uint8_t)0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ decode
@@ -967,6 +1049,7 @@ struct DecParams {
     int64_t sT, sH;
     const int64_t* slot_map;     // paged destination: token i lives in row slot_map[i]; NULL = row i
     int32_t L, H, D, C, out_dtype, max_dtype, n_chunks, tpp, tiles_max;
+    int32_t compact;             // containers are version 3
     const DecChunk* chunks;      // device
     unsigned long long* tile_base;   // [n_chunks][tiles_max]: tile sums, then exclusive prefix
     uint32_t* status;            // [n_chunks] or NULL: bit 0 = a rANS stream did not return to its initial state,
@@ -984,11 +1067,10 @@ __global__ void __launch_bounds__(128) tile_sum_kernel(DecParams P) {
     if (tile >= ntiles) return;
     const int plane_row = tile / P.tpp;          // g * NL + nl
     const int ct = tile - plane_row * P.tpp;
-    const Layout lo = make_layout(P.L, P.C, dc.t);
-    const int32_t* lengths = reinterpret_cast<const int32_t*>(dc.base + lo.off_lengths) + (int64_t)plane_row * P.C;
+    const Layout lo = layout_of(P, dc.t);
     const int c0 = ct * CT, c1 = min(P.C, c0 + CT);
     uint32_t s = 0;
-    for (int c = c0 + lane; c < c1; c += 32) s += (uint32_t)lengths[c];
+    for (int c = c0 + lane; c < c1; c += 32) s += load_len(dc.base + lo.off_lengths, (int64_t)plane_row * P.C + c, P.compact != 0);
     s = __reduce_add_sync(0xffffffffu, s);
     if (lane == 0) P.tile_base[(int64_t)j * P.tiles_max + tile] = s;
 }
@@ -1247,10 +1329,9 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     const int c = ct * CT + tid;
     const bool active = c < P.C;
     const int ncols = min(CT, P.C - ct * CT);
-    const Layout lo = make_layout(P.L, P.C, dc.t);
+    const Layout lo = layout_of(P, dc.t);
 
-    const int32_t* lengths = reinterpret_cast<const int32_t*>(dc.base + lo.off_lengths) + ((int64_t)g * NL + nl) * P.C;
-    const uint32_t len = active ? (uint32_t)lengths[c] : 0u;
+    const uint32_t len = active ? load_len(dc.base + lo.off_lengths, ((int64_t)g * NL + nl) * P.C + c, P.compact != 0) : 0u;
     uint32_t tile_total;
     const uint32_t my_rel = block_excl_scan(len, s_warp, &tile_total);
     // the stream's byte offset inside the container; a corrupt lengths section cannot push it outside the payload
@@ -1262,54 +1343,100 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
     const uint16_t* cdf_src = reinterpret_cast<const uint16_t*>(dc.base + lo.off_cdf) + ((int64_t)nl * P.C + ct * CT) * kLp;
     const uint16_t* maxes = reinterpret_cast<const uint16_t*>(dc.base + lo.off_maxes) + (int64_t)nl * dc.t + tok0;
     const float cq = P.pt.maxq[nl];
-    if constexpr (CODER == CODER_RANS && TR) {
-        // TRANSPOSED table: entry i of stream tid at tab[i * CT + tid], entry = (cdf[i] << 16) | freq(i).  Built in two
-        // steps through a staging copy of the raw CDF rows that lives in the table's own upper half (bytes 8448..16895):
-        // coalesced global -> staging; every thread turns ITS row (33 halfwords, stride 33: conflict-free) into column
-        // entries 0..15 (bytes 0..8191, clear of the staging); entries 16..31 -- needed by 32-bin planes only -- go
-        // through registers so that they may overwrite the staging once everybody has read it.
-        uint16_t* stg = reinterpret_cast<uint16_t*>(smem) + (CT * kLp);            // second half of the CT*kLp words
-        for (int e = tid; e < ncols * kLp; e += CT) stg[e] = __ldg(cdf_src + e);
-        for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
-        if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
-        __syncthreads();
-        const uint16_t* my = stg + tid * kLp;
-        if (active) {
-            uint32_t c0 = my[0];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t c1 = my[i + 1];
-                tab[i * CT + tid] = rans_table_entry(c0, c1);
-                c0 = c1;
-            }
-        }
-        if (cq > 7.0f) {                                                            // uniform per CTA
-            uint32_t cv[17];
-            if (active) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) cv[i] = my[16 + i];
-                cv[16] = 0x10000u;                                                   // cdf[32] is stored as 0 and means 65536
-            }
+    bool built = false;
+    if constexpr (CODER == CODER_RANS) {
+        if (P.compact) {
+            // Container version 3: the stream's record holds its symbol counts; the CDF is a function of them (CdfAccum,
+            // the same arithmetic as the encoder), so every thread rebuilds its own table -- row-major or transposed,
+            // both conflict-free for thread-private writes.  fl32(n / t) comes from a table that borrows the row-maxima
+            // area (mx[0..255] + lut[0] = 257 floats) until the table is built.
+            float* pn = mx;
+            const float tf = (float)dc.t;
+            for (int n = tid; n <= kGroup; n += CT) pn[n] = fdiv((float)n, tf);
             __syncthreads();
             if (active) {
+                const CountRec cr = count_rec(P, lo, nl, c);
+                uint32_t w[8];
+                load_counts(dc.base + cr.off, cr.nb, cr.vec, w);
+                uint32_t sum = 0u;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) tab[(16 + i) * CT + tid] = rans_table_entry(cv[i], cv[i + 1]);
+                for (int k = 0; k < 8; ++k) sum = __dp4a(w[k], 0x01010101u, sum);
+                const uint32_t fix = sum + 1u == (uint32_t)dc.t ? 1u : 0u;      // a count of 256 is stored as 255
+                auto count = [&](int i) -> uint32_t {
+                    const uint32_t n = (w[(i & 31) >> 2] >> (8 * (i & 3))) & 255u;
+                    return i < 32 ? n + (n == 255u ? fix : 0u) : 0u;
+                };
+                CdfAccum acc;
+                acc.init(dc.t);
+                uint32_t c0 = acc.next_p(0u, pn[count(0)]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < cr.nb) {
+                        uint32_t c1 = acc.next_p((uint32_t)i + 1u, pn[count(i + 1)]);
+                        if (i == 31) c1 = 0x10000u;                              // cdf[32] wraps to 0 in 16 bits and means 65536
+                        const uint32_t e = rans_table_entry(c0, c1);
+                        if (TR) tab[i * CT + tid] = e;
+                        else tab[tid * kLp + i] = e;
+                        c0 = c1;
+                    }
+                }
             }
+            __syncthreads();                                                     // pn is dead: maxima and LUT take its place
+            for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
+            if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
+            built = true;
         }
-    } else {
-        for (int e = tid; e < ncols * kLp; e += CT) {
-            const uint32_t i = (uint32_t)e % (uint32_t)kLp;
-            const uint32_t c0 = __ldg(cdf_src + e);
-            if constexpr (CODER == CODER_RANS) {
-                // (cdf[i] << 16) | freq(i); cdf[32] is stored as 0 and stands for 65536; entry 32 is never searched
-                const uint32_t c1 = i < 31u ? (uint32_t)__ldg(cdf_src + e + 1) : 0x10000u;
-                tab[e] = i < 32u ? rans_table_entry(c0, c1) : 0xFFFFFFFFu;
-            } else {
-                tab[e] = dec_table_entry(i, c0);
+    }
+    if (!built) {
+        if constexpr (CODER == CODER_RANS && TR) {
+            // TRANSPOSED table: entry i of stream tid at tab[i * CT + tid], entry = (cdf[i] << 16) | freq(i).  Built in two
+            // steps through a staging copy of the raw CDF rows that lives in the table's own upper half (bytes 8448..16895):
+            // coalesced global -> staging; every thread turns ITS row (33 halfwords, stride 33: conflict-free) into column
+            // entries 0..15 (bytes 0..8191, clear of the staging); entries 16..31 -- needed by 32-bin planes only -- go
+            // through registers so that they may overwrite the staging once everybody has read it.
+            uint16_t* stg = reinterpret_cast<uint16_t*>(smem) + (CT * kLp);            // second half of the CT*kLp words
+            for (int e = tid; e < ncols * kLp; e += CT) stg[e] = __ldg(cdf_src + e);
+            for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
+            if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
+            __syncthreads();
+            const uint16_t* my = stg + tid * kLp;
+            if (active) {
+                uint32_t c0 = my[0];
+    #pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t c1 = my[i + 1];
+                    tab[i * CT + tid] = rans_table_entry(c0, c1);
+                    c0 = c1;
+                }
             }
+            if (cq > 7.0f) {                                                            // uniform per CTA
+                uint32_t cv[17];
+                if (active) {
+    #pragma unroll
+                    for (int i = 0; i < 16; ++i) cv[i] = my[16 + i];
+                    cv[16] = 0x10000u;                                                   // cdf[32] is stored as 0 and means 65536
+                }
+                __syncthreads();
+                if (active) {
+    #pragma unroll
+                    for (int i = 0; i < 16; ++i) tab[(16 + i) * CT + tid] = rans_table_entry(cv[i], cv[i + 1]);
+                }
+            }
+        } else {
+            for (int e = tid; e < ncols * kLp; e += CT) {
+                const uint32_t i = (uint32_t)e % (uint32_t)kLp;
+                const uint32_t c0 = __ldg(cdf_src + e);
+                if constexpr (CODER == CODER_RANS) {
+                    // (cdf[i] << 16) | freq(i); cdf[32] is stored as 0 and stands for 65536; entry 32 is never searched
+                    const uint32_t c1 = i < 31u ? (uint32_t)__ldg(cdf_src + e + 1) : 0x10000u;
+                    tab[e] = i < 32u ? rans_table_entry(c0, c1) : 0xFFFFFFFFu;
+                } else {
+                    tab[e] = dec_table_entry(i, c0);
+                }
+            }
+            for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
+            if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
         }
-        for (int i = tid; i < gt; i += CT) mx[i] = half_to_float(maxes[i], P.max_dtype);
-        if (tid < 32) lut[tid] = dequant_lut((uint32_t)tid, cq);
     }
     __syncthreads();
 
@@ -1341,6 +1468,7 @@ int make_plane_table(const b200kv_kv_desc* kv, const float* key_bins, const floa
     B2_REQUIRE(kv->H > 0 && kv->D > 0, "H/D must be positive");
     B2_REQUIRE(kv->dtype == B200KV_DT_BF16 || kv->dtype == B200KV_DT_FP16, "dtype must be bf16 or fp16");
     B2_REQUIRE(kv->planes != nullptr || kv->base != nullptr, "no KV pointer");
+    int nbsum = 0;
     for (int kvi = 0; kvi < 2; ++kvi)
         for (int l = 0; l < kv->L; ++l) {
             const int nl = kvi * kv->L + l;
@@ -1351,8 +1479,23 @@ int make_plane_table(const b200kv_kv_desc* kv, const float* key_bins, const floa
             const float bins = kvi ? value_bins[l] : key_bins[l];
             out->maxq[nl] = floorf(bins / 2.0f) - 1.0f;       // bins // 2 - 1  (cachegen_encoder.py:53)
             B2_REQUIRE(out->maxq[nl] >= 1.0f && out->maxq[nl] <= 15.0f, "bins must be in [4, 32]");
+            out->nbpre[nl] = (uint16_t)nbsum;
+            nbsum += 2 * ((int)out->maxq[nl] + 1);
         }
+    out->nbsum = nbsum;
     return 0;
+}
+
+// sum over the 2L planes of nb(plane) = 2 * (bins // 2): the compact container's bytes of counts per channel
+static int nb_sum(int L, const float* key_bins, const float* value_bins) {
+    int s = 0;
+    for (int kvi = 0; kvi < 2; ++kvi)
+        for (int l = 0; l < L; ++l) {
+            const float maxq = floorf((kvi ? value_bins[l] : key_bins[l]) / 2.0f) - 1.0f;
+            if (!(maxq >= 1.0f && maxq <= 15.0f)) return -1;
+            s += 2 * ((int)maxq + 1);
+        }
+    return s;
 }
 
 static int tiles_per_plane(int C) { return (C + CT - 1) / CT; }
@@ -1411,8 +1554,21 @@ using namespace b200kv;
 extern "C" {
 
 int b200kv_container_layout(int32_t L, int32_t H, int32_t D, int32_t ntokens, b200kv_layout* out) {
+    return b200kv_container_layout_v(L, H, D, ntokens, CODER_RANS, nullptr, nullptr, out);
+}
+
+int b200kv_container_layout_v(int32_t L, int32_t H, int32_t D, int32_t ntokens, int32_t coder, const float* key_bins,
+                              const float* value_bins, b200kv_layout* out) {
     B2_REQUIRE(out != nullptr && L > 0 && H > 0 && D > 0 && ntokens > 0, "bad shape");
-    const Layout lo = make_layout(L, H * D, ntokens);
+    B2_REQUIRE(coder >= CODER_AC && coder <= CODER_RANS_COMPACT, "unknown coder");
+    int nbsum = 0;
+    if (coder == CODER_RANS_COMPACT) {
+        B2_REQUIRE(key_bins && value_bins && 2 * L <= B200KV_MAX_PLANES, "the compact container's layout depends on the bins");
+        B2_REQUIRE(ntokens <= kGroup, "the compact container holds chunks of at most 256 tokens");
+        nbsum = nb_sum(L, key_bins, value_bins);
+        B2_REQUIRE(nbsum > 0, "bins must be in [4, 32]");
+    }
+    const Layout lo = make_layout(L, H * D, ntokens, nbsum);
     out->off_cdf = lo.off_cdf;
     out->off_maxes = lo.off_maxes;
     out->off_lengths = lo.off_lengths;
@@ -1429,6 +1585,7 @@ int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t c
                                       int32_t coder) {
     if (L <= 0 || H <= 0 || D <= 0 || chunk_tokens <= 0 || n_chunks <= 0) return -2;
     coder &= 0xff;
+    if (coder == CODER_RANS_COMPACT) coder = CODER_RANS;       // same kernels, same scratch
     if (coder != CODER_AC && coder != CODER_RANS) return -2;
     const int64_t G = (chunk_tokens + kGroup - 1) / kGroup;
     const int64_t n_tiles = (int64_t)n_chunks * G * 2 * L * tiles_per_plane(H * D);
@@ -1453,10 +1610,13 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     B2_REQUIRE(key_bins && value_bins, "bins are NULL");
     const bool hint_tma = (coder & B200KV_ENCODE_HINT_HIGH_ENTROPY) != 0;
     coder &= 0xff;
-    B2_REQUIRE(coder == CODER_AC || coder == CODER_RANS, "coder must be B200KV_CODER_AC or B200KV_CODER_RANS");
+    B2_REQUIRE(coder >= CODER_AC && coder <= CODER_RANS_COMPACT, "coder must be one of B200KV_CODER_*");
+    P.compact = coder == CODER_RANS_COMPACT ? 1 : 0;
+    if (P.compact) coder = CODER_RANS;                          // version 3 = rANS payload + compact side information
     P.coder = coder;
     if (int rc = make_plane_table(kv, key_bins, value_bins, &P.pt)) return rc;
     B2_REQUIRE(n_chunks > 0 && chunk_tokens > 0, "n_chunks / chunk_tokens must be positive");
+    B2_REQUIRE(!P.compact || chunk_tokens <= kGroup, "the compact container (B200KV_CODER_RANS_COMPACT) holds chunks of at most 256 tokens");
     B2_REQUIRE(last_chunk_tokens > 0 && last_chunk_tokens <= chunk_tokens, "last_chunk_tokens out of range");
     B2_REQUIRE(out != nullptr && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (out_stride & 15) == 0,
                "out / out_stride must be 16-byte aligned");
@@ -1470,7 +1630,7 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
     P.out = static_cast<uint8_t*>(out);
     P.out_stride = out_stride;
     P.sizes_out = sizes_out;
-    const Layout lo = make_layout(P.L, P.C, chunk_tokens);
+    const Layout lo = make_layout(P.L, P.C, chunk_tokens, P.compact ? P.pt.nbsum : 0);
     B2_REQUIRE(out_stride >= lo.off_payload + 16, "out_stride smaller than the fixed container sections");
 
     const int64_t G = lo.ngroups;
@@ -1597,8 +1757,11 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DecParams P;
     B2_REQUIRE(key_bins && value_bins, "bins are NULL");
-    B2_REQUIRE(coder == CODER_AC || coder == CODER_RANS, "coder must be B200KV_CODER_AC or B200KV_CODER_RANS");
+    B2_REQUIRE(coder >= CODER_AC && coder <= CODER_RANS_COMPACT, "coder must be one of B200KV_CODER_*");
+    P.compact = coder == CODER_RANS_COMPACT ? 1 : 0;
+    if (P.compact) coder = CODER_RANS;
     if (int rc = make_plane_table(dst, key_bins, value_bins, &P.pt)) return rc;
+    const int nbsum = P.compact ? P.pt.nbsum : 0;
     B2_REQUIRE(containers && offsets && total_bytes && ntokens && dst_tok && n_chunks > 0, "bad chunk arrays");
     B2_REQUIRE(max_dtype == B200KV_DT_BF16 || max_dtype == B200KV_DT_FP16, "bad max_dtype");
     B2_REQUIRE(dst->sT > 0 && dst->sT < (1ll << 23), "destination token stride out of range");
@@ -1610,9 +1773,10 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
     int tmax = 0;
     for (int j = 0; j < n_chunks; ++j) {
         B2_REQUIRE(ntokens[j] > 0, "ntokens must be positive");
+        B2_REQUIRE(!P.compact || ntokens[j] <= kGroup, "a compact container holds at most 256 tokens");
         B2_REQUIRE((offsets[j] & 15) == 0, "container offsets must be 16-byte aligned");
         // the fixed sections are addressed from (L, H, D, ntokens); the buffer must hold them in full
-        const Layout lj = make_layout(P.L, P.C, ntokens[j]);
+        const Layout lj = make_layout(P.L, P.C, ntokens[j], nbsum);
         B2_REQUIRE(total_bytes[j] >= lj.off_payload && total_bytes[j] - lj.off_payload < (1ll << 32),
                    "container shorter than its fixed sections (truncated or corrupt)");
         B2_REQUIRE(offsets[j] >= 0 && offsets[j] + total_bytes[j] + B200KV_READ_SLACK <= containers_bytes,
@@ -1629,7 +1793,7 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
     {
         double bits = 0.0, syms = 0.0;
         for (int j = 0; j < n_chunks; ++j) {
-            const Layout lj = make_layout(P.L, P.C, ntokens[j]);
+            const Layout lj = make_layout(P.L, P.C, ntokens[j], nbsum);
             bits += 8.0 * (double)(total_bytes[j] - lj.off_payload);
             syms += 2.0 * P.L * (double)P.C * ntokens[j];
         }
@@ -1650,7 +1814,7 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
             hc[j].dst_tok = dst_tok[j];
             hc[j].t = ntokens[j];
             hc[j].ngroups = (ntokens[j] + kGroup - 1) / kGroup;
-            const Layout lj = make_layout(P.L, P.C, ntokens[j]);
+            const Layout lj = make_layout(P.L, P.C, ntokens[j], nbsum);
             hc[j].payload_bytes = (uint32_t)(total_bytes[j] - lj.off_payload);
             hc[j].pad = 0;
         }

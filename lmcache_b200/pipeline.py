@@ -277,7 +277,7 @@ def fetch_decode(codec: CacheGenCodec, upload: UploadRing, futures: Sequence, ds
             blk, n = got
             try:
                 hd = parse_header(blk.view()[:n])
-                ok = (hd.L, hd.H, hd.D) == (dst.L, dst.H, dst.D) and \
+                ok = codec.accepts(hd) and (hd.L, hd.H, hd.D) == (dst.L, dst.H, dst.D) and \
                     dst_tok0 + i * chunk_size + hd.ntokens <= dst.ntokens and \
                     (not wave_items or (hd.max_dtype, hd.version) == (wave_items[0][2].max_dtype, wave_items[0][2].version))
             except ValueError:

@@ -541,10 +541,11 @@ class LMCLocalDiskBackend(LMCLocalCompressedBackend):
                 if size < N.HEADER_BYTES:
                     continue
                 with open(full, "rb") as f:
-                    hd = N.Header.from_buffer_copy(f.read(N.HEADER_BYTES))
-                if hd.magic != N.MAGIC or hd.version not in (1, 2) or hd.status != 0 or int(hd.total_bytes) != size:
+                    head = f.read(N.HEADER_BYTES + N.MAX_PLANES)
+                hd = N.Header.from_buffer_copy(head[:N.HEADER_BYTES])
+                if hd.magic != N.MAGIC or hd.version not in (1, 2, 3) or hd.status != 0 or int(hd.total_bytes) != size:
                     continue
-                check_header(hd)
+                check_header(hd, list(head[N.HEADER_BYTES:N.HEADER_BYTES + 2 * hd.L]) if hd.version == 3 else None)
             except (OSError, ValueError):
                 continue                         # damaged / foreign file: not part of the cache
             # "/" in a model name was written as "-": the key of a lookup goes through the same rule, so index by path

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes
 from dataclasses import dataclass
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 import torch
@@ -83,6 +83,24 @@ class CacheGenGPUBytestream:
 _HALF = {N.DT_BF16: torch.bfloat16, N.DT_FP16: torch.float16}
 
 
+def cdf_from_counts(counts: np.ndarray, ntokens: int) -> np.ndarray:
+    """The CDF tensor the reference stores, as a function of the symbol histogram (what a version-3 container keeps):
+    counts [..., 33] (entry 32 is 0) -> int16 [..., 33].  Restates the in-tree spec of torchac_cuda.calculate_cdf
+    (cachegen_encoder.py:95-126,185-196) the way the kernels evaluate it (csrc/ac_core.cuh, CdfAccum):
+    p_i = fl32(n_i / t); cdf_f[i] = fl32(sum_{k<i} p_k accumulated in double); cdf[i] = int16(rint(cdf_f[i] * 65504) + i).
+    Host-side helper of the from_bytes shim -- the decoder evaluates this on the device."""
+    counts = np.asarray(counts)
+    p = (counts.astype(np.float32) / np.float32(ntokens)).astype(np.float32)
+    cum = np.zeros(counts.shape[:-1], np.float64)
+    out = np.empty(counts.shape, np.int16)
+    for i in range(counts.shape[-1]):
+        prev = cum.astype(np.float32)
+        r = np.rint(prev * np.float32(65504.0)).astype(np.int64) + i
+        out[..., i] = (r & 0xFFFF).astype(np.uint16).view(np.int16)
+        cum = cum + p[..., i].astype(np.float64)
+    return out
+
+
 @dataclass
 class CacheGenGPUEncoderOutput:
     data_chunks: List[CacheGenGPUBytestream]
@@ -92,6 +110,8 @@ class CacheGenGPUEncoderOutput:
     num_heads: int
     head_size: int
     coder: int = N.CODER_RANS         # entropy coder of the bytestreams = container version - 1 (not in the reference)
+    counts: Optional[torch.Tensor] = None   # version 3 only: int32 [2L, C, 33] symbol histogram the CDF was rebuilt from
+    nb: Optional[List[int]] = None          # version 3 only: counts stored per stream of each plane (the container's nb map)
 
     def __getitem__(self, key: str):
         return getattr(self, key)
@@ -100,18 +120,34 @@ class CacheGenGPUEncoderOutput:
     def from_bytes(bs) -> "CacheGenGPUEncoderOutput":
         """Parse a B2KV container into host tensors (zero-copy views where possible)."""
         from lmcache_b200.codec import parse_header
+        from lmcache_b200.codec import container_layout_of
         hd = parse_header(bs)
         L, H, D, t, G = hd.L, hd.H, hd.D, hd.ntokens, hd.ngroups
         C = H * D
-        lo = N.container_layout(L, H, D, t)
+        lo = container_layout_of(hd)
         raw = np.frombuffer(bs, dtype=np.uint8, count=int(hd.total_bytes))
 
         def section(off, count, dtype):
             return torch.from_numpy(raw[off:off + count * np.dtype(dtype).itemsize].view(dtype).copy())
 
-        cdf = section(lo.off_cdf, 2 * L * C * N.LP, np.int16).reshape(2 * L, C, N.LP)
+        counts_t = None
+        if hd.version == 3:
+            # compact container: rebuild the reference's CDF tensor from the stored histogram; widen the lengths
+            counts = np.zeros((2 * L, C, N.LP), np.int32)
+            o = lo.off_cdf + ((2 * L + 15) & ~15)
+            for nl, nb in enumerate(hd.nb):
+                rec = raw[o:o + C * nb].reshape(C, nb).astype(np.int32)
+                short = rec.sum(axis=1) == t - 1                       # a count of 256 is stored as 255
+                rec[short] += (rec[short] == 255)
+                counts[nl, :, :nb] = rec
+                o += C * nb
+            cdf = torch.from_numpy(cdf_from_counts(counts, t))
+            counts_t = torch.from_numpy(counts)
+            lengths = (section(lo.off_lengths, G * 2 * L * C, np.uint8).to(torch.int32) * 2).reshape(G, 2 * L, C)
+        else:
+            cdf = section(lo.off_cdf, 2 * L * C * N.LP, np.int16).reshape(2 * L, C, N.LP)
+            lengths = section(lo.off_lengths, G * 2 * L * C, np.int32).reshape(G, 2 * L, C)
         maxes = section(lo.off_maxes, 2 * L * t, np.int16).view(_HALF[hd.max_dtype]).reshape(2, L, t, 1)
-        lengths = section(lo.off_lengths, G * 2 * L * C, np.int32).reshape(G, 2 * L, C)
         payload = raw[lo.off_payload: lo.off_payload + int(hd.payload_bytes)]
         chunks, pos = [], 0
         for g in range(G):
@@ -119,20 +155,29 @@ class CacheGenGPUEncoderOutput:
             gt = min(N.GROUP_TOKENS, t - g * N.GROUP_TOKENS)
             chunks.append(CacheGenGPUBytestream(torch.from_numpy(payload[pos:pos + nb].copy()), lengths[g], gt))
             pos += nb
-        return CacheGenGPUEncoderOutput(chunks, cdf, maxes[0], maxes[1], H, D, int(hd.version) - 1)
+        return CacheGenGPUEncoderOutput(chunks, cdf, maxes[0], maxes[1], H, D, int(hd.version) - 1, counts_t, hd.nb)
 
     def to_bytes(self) -> bytes:
-        """Re-assemble the flat container from the logical fields (host side; used by tests / tools)."""
+        """Re-assemble the flat container from the logical fields (host side; used by tests / tools).  A version-3
+        object (rANS bytestreams + the histogram) is written back as version 3; without the histogram the same
+        bytestreams go into a version-2 container with the CDF tensor."""
         L = self.max_tensors_key.shape[0]
         t = self.max_tensors_key.shape[1]
         H, D = self.num_heads, self.head_size
         C = H * D
-        lo = N.container_layout(L, H, D, t)
+        compact = int(self.coder) == N.CODER_RANS_COMPACT and self.counts is not None and self.nb is not None
+        coder = int(self.coder) if compact or int(self.coder) != N.CODER_RANS_COMPACT else N.CODER_RANS
+        nb = self.nb
+        if compact:
+            cnt = self.counts.numpy()
+            lo = N.container_layout(L, H, D, t, N.CODER_RANS_COMPACT, nb[:L], nb[L:])
+        else:
+            lo = N.container_layout(L, H, D, t)
         payload = b"".join(c.bytestream.cpu().numpy().tobytes() for c in self.data_chunks)
         total = lo.off_payload + len(payload)
         buf = bytearray(total)
         hd = N.Header.from_buffer(buf)
-        hd.magic, hd.version = N.MAGIC, int(self.coder) + 1
+        hd.magic, hd.version = N.MAGIC, coder + 1
         hd.L, hd.H, hd.D, hd.ntokens, hd.ngroups = L, H, D, t, len(self.data_chunks)
         hd.max_dtype = N.DT_BF16 if self.max_tensors_key.dtype == torch.bfloat16 else N.DT_FP16
         hd.payload_bytes, hd.total_bytes, hd.status = len(payload), total, 0
@@ -142,9 +187,19 @@ class CacheGenGPUEncoderOutput:
             b = tensor.contiguous().cpu().view(torch.uint8).numpy().tobytes()
             buf[off:off + len(b)] = b
 
-        put(lo.off_cdf, self.cdf.reshape(2 * L, C, N.LP))
+        lens = torch.stack([c.bytestream_lengths.reshape(2 * L, C) for c in self.data_chunks])
+        if compact:
+            buf[lo.off_cdf:lo.off_cdf + 2 * L] = bytes(nb)
+            o = lo.off_cdf + ((2 * L + 15) & ~15)
+            for nl in range(2 * L):
+                rec = np.minimum(cnt[nl, :, :nb[nl]], 255).astype(np.uint8).tobytes()
+                buf[o:o + len(rec)] = rec
+                o += len(rec)
+            put(lo.off_lengths, (lens // 2).to(torch.uint8))
+        else:
+            put(lo.off_cdf, self.cdf.reshape(2 * L, C, N.LP))
+            put(lo.off_lengths, lens.to(torch.int32))
         put(lo.off_maxes, torch.stack([self.max_tensors_key.reshape(L, t), self.max_tensors_value.reshape(L, t)]))
-        put(lo.off_lengths, torch.stack([c.bytestream_lengths.reshape(2 * L, C) for c in self.data_chunks]))
         buf[lo.off_payload:] = payload
         return bytes(buf)
 

@@ -49,7 +49,7 @@ class CacheGenDeserializer(Deserializer):
 
     def container_bound(self, L: int, H: int, D: int, chunk_tokens: int) -> int:
         """Upper bound of one container's size (what a receive slab must reserve per chunk)."""
-        return self.codec.out_stride(L, H, D, chunk_tokens)
+        return self.codec.max_container_bytes(L, H, D, chunk_tokens)
 
     def pinned_staging(self, nbytes: int):
         return self.codec.pinned_staging(nbytes)

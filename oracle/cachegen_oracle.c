@@ -129,6 +129,39 @@ void oracle_quantize(const uint16_t* x, int dtype, int L, int t, int C,
  *
  * sym : [NL, t, C] int8 ; cdf : [NL, C, 33] int16
  */
+static void cdf_row(const uint32_t* n, int t, int16_t* o) {
+    double cum = 0.0;
+    float prev = 0.0f; /* cdf_f[i] = cumsum[i-1] */
+    for (int i = 0; i < ORACLE_LP; ++i) {
+        float scaled = prev * 65504.0f;             /* 2^16 - (Lp - 1) */
+        float r = nearbyintf(scaled);
+        o[i] = (int16_t)(uint16_t)((uint32_t)(int32_t)r + (uint32_t)i);
+        float p = (float)n[i] / (float)t;
+        cum += (double)p;
+        prev = (float)cum;
+    }
+}
+
+/* the histogram the CDF is computed from: counts [NL, C, 33] uint32 (entry 32 is always 0) */
+void oracle_counts(const int8_t* sym, int NL, int t, int C, uint32_t* counts) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < (int64_t)NL * C; ++s) {
+        const int nl = (int)(s / C), c = (int)(s % C);
+        uint32_t* n = counts + s * ORACLE_LP;
+        memset(n, 0, sizeof(uint32_t) * ORACLE_LP);
+        for (int tok = 0; tok < t; ++tok) {
+            int v = sym[((int64_t)nl * t + tok) * C + c];
+            if (v >= 0 && v < ORACLE_LP) n[v]++;
+        }
+    }
+}
+
+/* the CDF as a function of the histogram and the token count (what a version-3 container's reader evaluates) */
+void oracle_cdf_from_counts(const uint32_t* counts, int64_t nstreams, int t, int16_t* cdf) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < nstreams; ++s) cdf_row(counts + s * ORACLE_LP, t, cdf + s * ORACLE_LP);
+}
+
 void oracle_cdf(const int8_t* sym, int NL, int t, int C, int16_t* cdf) {
 #pragma omp parallel for schedule(static)
     for (int64_t s = 0; s < (int64_t)NL * C; ++s) {
@@ -139,17 +172,7 @@ void oracle_cdf(const int8_t* sym, int NL, int t, int C, int16_t* cdf) {
             int v = sym[((int64_t)nl * t + tok) * C + c];
             if (v >= 0 && v < ORACLE_LP) n[v]++;
         }
-        int16_t* o = cdf + s * ORACLE_LP;
-        double cum = 0.0;
-        float prev = 0.0f; /* cdf_f[i] = cumsum[i-1] */
-        for (int i = 0; i < ORACLE_LP; ++i) {
-            float scaled = prev * 65504.0f;             /* 2^16 - (Lp - 1) */
-            float r = nearbyintf(scaled);
-            o[i] = (int16_t)(uint16_t)((uint32_t)(int32_t)r + (uint32_t)i);
-            float p = (float)n[i] / (float)t;
-            cum += (double)p;
-            prev = (float)cum;
-        }
+        cdf_row(n, t, cdf + s * ORACLE_LP);
     }
 }
 
@@ -530,4 +553,4 @@ int oracle_set_threads(int n) {
     return omp_get_max_threads();
 }
 
-int oracle_version(void) { return 2; }
+int oracle_version(void) { return 3; }

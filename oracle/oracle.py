@@ -47,6 +47,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_quantize.restype = None
         L.oracle_cdf.argtypes = [vp, i32, i32, i32, vp]
         L.oracle_cdf.restype = None
+        L.oracle_counts.argtypes = [vp, i32, i32, i32, vp]
+        L.oracle_counts.restype = None
+        L.oracle_cdf_from_counts.argtypes = [vp, i64, i32, vp]
+        L.oracle_cdf_from_counts.restype = None
         L.oracle_encode_group.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i64, vp]
         L.oracle_encode_group.restype = i64
         L.oracle_decode_group.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
@@ -122,8 +126,38 @@ def cdf(sym: np.ndarray) -> np.ndarray:
     return out
 
 
+def counts(sym: np.ndarray) -> np.ndarray:
+    """sym int8 [NL,t,C] -> uint32 [NL,C,33]: the histogram calculate_cdf normalises (cachegen_encoder.py:185-196)."""
+    sym = np.ascontiguousarray(sym, np.int8)
+    NL, t, C = sym.shape
+    out = np.empty((NL, C, LP), np.uint32)
+    lib().oracle_counts(_p(sym), NL, t, C, _p(out))
+    return out
+
+
+def cdf_from_counts(cnt: np.ndarray, t: int) -> np.ndarray:
+    """uint32 [..., 33] histogram + token count -> int16 [..., 33] CDF: the second half of oracle_cdf on its own (what
+    the reader of a version-3 container evaluates)."""
+    cnt = np.ascontiguousarray(cnt, np.uint32)
+    out = np.empty(cnt.shape, np.int16)
+    lib().oracle_cdf_from_counts(_p(cnt), cnt.size // LP, int(t), _p(out))
+    return out
+
+
 CODER_AC = 0     # B2KV container version 1: torchac-lineage arithmetic coder
 CODER_RANS = 1   # B2KV container version 2: rANS, 32-bit state / 16-bit renormalisation, same CDF section
+CODER_RANS_COMPACT = 2   # version 3: the same rANS streams; the CDF section is replaced by the histogram it is a function
+                         # of (u8 counts, nb = 2 * (bins // 2) per stream), stream lengths are stored as bytes / 2 in a u8
+
+
+def nb_map(key_bins, value_bins, L: int) -> List[int]:
+    """counts a version-3 container stores per stream of every plane (keys, then values): 2 * (bins // 2)"""
+    return [2 * (int(b) // 2) for b in list(key_bins)[:L]] + [2 * (int(b) // 2) for b in list(value_bins)[:L]]
+
+
+def v3_counts_section(cnt: np.ndarray, nb: List[int]) -> bytes:
+    """uint32 [NL,C,33] -> the counts section of a version-3 container: per plane u8 [C][nb], 256 stored as 255"""
+    return b"".join(np.minimum(cnt[nl, :, :nb[nl]], 255).astype(np.uint8).tobytes() for nl in range(cnt.shape[0]))
 
 
 def encode_group(cdf_i16: np.ndarray, sym: np.ndarray, tok0: int, g: int, coder: int = CODER_AC):
@@ -135,7 +169,7 @@ def encode_group(cdf_i16: np.ndarray, sym: np.ndarray, tok0: int, g: int, coder:
     cap = NL * C * (2 * g + 8)
     out = np.empty(cap, np.uint8)
     lengths = np.empty((NL, C), np.int32)
-    fn = lib().oracle_encode_group_rans if coder == CODER_RANS else lib().oracle_encode_group
+    fn = lib().oracle_encode_group if coder == CODER_AC else lib().oracle_encode_group_rans
     n = fn(_p(cdf_i16), _p(sym), NL, t, tok0, g, C, _p(out), cap, _p(lengths))
     assert n >= 0
     return out[:n].copy(), lengths
@@ -150,7 +184,7 @@ def decode_group(cdf_i16: np.ndarray, bytestream: np.ndarray, lengths: np.ndarra
     bs = np.ascontiguousarray(bytestream, np.uint8)
     ln = np.ascontiguousarray(lengths, np.int32)
     cdf_i16 = np.ascontiguousarray(cdf_i16, np.int16)
-    if coder == CODER_RANS:
+    if coder != CODER_AC:
         bad = lib().oracle_decode_group_rans(_p(cdf_i16), _p(bs), _p(ln), NL, t, tok0, g, C, _p(out_sym))
         assert bad == 0, f"{bad} rANS streams did not return to the initial state"
     else:
@@ -174,7 +208,8 @@ def dequantize(sym_u8: np.ndarray, maxes: np.ndarray, max_dtype: int, key_bins, 
 
 def encode_chunk(x_bits: np.ndarray, dtype: int, key_bins, value_bins, coder: int = CODER_AC):
     """Full encode_function (cachegen_encoder.py:266-325) on one chunk [L,2,t,C]:
-    returns dict(cdf, maxes, groups=[(bytestream, lengths, ntokens)], sym)."""
+    returns dict(cdf, maxes, groups=[(bytestream, lengths, ntokens)], sym, counts).  coder = CODER_RANS_COMPACT codes
+    the same streams as CODER_RANS; the dict's `counts` is what such a container stores in place of `cdf`."""
     sym, maxes = quantize(x_bits, dtype, key_bins, value_bins)
     c = cdf(sym)
     t = sym.shape[1]
@@ -183,7 +218,7 @@ def encode_chunk(x_bits: np.ndarray, dtype: int, key_bins, value_bins, coder: in
         g = min(GROUP, t - tok0)
         bs, ln = encode_group(c, sym, tok0, g, coder)
         groups.append((bs, ln, g))
-    return dict(cdf=c, maxes=maxes, groups=groups, sym=sym, coder=coder)
+    return dict(cdf=c, maxes=maxes, groups=groups, sym=sym, coder=coder, counts=counts(sym))
 
 
 def decode_chunk(enc: dict, max_dtype: int, key_bins, value_bins, out_dtype: int) -> np.ndarray:

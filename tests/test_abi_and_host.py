@@ -22,7 +22,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in b200kv.h but not exported"
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
-    assert L.b200kv_version() == 3
+    assert L.b200kv_version() == 4
 
 
 def test_layout_arithmetic():
@@ -33,6 +33,20 @@ def test_layout_arithmetic():
     assert lo.off_payload == lo.off_lengths + 64 * 4096 * 4
     with pytest.raises(N.NativeError):
         N.container_layout(0, 1, 1, 1)
+    # compact container (version 3): nb map, u8 counts per plane (nb = 2 * (bins // 2)), maxes, u8 half-lengths
+    kb, vb = [32.0] * 10 + [16.0] * 22, [32.0] * 2 + [16.0] * 30
+    lo = N.container_layout(32, 32, 128, 256, N.CODER_RANS_COMPACT, kb, vb)
+    nbsum = 12 * 32 + 52 * 16
+    assert sum(N.nb_map(kb, vb, 32)) == nbsum
+    assert lo.off_cdf == 64
+    assert lo.off_maxes == 64 + 64 + 4096 * nbsum
+    assert lo.off_lengths == lo.off_maxes + 64 * 256 * 2
+    assert lo.off_payload == lo.fixed_bytes == lo.off_lengths + 64 * 4096
+    assert lo.fixed_bytes < 0.32 * N.container_layout(32, 32, 128, 256).fixed_bytes
+    with pytest.raises(N.NativeError):
+        N.container_layout(32, 32, 128, 257, N.CODER_RANS_COMPACT, kb, vb)       # one <= 256-token group only
+    with pytest.raises(N.NativeError):
+        N.container_layout(2, 1, 8, 16, N.CODER_RANS_COMPACT, [2.0, 2.0], [32.0, 32.0])
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -137,3 +151,71 @@ def test_container_view_roundtrip_from_oracle_stream(golden):
         assert torch.equal(a.bytestream_lengths, b.bytestream_lengths)
     with pytest.raises(ValueError):
         CacheGenGPUEncoderOutput.from_bytes(b"\0" * 100)
+
+
+@pytest.mark.parametrize("name", ["bf16_t1", "bf16_t40", "bf16_t236", "bf16_t256", "bf16_uniform_t16", "fp16_uniform_t128"])
+def test_compact_container_rebuilds_the_reference_cdf(golden, name):
+    """A version-3 container stores the symbol histogram instead of the CDF rows.  Assembled on the host from oracle
+    output, it parses back to the CDF tensor THE REFERENCE'S OWN calculate_cdf spec produced (goldens), to the same
+    lengths and bytestreams; a repeated symbol filling a whole 256-token stream (count 256 in a byte) survives."""
+    import numpy as np
+    from lmcache_b200.codec import parse_header
+    from lmcache_b200.storage_backend.serde.cachegen_basics import (CacheGenGPUBytestream, CacheGenGPUEncoderOutput,
+                                                                     cdf_from_counts)
+    from oracle import oracle as O
+    x = golden[f"{name}/x"]
+    dt = int(golden[f"{name}/dtype"][0])
+    L, _, t, H, D = x.shape
+    kb, vb = golden["key_bins"], golden["value_bins"]
+    enc = O.encode_chunk(x.reshape(L, 2, t, H * D), dt, kb, vb, O.CODER_RANS_COMPACT)
+    assert np.array_equal(cdf_from_counts(enc["counts"], t), golden[f"{name}/cdf"])       # product host helper vs reference
+    assert np.array_equal(O.cdf_from_counts(enc["counts"], t), golden[f"{name}/cdf"])     # oracle vs reference
+    half = torch.bfloat16 if dt == 0 else torch.float16
+    mk = torch.from_numpy(enc["maxes"][0].view(np.int16)).view(half).reshape(L, t, 1)
+    mv = torch.from_numpy(enc["maxes"][1].view(np.int16)).view(half).reshape(L, t, 1)
+    nb = O.nb_map(kb, vb, L)
+    obj = CacheGenGPUEncoderOutput(
+        [CacheGenGPUBytestream(torch.from_numpy(b), torch.from_numpy(ln), g) for b, ln, g in enc["groups"]],
+        torch.from_numpy(enc["cdf"]), mk, mv, H, D, N.CODER_RANS_COMPACT, torch.from_numpy(enc["counts"].astype(np.int32)), nb)
+    bs = obj.to_bytes()
+    hd = parse_header(bs)
+    assert hd.version == 3 and hd.nb == nb
+    v2 = CacheGenGPUEncoderOutput(obj.data_chunks, obj.cdf, mk, mv, H, D, N.CODER_RANS).to_bytes()
+    assert len(bs) < len(v2)
+    back = CacheGenGPUEncoderOutput.from_bytes(bs)
+    assert back.coder == N.CODER_RANS_COMPACT
+    assert np.array_equal(back.cdf.numpy(), golden[f"{name}/cdf"])
+    assert torch.equal(back.max_tensors_key, mk) and torch.equal(back.max_tensors_value, mv)
+    for a, b in zip(back.data_chunks, obj.data_chunks):
+        assert a.ntokens == b.ntokens and torch.equal(a.bytestream, b.bytestream)
+        assert torch.equal(a.bytestream_lengths, b.bytestream_lengths.to(torch.int32))
+    # a damaged nb map or a truncated blob is a ValueError (a miss), never a wrong layout
+    bad = bytearray(bs)
+    bad[64] = 33
+    with pytest.raises(ValueError):
+        parse_header(bytes(bad))
+    with pytest.raises(ValueError):
+        parse_header(bs[:-1])
+
+
+def test_compact_container_count_of_256():
+    """all 256 tokens of a stream on one symbol: the count does not fit a byte, is stored as 255 and restored"""
+    import numpy as np
+    from lmcache_b200.storage_backend.serde.cachegen_basics import (CacheGenGPUBytestream, CacheGenGPUEncoderOutput)
+    from oracle import oracle as O
+    L, t, H, D = 2, 256, 1, 8
+    kb = vb = np.array([32.0, 16.0], np.float32)
+    x = np.zeros((L, 2, t, H * D), np.float32)
+    x[..., 0] = 1.0                      # channel 0 pins every row maximum: constant symbols everywhere
+    x[0, 0, ::2, 3] = -0.5               # ... except one stream with two symbols
+    enc = O.encode_chunk(O.f32_to_bf16_bits(x), 0, kb, vb, O.CODER_RANS_COMPACT)
+    assert enc["counts"].max() == 256
+    mk = torch.from_numpy(enc["maxes"][0].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
+    mv = torch.from_numpy(enc["maxes"][1].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
+    obj = CacheGenGPUEncoderOutput(
+        [CacheGenGPUBytestream(torch.from_numpy(b), torch.from_numpy(ln), g) for b, ln, g in enc["groups"]],
+        torch.from_numpy(enc["cdf"]), mk, mv, H, D, N.CODER_RANS_COMPACT, torch.from_numpy(enc["counts"].astype(np.int32)),
+        O.nb_map(kb, vb, L))
+    back = CacheGenGPUEncoderOutput.from_bytes(obj.to_bytes())
+    assert np.array_equal(back.counts.numpy(), enc["counts"].astype(np.int32))
+    assert np.array_equal(back.cdf.numpy(), enc["cdf"])

@@ -64,7 +64,9 @@ if role == "writer":
         mk = torch.from_numpy(enc["maxes"][0].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
         mv = torch.from_numpy(enc["maxes"][1].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
         raw = CacheGenGPUEncoderOutput([CacheGenGPUBytestream(torch.from_numpy(b), torch.from_numpy(ln), g) for b, ln, g in enc["groups"]],
-                                       torch.from_numpy(enc["cdf"]), mk, mv, H, D, coder).to_bytes()
+                                       torch.from_numpy(enc["cdf"]), mk, mv, H, D, coder,
+                                       torch.from_numpy(enc["counts"].astype(np.int32)), O.nb_map(kb, vb, L)).to_bytes()
+        assert raw[4] == coder + 1
         conn.set(key, raw)
     assert conn.exists(keys[-1]) or True          # one round trip: the server has consumed the PUTs before it
     print(json.dumps({{"stored": len(keys)}}))
@@ -89,7 +91,7 @@ conn.close()
 '''
 
 
-@pytest.mark.parametrize("coder", [0, 1])
+@pytest.mark.parametrize("coder", [0, 1, 2])
 @pytest.mark.parametrize("server_kind", ["native", "python"])
 def test_c4_flow_two_processes_one_server(coder, server_kind, tmp_path):
     import json

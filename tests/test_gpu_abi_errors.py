@@ -39,13 +39,14 @@ def test_encode_argument_validation():
         return lib.b200kv_encode_chunks(a["kv"], a["tok"], a["n"], a["ct"], a["last"], a["kb"], a["vb"], a["coder"], a["out"],
                                         a["stride"], a["sizes"], a["ws"], a["wsb"], sp)
 
-    for coder in (N.CODER_AC, N.CODER_RANS):
+    for coder in (N.CODER_AC, N.CODER_RANS, N.CODER_RANS_COMPACT):
         assert call(coder=coder) == 0
         torch.cuda.synchronize()
-        assert int(sizes[0]) > lo.fixed_bytes
+        assert int(sizes[0]) > N.container_layout(L, H, D, t, coder, bins, bins).fixed_bytes
         assert N.Header.from_buffer_copy(out[:64].cpu().numpy().tobytes()).version == coder + 1
     for bad in (dict(n=0), dict(ct=0), dict(last=t + 1), dict(out=None), dict(out=out.data_ptr() + 1), dict(wsb=16),
-                dict(kb=None), dict(tok=-1), dict(stride=64), dict(coder=2), dict(coder=-1)):
+                dict(kb=None), dict(tok=-1), dict(stride=64), dict(coder=3), dict(coder=-1),
+                dict(coder=N.CODER_RANS_COMPACT, ct=257, last=257)):      # the compact container holds <= 256 tokens
         rc = call(**bad)
         assert rc < 0 and len(N.last_error()) > 0, bad
     bad_desc = _desc(kv, L, H, D, dtype=7)
@@ -54,7 +55,7 @@ def test_encode_argument_validation():
     assert call(kb=bad_bins) < 0
 
 
-@pytest.mark.parametrize("coder", [0, 1])
+@pytest.mark.parametrize("coder", [0, 1, 2])
 def test_slot_too_small_sets_status_not_corruption(coder):
     """A payload that does not fit its slot must not be written past it; the header carries a nonzero status."""
     from lmcache_b200 import _native as N
@@ -64,7 +65,7 @@ def test_slot_too_small_sets_status_not_corruption(coder):
     kv = torch.rand(L, 2, t, H, D, device="cuda").to(torch.bfloat16)       # ~5 bits/symbol: a real payload
     d = _desc(kv, L, H, D)
     bins = N.float_array([32.0] * L)
-    lo = N.container_layout(L, H, D, t)
+    lo = N.container_layout(L, H, D, t, coder, bins, bins)
     stride = lo.fixed_bytes + 256                                           # far too small for the payload
     guard = 4096
     out = torch.full((stride + guard,), 0xAB, dtype=torch.uint8, device="cuda")
@@ -101,6 +102,12 @@ def test_decode_and_misc_validation():
         a = list(ok)
         a[i] = bad
         assert lib.b200kv_decode_chunks(*a) < 0 and N.last_error(), i
+    # a compact container cannot hold more than one 256-token group
+    a = list(ok)
+    a[4], a[8] = N.i32_array([257]), N.CODER_RANS_COMPACT
+    assert lib.b200kv_decode_chunks(*a) < 0 and N.last_error()
+    with pytest.raises(ValueError):
+        N.container_layout(L, H, D, t, N.CODER_RANS_COMPACT)           # the compact layout needs the bins
     assert lib.b200kv_sha256_chain(buf.data_ptr(), 3, N.i64_array([0, 4]), 1, 4, buf.data_ptr(), sp) < 0     # elem_size
     assert lib.b200kv_sha256_chain(buf.data_ptr(), 8, N.i64_array([4, 0]), 1, 4, buf.data_ptr(), sp) < 0     # decreasing offsets
     assert lib.b200kv_sha256_chain(buf.data_ptr(), 8, N.i64_array([0, 0]), 1, 4, buf.data_ptr(), sp) == 0    # empty: no-op

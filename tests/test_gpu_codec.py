@@ -30,30 +30,50 @@ def _eq_nan(a: np.ndarray, b: np.ndarray, dt: int) -> bool:
     return bool(np.all((a == b) | both_nan))
 
 
-@pytest.fixture(scope="module", params=["rans", "ac"])
+@pytest.fixture(scope="module", params=["rans_compact", "rans", "ac"])
 def codec(request):
-    """both payload formats: container version 2 (rANS, the default) and version 1 (arithmetic coder)"""
+    """all container formats: version 3 (rANS + symbol counts, the default), 2 (rANS + CDF rows), 1 (arithmetic coder)"""
     from lmcache_b200.codec import CacheGenCodec
     return CacheGenCodec(MODEL, coder=request.param)
 
 
 def _oenc(codec, *args):
-    """the oracle's encode with the coder under test"""
-    return O.encode_chunk(*args, coder=codec.coder)
+    """the oracle's encode with the coder under test (the compact container holds chunks of <= 256 tokens only)"""
+    return O.encode_chunk(*args, coder=codec.coder_for(args[0].shape[2]))
 
 
 def _sections(raw: bytes, L, H, D, t):
     from lmcache_b200 import _native as N
     from lmcache_b200.codec import parse_header
+    from lmcache_b200.codec import container_layout_of
     hd = parse_header(raw)
     assert (hd.L, hd.H, hd.D, hd.ntokens) == (L, H, D, t)
-    lo = N.container_layout(L, H, D, t)
+    lo = container_layout_of(hd)
     C = H * D
     G = (t + 255) // 256
     a = np.frombuffer(raw, np.uint8)
-    cdf = a[lo.off_cdf: lo.off_cdf + 2 * L * C * 33 * 2].view(np.int16).reshape(2 * L, C, 33)
+    if hd.version == 3:
+        # compact container: the histogram stands in for the CDF (rebuilt here with the ORACLE's arithmetic and compared
+        # with the reference-made goldens by the callers); stream lengths are stored halved in one byte
+        kb, vb = O.make_bins(MODEL)
+        nb = O.nb_map(kb, vb, L)
+        assert list(a[lo.off_cdf: lo.off_cdf + 2 * L]) == nb == hd.nb
+        cnt = np.zeros((2 * L, C, 33), np.uint32)
+        o = lo.off_cdf + ((2 * L + 15) & ~15)
+        for nl in range(2 * L):
+            rec = a[o:o + C * nb[nl]].reshape(C, nb[nl]).astype(np.uint32)
+            short = rec.sum(axis=1) == t - 1
+            rec[short] += (rec[short] == 255)
+            assert np.all(rec.sum(axis=1) == t)
+            cnt[nl, :, :nb[nl]] = rec
+            o += C * nb[nl]
+        assert o <= lo.off_maxes
+        cdf = O.cdf_from_counts(cnt, t)
+        lengths = a[lo.off_lengths: lo.off_lengths + G * 2 * L * C].astype(np.int32).reshape(G, 2 * L, C) * 2
+    else:
+        cdf = a[lo.off_cdf: lo.off_cdf + 2 * L * C * 33 * 2].view(np.int16).reshape(2 * L, C, 33)
+        lengths = a[lo.off_lengths: lo.off_lengths + G * 2 * L * C * 4].view(np.int32).reshape(G, 2 * L, C)
     maxes = a[lo.off_maxes: lo.off_maxes + 2 * L * t * 2].view(np.uint16).reshape(2, L, t)
-    lengths = a[lo.off_lengths: lo.off_lengths + G * 2 * L * C * 4].view(np.int32).reshape(G, 2 * L, C)
     payload = a[lo.off_payload: lo.off_payload + hd.payload_bytes]
     assert hd.total_bytes == lo.off_payload + hd.payload_bytes == len(raw)
     return cdf, maxes, lengths, payload
@@ -81,6 +101,12 @@ def test_encode_container_bit_exact_vs_oracle_and_goldens(codec, golden, name):
     enc = _oenc(codec, x.reshape(L, 2, t, H * D), dt, kb, vb)
     assert np.array_equal(np.stack([ln for _, ln, _ in enc["groups"]]), lengths)
     assert np.array_equal(np.concatenate([b for b, _, _ in enc["groups"]]), payload)
+    if raw[4] == 3:     # the stored histogram itself, byte for byte
+        from lmcache_b200.codec import container_layout_of, parse_header
+        lo = container_layout_of(parse_header(raw))
+        want = O.v3_counts_section(enc["counts"], O.nb_map(kb, vb, L))
+        o = lo.off_cdf + ((2 * L + 15) & ~15)
+        assert bytes(raw[o:o + len(want)]) == want
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -103,11 +129,11 @@ def test_decode_bit_exact_vs_reference_goldens(codec, golden, name, fmt):
     assert _eq_nan(_tensor_bits(out), want, 0 if fmt == "vllm" else 1)
 
 
-def test_oracle_made_container_decodes_on_gpu(codec, golden):
+@pytest.mark.parametrize("name", ["bf16_t300", "bf16_t236", "bf16_t256"])
+def test_oracle_made_container_decodes_on_gpu(codec, golden, name):
     """Decoder accepts a container assembled entirely on the CPU by the oracle (wire compatibility both ways)."""
     from lmcache_b200.codec import KvView
     from lmcache_b200.storage_backend.serde.cachegen_basics import CacheGenGPUBytestream, CacheGenGPUEncoderOutput
-    name = "bf16_t300"
     x = golden[f"{name}/x"]
     L, _, t, H, D = x.shape
     enc = _oenc(codec, x.reshape(L, 2, t, H * D), 0, golden["key_bins"], golden["value_bins"])
@@ -115,7 +141,9 @@ def test_oracle_made_container_decodes_on_gpu(codec, golden):
     mv = torch.from_numpy(enc["maxes"][1].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
     raw = CacheGenGPUEncoderOutput(
         [CacheGenGPUBytestream(torch.from_numpy(b), torch.from_numpy(ln), g) for b, ln, g in enc["groups"]],
-        torch.from_numpy(enc["cdf"]), mk, mv, H, D, codec.coder).to_bytes()
+        torch.from_numpy(enc["cdf"]), mk, mv, H, D, codec.coder_for(t), torch.from_numpy(enc["counts"].astype(np.int32)),
+        O.nb_map(golden["key_bins"], golden["value_bins"], L)).to_bytes()
+    assert raw[4] == codec.coder_for(t) + 1
     out = torch.zeros((L, 2, t, H, D), dtype=torch.bfloat16, device="cuda")
     codec.decode([raw], KvView.from_blob(out, "vllm"), [0])
     torch.cuda.synchronize()
@@ -298,8 +326,8 @@ def test_baseline_block_full_size_properties(codec):
     import zlib
     import ref_torch
     from lmcache_b200.codec import KvView
-    if codec.coder == 0:
-        pytest.skip("the 4 GiB block runs once, on the default coder")
+    if codec.coder != 2:
+        pytest.skip("the 4 GiB block runs once, on the default container")
     L, H, D, T, cs = 32, 32, 128, 8192, 256
     g = torch.Generator(device="cuda").manual_seed(2)
     sigma = torch.exp(0.5 * torch.randn((L, 2, 1, H * D), device="cuda", generator=g)).clamp(0.1, 8.0)
@@ -487,8 +515,9 @@ def test_torch_serde_gpu_lossless():
     assert back.device.type == "cpu" and torch.equal(back, t.cpu())
 
 
+@pytest.mark.parametrize("coder", ["rans_compact", "rans"])
 @pytest.mark.parametrize("kind", ["peaked", "uniform"])
-def test_kernel_variants_agree(kind, monkeypatch):
+def test_kernel_variants_agree(kind, coder, monkeypatch):
     """the library's measurement knobs select kernel variants that must be interchangeable: the TMA-staged and the
     register-staged fused encoder produce byte-identical containers, the row-major and the transposed decoder table
     produce identical KV (the product picks by eligibility / by the containers' bits per symbol)"""
@@ -501,7 +530,7 @@ def test_kernel_variants_agree(kind, monkeypatch):
     else:
         kv = torch.rand((L, 2, T, H, D), device="cuda", generator=g) * 2 - 1
     kv = kv.to(torch.bfloat16)
-    codec = CacheGenCodec(MODEL, coder="rans")
+    codec = CacheGenCodec(MODEL, coder=coder)
     view = KvView.from_blob(kv, "vllm")
     outs, decs = {}, {}
     for path in ("tma", "legacy"):

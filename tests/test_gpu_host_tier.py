@@ -211,9 +211,10 @@ def test_disk_tier_store_restart_retrieve(tmp_path, autorelease):
     assert len(files) == 6 and not [f for f in os.listdir(d) if f.endswith(".tmp")]
     raw = sum(k.numel() * 2 * 2 for k, _ in kv)
     assert sum(os.path.getsize(d + f) for f in files) < 0.75 * raw          # containers, not raw blobs
+    # restart: damage the file of chunk 3 (truncate), drop a foreign file in
+    victim = engine.engine_._key_to_path(engine._make_key(engine._prefix_hash(tokens)[3], "vllm"))
+    assert os.path.basename(victim) in files
     engine.close()
-    # restart: damage one file (truncate), drop a foreign file in
-    victim = d + files[3]
     with open(victim, "r+b") as f:
         f.truncate(os.path.getsize(victim) // 2)
     open(d + "notes.b2kv", "wb").write(b"not a container")
