@@ -35,9 +35,10 @@ extern "C" {
                                     * 4: compact container (B200KV_CODER_RANS_COMPACT), b200kv_container_layout_v */
 #define B200KV_CODER_AC 0          /* payload = torchac-lineage arithmetic coder; container version 1 */
 #define B200KV_CODER_RANS 1        /* payload = rANS, 32-bit state / 16-bit renormalisation; container version 2 */
-#define B200KV_CODER_RANS_COMPACT 2 /* rANS payload as in version 2, compact side information; container version 3 (chunks
-                                     * of <= 256 tokens): the per-stream CDF rows (66 B) are replaced by the symbol counts
-                                     * they are a function of (16 or 32 B), the int32 stream lengths by one byte */
+#define B200KV_CODER_RANS_COMPACT 2 /* rANS as in version 2, compact side information; container version 3 (chunks of
+                                     * <= 256 tokens): the per-stream CDF row (66 B) is replaced by the symbol histogram it
+                                     * is a function of, carried sparsely in front of the stream's rANS bytes (~5 B at the
+                                     * headline entropy), the int32 stream length by one byte */
 #define B200KV_CONTAINER_VERSION(coder) ((coder) + 1) /* "B2KV" wire container version (b200kv_header.version) */
 #define B200KV_ENCODE_HINT_HIGH_ENTROPY 0x100 /* OR into `coder` of b200kv_encode_chunks: the caller expects more than ~2.7
                                                * payload bits per symbol (e.g. the previous call's sizes said so); selects the
@@ -77,13 +78,15 @@ typedef struct b200kv_kv_desc {
  * un-vendored torchac_cuda wheel, so the bitstream is this build's own.  v1 = 32-bit binary arithmetic
  * coder (torchac lineage, MSB-first bits); v2 = rANS over the same 16-bit CDFs: LE32 final state, then LE16
  * renormalisation words in decode order (normative description: lmcache_b200/csrc/ac_core.cuh).
- * Version 3 (one <= 256-token group per container) keeps v2's bytestream and stores the rest compactly:
- *   header | nb u8[2L] (pad to 16) | counts u8[plane][C][nb(plane)] | maxes | half-lengths u8[2L][C] | bytestream
- * nb(plane) = 2 * (bins(plane) // 2) (16 or 32 for the reference's bin tables); counts[c][s] = how many of the chunk's
- * tokens quantise to symbol s in channel c, a count of 256 stored as 255 (then the counts sum to ntokens - 1).  The CDF
- * the reference keeps (cachegen_encoder.py:287-290) is a function of these counts and ntokens:
+ * Version 3 (one <= 256-token group per container) has no CDF section:
+ *   header | nb u8[2L] (pad to 16) | maxes | half-lengths u8[2L][C] | bytestream
+ * nb(plane) = 2 * (bins(plane) // 2) = the symbols a plane can emit (16 or 32 for the reference's bin tables).  Every
+ * stream of the bytestream is  [mask: ceil(nb / 8) bytes LE, bit s set <=> symbol s occurs in the stream]
+ *   [one count byte per set bit, ascending, except the LAST set bit, whose count is ntokens - (sum of the others)]
+ *   [a zero byte if that makes the length even] [the version-2 rANS stream];  half-lengths[c] = bytes of all that / 2.
+ * The CDF the reference keeps (cachegen_encoder.py:287-290) is a function of these counts n_s and t = ntokens:
  *   cdf[i] = int16(rint(fl32(sum_{k<i} fl32(n_k / t), accumulated in double) * 65504) + i)      (in-tree spec :95-126)
- * so CacheGenGPUEncoderOutput.from_bytes rebuilds the identical tensor; half-lengths[c] = bytes of the stream / 2. */
+ * so CacheGenGPUEncoderOutput.from_bytes rebuilds the identical tensor, and the decoder evaluates it on the device. */
 typedef struct b200kv_header {
     uint32_t magic, version;
     uint32_t L, H, D;
@@ -108,11 +111,8 @@ const char* b200kv_last_error(void);
 int b200kv_device_count(void);
 
 int b200kv_container_layout(int32_t L, int32_t H, int32_t D, int32_t ntokens, b200kv_layout* out);   /* versions 1, 2 */
-/* Same for the container `coder` produces; key_bins / value_bins (HOST float[L]) are needed for
- * B200KV_CODER_RANS_COMPACT only, whose counts section depends on them (off_cdf is then the nb map, the counts start
- * at off_cdf + align16(2L)), and may be NULL otherwise. */
-int b200kv_container_layout_v(int32_t L, int32_t H, int32_t D, int32_t ntokens, int32_t coder, const float* key_bins,
-                              const float* value_bins, b200kv_layout* out);
+/* Same for the container `coder` produces (B200KV_CODER_RANS_COMPACT: off_cdf is the nb map, there is no CDF section). */
+int b200kv_container_layout_v(int32_t L, int32_t H, int32_t D, int32_t ntokens, int32_t coder, b200kv_layout* out);
 
 /* Bytes of device scratch b200kv_encode_chunks / b200kv_decode_chunks need for a call. */
 int64_t b200kv_encode_workspace_bytes(int32_t L, int32_t H, int32_t D, int32_t chunk_tokens, int32_t n_chunks,

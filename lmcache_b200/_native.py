@@ -18,7 +18,8 @@ DT_BF16 = 0
 DT_FP16 = 1
 CODER_AC = 0       # container version 1: arithmetic coder
 CODER_RANS = 1     # container version 2: rANS
-CODER_RANS_COMPACT = 2   # container version 3: rANS payload, symbol counts instead of CDF rows, one-byte stream lengths
+CODER_RANS_COMPACT = 2   # container version 3: rANS streams that carry their own histogram (no CDF section), one-byte lengths
+HDR_MAX = 36             # longest version-3 stream header (4 mask bytes + 31 counts + 1 pad)
 CODERS = {"ac": CODER_AC, "rans": CODER_RANS, "rans_compact": CODER_RANS_COMPACT}
 ENCODE_HINT_HIGH_ENTROPY = 0x100   # B200KV_ENCODE_HINT_HIGH_ENTROPY
 LP = 33
@@ -73,7 +74,7 @@ SIGNATURES = {
     "b200kv_last_error": (ctypes.c_char_p, []),
     "b200kv_device_count": (c_i32, []),
     "b200kv_container_layout": (c_i32, [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Layout)]),
-    "b200kv_container_layout_v": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, ctypes.POINTER(Layout)]),
+    "b200kv_container_layout_v": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(Layout)]),
     "b200kv_encode_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "b200kv_decode_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32]),
     "b200kv_encode_chunks": (c_i32, [ctypes.POINTER(KvDesc), c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i64,
@@ -163,24 +164,15 @@ def require_cuda() -> None:
                                f"There is no CPU fallback.")
 
 
-def container_layout(L: int, H: int, D: int, ntokens: int, coder: int = CODER_RANS, key_bins=None,
-                     value_bins=None) -> Layout:
-    """Section offsets of the container `coder` produces.  The compact container (CODER_RANS_COMPACT) needs the
-    per-layer bins -- or, equally, the nb map a container carries (nb = 2 * (bins // 2) per plane, keys then values)."""
+def container_layout(L: int, H: int, D: int, ntokens: int, coder: int = CODER_RANS) -> Layout:
+    """Section offsets of the container `coder` produces (versions 1 and 2 share a layout)."""
     lo = Layout()
-    if coder == CODER_RANS_COMPACT:
-        if key_bins is None or value_bins is None:
-            raise ValueError("the compact container's layout depends on the bins")
-        kb = key_bins if isinstance(key_bins, ctypes.Array) else float_array(list(key_bins)[:L])
-        vb = value_bins if isinstance(value_bins, ctypes.Array) else float_array(list(value_bins)[:L])
-        check(lib().b200kv_container_layout_v(L, H, D, ntokens, coder, kb, vb, ctypes.byref(lo)), "container_layout")
-    else:
-        check(lib().b200kv_container_layout(L, H, D, ntokens, ctypes.byref(lo)), "container_layout")
+    check(lib().b200kv_container_layout_v(L, H, D, ntokens, coder, ctypes.byref(lo)), "container_layout")
     return lo
 
 
 def nb_map(key_bins, value_bins, L: int) -> list:
-    """counts stored per stream of every plane (keys then values) in a compact container: 2 * (bins // 2)"""
+    """symbols a stream of every plane (keys then values) can emit = the nb map of a compact container: 2 * (bins // 2)"""
     return [2 * (int(b) // 2) for b in list(key_bins)[:L]] + [2 * (int(b) // 2) for b in list(value_bins)[:L]]
 
 

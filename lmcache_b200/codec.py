@@ -210,17 +210,15 @@ def parse_header(buf) -> N.Header:
 
 
 def container_layout_of(hd: "N.Header") -> "N.Layout":
-    """Section offsets of a parsed container (version 3: from the nb map parse_header / check_header attached)."""
-    if hd.version == 3:
-        return N.container_layout(hd.L, hd.H, hd.D, hd.ntokens, N.CODER_RANS_COMPACT, hd.nb[:hd.L], hd.nb[hd.L:])
-    return N.container_layout(hd.L, hd.H, hd.D, hd.ntokens)
+    """Section offsets of a parsed container."""
+    return N.container_layout(hd.L, hd.H, hd.D, hd.ntokens, int(hd.version) - 1)
 
 
 def check_header(hd: "N.Header", nb: Optional[Sequence[int]] = None) -> None:
     """Structural checks that make a damaged blob a miss (ValueError) instead of bad device addresses: the section
-    offsets follow from (L, H, D, ntokens) -- and, for the compact container (version 3), from its nb map, the 2L bytes
-    after the header, passed as `nb` and attached to the header as `hd.nb` -- so total_bytes must be exactly fixed
-    sections + payload."""
+    offsets follow from (L, H, D, ntokens, version), so total_bytes must be exactly fixed sections + payload.  A compact
+    container (version 3) also carries its nb map -- the 2L bytes after the header, passed as `nb` and attached to the
+    header as `hd.nb`: the symbols per plane its writer's bin table allowed."""
     if not (0 < hd.L <= N.MAX_PLANES // 2 and hd.H > 0 and hd.D > 0 and hd.ntokens > 0):
         raise ValueError("B2KV header carries an impossible shape")
     if hd.max_dtype not in (N.DT_BF16, N.DT_FP16):
@@ -341,7 +339,7 @@ class CacheGenCodec:
         return self.coder
 
     def layout(self, L: int, H: int, D: int, chunk_tokens: int) -> "N.Layout":
-        return N.container_layout(L, H, D, chunk_tokens, self.coder_for(chunk_tokens), self._kb, self._vb)
+        return N.container_layout(L, H, D, chunk_tokens, self.coder_for(chunk_tokens))
 
     def accepts(self, hd: "N.Header") -> bool:
         """Can this codec decode the container?  A compact container must have been written with this model's bins."""
@@ -363,7 +361,8 @@ class CacheGenCodec:
         so a stream costs <= 8 bits/symbol (+ flush); larger chunks may reach 16 bits/symbol."""
         lo = self.layout(L, H, D, chunk_tokens)
         if chunk_tokens <= N.GROUP_TOKENS:
-            return (lo.fixed_bytes + 2 * L * H * D * (chunk_tokens + 4) + 16 + 15) & ~15
+            hdr = N.HDR_MAX if self.coder_for(chunk_tokens) == N.CODER_RANS_COMPACT else 0
+            return (lo.fixed_bytes + 2 * L * H * D * (chunk_tokens + 4 + hdr) + 16 + 15) & ~15
         return lo.max_total_bytes
 
     # ------------------------------------------------------------------ encode

@@ -773,19 +773,20 @@ struct Layout {
     int32_t ngroups;
 };
 
-// Containers of version 1 / 2 (nbsum == 0):  header | cdf i16[2L][C][33] | maxes | lengths i32[G][2L][C] | payload.
-// Compact container, version 3 (nbsum = sum over the 2L planes of nb(plane) = 2 * (bins // 2), chunks of <= 256 tokens):
-//   header | nb u8[2L] | counts u8[plane][C][nb(plane)] | maxes | half-lengths u8[2L][C] | payload
-// i.e. the per-stream CDF is replaced by the symbol histogram it is a function of (CdfAccum: cdf = f(counts, t)), and
-// a stream's byte length L (even, <= 194) by L / 2.  off_cdf is the first byte after the header in both (the nb map in
-// version 3); counts start at off_cdf + align16(2L).
-B2_HD Layout make_layout(int L, int C, int t, int nbsum = 0) {
+// Containers of version 1 / 2:  header | cdf i16[2L][C][33] | maxes | lengths i32[G][2L][C] | payload.
+// Compact container, version 3 (chunks of <= 256 tokens, i.e. one group):
+//   header | nb u8[2L] (pad to 16) | maxes | half-lengths u8[2L][C] | payload
+// The per-stream CDF row is gone: the CDF is a function of the stream's symbol histogram and the token count (CdfAccum),
+// and every stream carries that histogram in front of its rANS bytes (stream header, below); a stream's byte length
+// (even, <= 230) is stored halved in one byte.  nb(plane) = 2 * (bins // 2) is the number of symbols a plane can emit.
+// off_cdf is the first byte after the header in both layouts (the nb map in version 3).
+B2_HD Layout make_layout(int L, int C, int t, int compact = 0) {
     Layout lo;
     const int64_t NL = 2 * (int64_t)L;
     lo.ngroups = (t + kGroup - 1) / kGroup;
     lo.off_cdf = 64;
-    if (nbsum > 0) {
-        lo.off_maxes = align16(lo.off_cdf + align16(NL) + (int64_t)C * nbsum);
+    if (compact) {
+        lo.off_maxes = align16(lo.off_cdf + NL);
         lo.off_lengths = align16(lo.off_maxes + NL * t * 2);
         lo.off_payload = align16(lo.off_lengths + (int64_t)lo.ngroups * NL * C);
     } else {
@@ -796,8 +797,36 @@ B2_HD Layout make_layout(int L, int C, int t, int nbsum = 0) {
     return lo;
 }
 
-// compact container: a symbol count as stored (256 -- a stream of one repeated symbol in a full chunk -- is stored as
-// 255 and recognised by the stream's counts summing to t - 1)
-B2_HD uint32_t count_to_byte(uint32_t n) { return n < 255u ? n : 255u; }
+// ---------------------------------------------------------------- version-3 stream header
+// stream = [mask: ceil(nb / 8) bytes, little-endian, bit s set <=> symbol s occurs]
+//          [one count byte per set bit, ascending, EXCEPT the last set bit: its count is t - (sum of the others)]
+//          [one zero byte if the header length is odd]  [LE32 rANS state] [LE16 renormalisation words ...]
+// Counts that are stored are <= 255 (two or more symbols share <= 256 tokens); a lone symbol's count (up to 256) is
+// implied.  Header length <= 4 + 31 + 1 = 36 bytes.
+constexpr int kHdrMax = 36;
+B2_HD int hdr_mask_bytes(int nb) { return (nb + 7) >> 3; }
+B2_HD uint32_t hdr_len(uint32_t mask, int nb) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t nz = (uint32_t)__popc(mask);
+#else
+    uint32_t nz = 0;
+    for (uint32_t m = mask; m; m &= m - 1u) ++nz;
+#endif
+    const uint32_t h = (uint32_t)hdr_mask_bytes(nb) + (nz ? nz - 1u : 0u);
+    return h + (h & 1u);
+}
+// Host-side restatement (tests): build the header of one stream from its counts; returns its length.
+inline uint32_t hdr_write_host(uint8_t* dst, const uint32_t* cnt, int nb) {
+    uint32_t mask = 0;
+    for (int i = 0; i < nb; ++i) mask |= (cnt[i] ? 1u : 0u) << i;
+    const int mb = hdr_mask_bytes(nb);
+    for (int b = 0; b < mb; ++b) dst[b] = (uint8_t)(mask >> (8 * b));
+    int last = -1;
+    for (int i = 0; i < nb; ++i) if (cnt[i]) last = i;
+    uint32_t pos = (uint32_t)mb;
+    for (int i = 0; i < nb; ++i) if (cnt[i] && i != last) dst[pos++] = (uint8_t)cnt[i];
+    if (pos & 1u) dst[pos++] = 0;
+    return pos;
+}
 
 }  // namespace b200kv

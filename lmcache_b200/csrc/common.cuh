@@ -34,8 +34,6 @@ void set_error(const std::string& msg);   // thread-local last error (api.cu)
 struct PlaneTable {
     const uint16_t* p[B200KV_MAX_PLANES];
     float maxq[B200KV_MAX_PLANES];       // bins // 2 - 1
-    uint16_t nbpre[B200KV_MAX_PLANES];   // compact container: sum of nb(plane') = 2 * (bins // 2) over the planes before this one
-    int32_t nbsum;                       //   ... and over all planes
 };
 
 // Fill a PlaneTable from a kv_desc + bins; returns 0 or <0 with error set.

@@ -19,6 +19,7 @@
 
 #include <mutex>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -112,23 +113,50 @@ __global__ void __launch_bounds__(128) sha256_expand_kernel(ShaParams P) {
 }
 
 // 64 rounds over precomputed (W + K); state in registers, variables renamed instead of rotated.
-// One chain is one thread.  Every instruction of a round -- three funnel shifts + one LOP3 per Sigma, Ch, Maj, four adds --
-// is an integer-ALU-pipe instruction (one warp instruction per 2 cycles per SM sub-partition): 13 of them put a floor of
-// 26 cycles under a round; measured 42 (a single warp cannot hide its own dependency stalls).  Round 2 tried to take half
-// of the rotations off that pipe -- x * 2^(32-n) as a 64-bit product is (x >> n) : (x << (32-n)), whose halves sum to
-// rotr(x, n): one IMAD.WIDE + one IMAD.IADD on the FMA pipe -- and measured it SLOWER (1.74 ms vs 1.50 ms for 8192 tokens):
-// with one warp the round is bound by the latency of its dependency chain, and the multiply path is longer than a funnel
-// shift.  Kept: the plain form below.
-#define B2_SHA_ROUND(a, b, c, d, e, f, g, h, wk)                                              \
-    {                                                                                          \
-        const uint32_t t1_ = (h) + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + (((e) & (f)) ^ (~(e) & (g))) + (wk); \
-        const uint32_t t2_ = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + (((a) & (b)) ^ ((a) & (c)) ^ ((b) & (c))); \
-        (d) += t1_;                                                                            \
-        (h) = t1_ + t2_;                                                                       \
+// One chain is one thread.  Per round: three funnel shifts + one LOP3 per Sigma, one LOP3 each for Ch and Maj -- ten
+// integer-ALU-pipe instructions (one warp instruction per 2 cycles per SM sub-partition) -- and the additions.
+//   FMA_ADDS = false (default): the additions are IADD3s on the same pipe (4 more): pipe floor 28 cycles per round.
+//   FMA_ADDS = true : every addition is x * 1 + y with a multiplier the compiler cannot see through (IMAD, FMA pipe, one
+//                     warp instruction per cycle): 20 cycles of ALU pipe + 6 of FMA pipe, overlappable on paper.
+// The recurrence e -> Sigma1 -> t1 -> e' is SHF -> LOP3 -> add -> add, ~18 cycles of latency.  Measured (round 2, 8192
+// tokens = 1057 blocks in one chain): 1.225 ms with IADD3s (37 cycles per round), 1.345 ms with IMADs -- six two-input
+// IMADs form a longer dependency chain than two three-input IADD3s, and one warp is bound by that chain, not by pipe
+// throughput.  The same lesson as the attempt to move half of the ROTATIONS to the FMA pipe (x * 2^(32-n) as a 64-bit
+// product, halves summed): 1.74 ms.  B200KV_SHA_ADDS=alu|fma picks the variant (measurement knob, default alu).
+template <bool FMA_ADDS>
+__device__ __forceinline__ uint32_t sha_add(uint32_t x, uint32_t y, uint32_t one) {
+    if constexpr (FMA_ADDS) {
+        uint32_t r;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
+        return r;
+    } else {
+        return x + y;
+    }
+}
+
+#define B2_SHA_ROUND(a, b, c, d, e, f, g, h, wk)                                                          \
+    {                                                                                                      \
+        const uint32_t s1_ = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);                                       \
+        const uint32_t ch_ = ((e) & (f)) ^ (~(e) & (g));                                                   \
+        const uint32_t s0_ = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);                                       \
+        const uint32_t mj_ = ((a) & (b)) ^ ((a) & (c)) ^ ((b) & (c));                                      \
+        if constexpr (FMA_ADDS) {                                                                          \
+            uint32_t t1_ = sha_add<true>(h, wk, one);          /* off the critical path */                 \
+            t1_ = sha_add<true>(t1_, ch_, one);                                                            \
+            t1_ = sha_add<true>(t1_, s1_, one);                                                            \
+            const uint32_t t2_ = sha_add<true>(s0_, mj_, one);                                             \
+            (d) = sha_add<true>(d, t1_, one);                                                              \
+            (h) = sha_add<true>(t1_, t2_, one);                                                            \
+        } else {                                                                                           \
+            const uint32_t t1_ = (h) + s1_ + ch_ + (wk);                                                   \
+            (d) += t1_;                                                                                    \
+            (h) = t1_ + s0_ + mj_;                                                                         \
+        }                                                                                                  \
     }
 
 // 64 rounds over a block's (W + K) held in registers
-__device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q)[16]) {
+template <bool FMA_ADDS>
+__device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q)[16], uint32_t one) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
@@ -145,27 +173,68 @@ __device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
-__device__ __forceinline__ void load_block(uint4 (&q)[16], const uint4* p) {
+// ... and over a block staged in shared memory: slot[i * 32] is this lane's i-th 16-byte group
+template <bool FMA_ADDS>
+__device__ __forceinline__ void compress_smem(uint32_t (&st)[8], const uint4* slot, uint32_t one) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) q[i] = __ldg(p + i);
+    for (int i = 0; i < 16; i += 2) {
+        const uint4 x = slot[i * 32], y = slot[(i + 1) * 32];
+        B2_SHA_ROUND(a, b, c, d, e, f, g, h, x.x)
+        B2_SHA_ROUND(h, a, b, c, d, e, f, g, x.y)
+        B2_SHA_ROUND(g, h, a, b, c, d, e, f, x.z)
+        B2_SHA_ROUND(f, g, h, a, b, c, d, e, x.w)
+        B2_SHA_ROUND(e, f, g, h, a, b, c, d, y.x)
+        B2_SHA_ROUND(d, e, f, g, h, a, b, c, y.y)
+        B2_SHA_ROUND(c, d, e, f, g, h, a, b, y.z)
+        B2_SHA_ROUND(b, c, d, e, f, g, h, a, y.w)
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
-// One thread per sequence (chain).
+constexpr int kShaStages = 3;
+
+// One thread per sequence (chain).  The precomputed (W + K) blocks of a chunk are streamed through a three-stage ring in
+// shared memory with per-thread cp.async groups: block k + 2 is in flight while block k is consumed, so the chain never
+// waits for L2 / DRAM (round 1 kept the next block in registers; the compiler sank those loads to the point where the
+// registers became free, 70 % into the loop body, and a sixth of the cycles went to waiting for them -- ncu, round 2).
+// The ring is lane-interleaved at 16-byte granularity: a warp's LDS.128 of "its" i-th group is one conflict-free request.
+template <bool FMA_ADDS>
 __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
+    __shared__ __align__(16) uint4 ring[kShaStages][16][32];
+    const int lane = threadIdx.x;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.n_seq) return;
+    const uint32_t one = P.n_seq > 0 ? 1u : 0u;          // 1, but not a constant ptxas can fold
     const int64_t t0 = P.seq_offsets[s], t1 = P.seq_offsets[s + 1];
     int64_t slot = P.seq_chunk0[s];
     int64_t gb = P.seq_block0[s];
     uint32_t dig[8];
     bool first = true;
+    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(&ring[0][0][lane]);
     for (int64_t tb = t0; tb < t1; tb += P.chunk_size, ++slot) {
         const int64_t cnt = (t1 - tb) < P.chunk_size ? (t1 - tb) : P.chunk_size;
         const uint32_t ntail = ((uint32_t)(cnt * P.elem_size) + 9u + 63u) / 64u;
+        const uint4* wk4 = reinterpret_cast<const uint4*>(P.scratch + gb * 64);
+        // block k of this chunk -> ring stage k % 3, as one cp.async group (an empty group when k is past the end keeps
+        // the group arithmetic uniform)
+        auto issue = [&](uint32_t k) {
+            if (k < ntail) {
+                const uint4* src = wk4 + 16 * (size_t)k;
+                const uint32_t dst = ring_a + (k % kShaStages) * (16u * 32u * 16u);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 512u), "l"(src + i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue(0);
+        issue(1);
         uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
                           0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
         if (!first) {
-            // prefix block: the 64 hex characters of the previous digest, 8 per state word
+            // prefix block: the 64 hex characters of the previous digest, 8 per state word (its rounds cover the latency
+            // of the first two token blocks)
             uint32_t w[64];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -192,18 +261,15 @@ __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
             for (int i = 0; i < 16; ++i)
                 q[i] = make_uint4(w[4 * i] + kK[4 * i], w[4 * i + 1] + kK[4 * i + 1], w[4 * i + 2] + kK[4 * i + 2],
                                   w[4 * i + 3] + kK[4 * i + 3]);
-            compress_regs(st, q);
+            compress_regs<FMA_ADDS>(st, q, one);
         }
-        // stream the precomputed blocks: the next block's 16 loads are in flight while this block's rounds run
-        const uint4* wk4 = reinterpret_cast<const uint4*>(P.scratch + gb * 64);
-        uint4 cur[16], nxt[16];
-        load_block(cur, wk4);
+#pragma unroll 1
         for (uint32_t k = 0; k < ntail; ++k) {
-            if (k + 1 < ntail) load_block(nxt, wk4 + 16 * (k + 1));
-            compress_regs(st, cur);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+            asm volatile("cp.async.wait_group 1;" ::: "memory");          // all but the newest group: block k has landed
+            issue(k + 2);                                                  // into the stage block k - 1 has just left
+            compress_smem<FMA_ADDS>(st, &ring[k % kShaStages][0][lane], one);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         gb += P.blocks_per_full_chunk;      // scratch blocks are laid out at a fixed stride per chunk
         uint8_t* out = P.digests + slot * 32;
 #pragma unroll
@@ -302,7 +368,9 @@ extern "C" int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const 
     sha256_expand_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, stream>>>(P);
     e = cudaGetLastError();
     if (e == cudaSuccess) {
-        sha256_chain_kernel<<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
+        static const bool fma_adds = [] { const char* v = getenv("B200KV_SHA_ADDS"); return v != nullptr && v[0] == 'f'; }();
+        if (fma_adds) sha256_chain_kernel<true><<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
+        else sha256_chain_kernel<false><<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaEventRecord(g_ev[devi], stream);

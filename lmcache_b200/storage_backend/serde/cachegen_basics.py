@@ -101,6 +101,81 @@ def cdf_from_counts(counts: np.ndarray, ntokens: int) -> np.ndarray:
     return out
 
 
+def _v3_parse_streams(payload: np.ndarray, half: np.ndarray, nb: List[int], C: int, t: int):
+    """Version-3 payload -> (counts int32 [S, 33], rANS lengths int32 [S], rANS bytes u8): every stream starts with its
+    histogram header (include/b200kv.h).  Vectorised over the S = 2L * C streams; raises ValueError on a malformed one."""
+    S = half.size
+    total = half.astype(np.int64) * 2
+    start = np.cumsum(total) - total
+    if S == 0 or int(start[-1] + total[-1]) != payload.size:
+        raise ValueError("B2KV v3: stream lengths do not add up to the payload")
+    nbs = np.repeat(np.asarray(nb, np.int64), C)
+    mb = (nbs + 7) // 8
+    if np.any(total < mb + 4):
+        raise ValueError("B2KV v3: stream shorter than its header")
+    pad = np.concatenate([payload, np.zeros(8, np.uint8)])
+    mask = np.zeros(S, np.int64)
+    for k in range(4):
+        mask |= np.where(k < mb, pad[start + k].astype(np.int64), 0) << (8 * k)
+    mask &= (np.int64(1) << nbs) - 1
+    bits = ((mask[:, None] >> np.arange(32)[None, :]) & 1).astype(bool)
+    nz = bits.sum(axis=1)
+    if np.any(nz == 0):
+        raise ValueError("B2KV v3: empty symbol mask")
+    hlen = mb + nz - 1
+    hlen += hlen & 1
+    if np.any(hlen + 4 > total):
+        raise ValueError("B2KV v3: stream shorter than its header")
+    rank = np.cumsum(bits, axis=1) - 1
+    last = bits & (rank == (nz - 1)[:, None])
+    stored = bits & ~last
+    counts = np.zeros((S, N.LP), np.int32)
+    view = counts[:, :32]
+    idx = (start + mb)[:, None] + rank
+    view[stored] = payload[idx[stored]]
+    if np.any(view[stored] == 0):
+        raise ValueError("B2KV v3: zero count for a symbol the mask lists")
+    rest = t - view.sum(axis=1)
+    if np.any(rest <= 0):
+        raise ValueError("B2KV v3: counts exceed the token count")
+    view[last] = rest
+    rlen = (total - hlen).astype(np.int32)
+    keep = np.ones(payload.size, bool)
+    hpos = np.repeat(start, hlen) + (np.arange(int(hlen.sum())) - np.repeat(np.cumsum(hlen) - hlen, hlen))
+    keep[hpos] = False
+    return counts, rlen, payload[keep]
+
+
+def _v3_build_streams(counts: np.ndarray, nb: List[int], C: int, rlen: np.ndarray, rans: np.ndarray):
+    """Inverse of _v3_parse_streams: (payload u8, half-lengths u8 [S])."""
+    S = counts.shape[0]
+    nbs = np.repeat(np.asarray(nb, np.int64), C)
+    mb = (nbs + 7) // 8
+    view = counts[:, :32]
+    bits = view > 0
+    nz = bits.sum(axis=1)
+    hlen = mb + np.maximum(nz, 1) - 1
+    hlen += hlen & 1
+    rlen = rlen.astype(np.int64)
+    total = hlen + rlen
+    if np.any(total % 2) or np.any(total // 2 > 255):
+        raise ValueError("stream too long for a version-3 container")
+    start = np.cumsum(total) - total
+    out = np.zeros(int(total.sum()), np.uint8)
+    mask = (bits.astype(np.int64) << np.arange(32)[None, :]).sum(axis=1)
+    for k in range(4):
+        sel = k < mb
+        out[(start + k)[sel]] = ((mask[sel] >> (8 * k)) & 0xFF).astype(np.uint8)
+    rank = np.cumsum(bits, axis=1) - 1
+    stored = bits & ~(bits & (rank == (nz - 1)[:, None]))
+    idx = (start + mb)[:, None] + rank
+    out[idx[stored]] = view[stored].astype(np.uint8)
+    rstart = np.cumsum(rlen) - rlen
+    dst = np.repeat(start + hlen - rstart, rlen) + np.arange(int(rlen.sum()))
+    out[dst] = rans
+    return out, (total // 2).astype(np.uint8)
+
+
 @dataclass
 class CacheGenGPUEncoderOutput:
     data_chunks: List[CacheGenGPUBytestream]
@@ -131,24 +206,20 @@ class CacheGenGPUEncoderOutput:
             return torch.from_numpy(raw[off:off + count * np.dtype(dtype).itemsize].view(dtype).copy())
 
         counts_t = None
+        payload = raw[lo.off_payload: lo.off_payload + int(hd.payload_bytes)]
         if hd.version == 3:
-            # compact container: rebuild the reference's CDF tensor from the stored histogram; widen the lengths
-            counts = np.zeros((2 * L, C, N.LP), np.int32)
-            o = lo.off_cdf + ((2 * L + 15) & ~15)
-            for nl, nb in enumerate(hd.nb):
-                rec = raw[o:o + C * nb].reshape(C, nb).astype(np.int32)
-                short = rec.sum(axis=1) == t - 1                       # a count of 256 is stored as 255
-                rec[short] += (rec[short] == 255)
-                counts[nl, :, :nb] = rec
-                o += C * nb
+            # compact container: every stream carries its histogram; rebuild the reference's CDF tensor from it and
+            # hand out the bare rANS streams with their lengths, as a version-2 container would
+            half = raw[lo.off_lengths: lo.off_lengths + 2 * L * C]
+            counts, rlen, payload = _v3_parse_streams(payload, half, hd.nb, C, t)
+            counts = counts.reshape(2 * L, C, N.LP)
             cdf = torch.from_numpy(cdf_from_counts(counts, t))
             counts_t = torch.from_numpy(counts)
-            lengths = (section(lo.off_lengths, G * 2 * L * C, np.uint8).to(torch.int32) * 2).reshape(G, 2 * L, C)
+            lengths = torch.from_numpy(rlen).reshape(G, 2 * L, C)
         else:
             cdf = section(lo.off_cdf, 2 * L * C * N.LP, np.int16).reshape(2 * L, C, N.LP)
             lengths = section(lo.off_lengths, G * 2 * L * C, np.int32).reshape(G, 2 * L, C)
         maxes = section(lo.off_maxes, 2 * L * t, np.int16).view(_HALF[hd.max_dtype]).reshape(2, L, t, 1)
-        payload = raw[lo.off_payload: lo.off_payload + int(hd.payload_bytes)]
         chunks, pos = [], 0
         for g in range(G):
             nb = int(lengths[g].sum())
@@ -167,13 +238,13 @@ class CacheGenGPUEncoderOutput:
         C = H * D
         compact = int(self.coder) == N.CODER_RANS_COMPACT and self.counts is not None and self.nb is not None
         coder = int(self.coder) if compact or int(self.coder) != N.CODER_RANS_COMPACT else N.CODER_RANS
-        nb = self.nb
-        if compact:
-            cnt = self.counts.numpy()
-            lo = N.container_layout(L, H, D, t, N.CODER_RANS_COMPACT, nb[:L], nb[L:])
-        else:
-            lo = N.container_layout(L, H, D, t)
+        lens = torch.stack([c.bytestream_lengths.reshape(2 * L, C) for c in self.data_chunks])
         payload = b"".join(c.bytestream.cpu().numpy().tobytes() for c in self.data_chunks)
+        lo = N.container_layout(L, H, D, t, coder)
+        if compact:
+            pl, half = _v3_build_streams(self.counts.numpy().reshape(2 * L * C, N.LP), self.nb, C,
+                                         lens.numpy().reshape(-1), np.frombuffer(payload, np.uint8))
+            payload = pl.tobytes()
         total = lo.off_payload + len(payload)
         buf = bytearray(total)
         hd = N.Header.from_buffer(buf)
@@ -187,15 +258,9 @@ class CacheGenGPUEncoderOutput:
             b = tensor.contiguous().cpu().view(torch.uint8).numpy().tobytes()
             buf[off:off + len(b)] = b
 
-        lens = torch.stack([c.bytestream_lengths.reshape(2 * L, C) for c in self.data_chunks])
         if compact:
-            buf[lo.off_cdf:lo.off_cdf + 2 * L] = bytes(nb)
-            o = lo.off_cdf + ((2 * L + 15) & ~15)
-            for nl in range(2 * L):
-                rec = np.minimum(cnt[nl, :, :nb[nl]], 255).astype(np.uint8).tobytes()
-                buf[o:o + len(rec)] = rec
-                o += len(rec)
-            put(lo.off_lengths, (lens // 2).to(torch.uint8))
+            buf[lo.off_cdf:lo.off_cdf + 2 * L] = bytes(self.nb)
+            buf[lo.off_lengths:lo.off_lengths + half.size] = half.tobytes()
         else:
             put(lo.off_cdf, self.cdf.reshape(2 * L, C, N.LP))
             put(lo.off_lengths, lens.to(torch.int32))

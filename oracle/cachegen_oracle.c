@@ -162,6 +162,69 @@ void oracle_cdf_from_counts(const uint32_t* counts, int64_t nstreams, int t, int
     for (int64_t s = 0; s < nstreams; ++s) cdf_row(counts + s * ORACLE_LP, t, cdf + s * ORACLE_LP);
 }
 
+/* ------------------------------------------------------------------ B2KV version 3: streams that carry their histogram
+ * (this build's own wire format, include/b200kv.h; no reference counterpart -- the reference stores the CDF tensor).
+ * stream = [mask: ceil(nb/8) bytes LE, bit s <=> counts[s] > 0] [count byte per set bit, ascending, except the last set
+ *           bit (implied: t - sum of the others)] [zero byte if the header length is odd] [rANS stream]
+ * counts : [NL, C, 33] uint32; nb : [NL] symbols per plane; rans_len : [NL, C] int32; rans : concatenated rANS streams.
+ * Returns the packed payload size; half_len[s] = (header + rANS bytes) / 2. */
+static int v3_header(const uint32_t* n, int nb, uint8_t* h) {
+    uint32_t mask = 0;
+    int last = -1, pos, mb = (nb + 7) / 8;
+    for (int i = 0; i < nb; ++i) if (n[i]) { mask |= 1u << i; last = i; }
+    for (int b = 0; b < mb; ++b) h[b] = (uint8_t)(mask >> (8 * b));
+    pos = mb;
+    for (int i = 0; i < nb; ++i) if (n[i] && i != last) h[pos++] = (uint8_t)n[i];
+    if (pos & 1) h[pos++] = 0;
+    return pos;
+}
+
+int64_t oracle_v3_pack(const uint32_t* counts, const int32_t* nb, int NL, int C, const int32_t* rans_len,
+                       const uint8_t* rans, uint8_t* out, int64_t cap, uint8_t* half_len) {
+    int64_t o = 0, r = 0;
+    for (int64_t s = 0; s < (int64_t)NL * C; ++s) {
+        uint8_t h[40];
+        const int hl = v3_header(counts + s * ORACLE_LP, nb[s / C], h);
+        const int64_t total = hl + rans_len[s];
+        if (o + total > cap || (total & 1) || total / 2 > 255) return -1;
+        memcpy(out + o, h, (size_t)hl);
+        memcpy(out + o + hl, rans + r, (size_t)rans_len[s]);
+        half_len[s] = (uint8_t)(total / 2);
+        o += total;
+        r += rans_len[s];
+    }
+    return o;
+}
+
+/* inverse; returns the number of rANS bytes written to `rans`, or -1 on a malformed header */
+int64_t oracle_v3_unpack(const uint8_t* payload, int64_t n, const uint8_t* half_len, const int32_t* nb, int NL, int C,
+                         int t, uint32_t* counts, int32_t* rans_len, uint8_t* rans) {
+    int64_t o = 0, r = 0;
+    for (int64_t s = 0; s < (int64_t)NL * C; ++s) {
+        const int b = nb[s / C], mb = (b + 7) / 8;
+        const int64_t total = 2 * (int64_t)half_len[s];
+        uint32_t mask = 0, sum = 0, *c = counts + s * ORACLE_LP;
+        int nz = 0, last = -1, pos = mb, hl;
+        if (o + total > n || total < mb) return -1;
+        for (int k = 0; k < mb; ++k) mask |= (uint32_t)payload[o + k] << (8 * k);
+        if (b < 32) mask &= (1u << b) - 1u;
+        memset(c, 0, sizeof(uint32_t) * ORACLE_LP);
+        for (int i = 0; i < b; ++i) if (mask >> i & 1) { ++nz; last = i; }
+        hl = mb + (nz ? nz - 1 : 0);
+        hl += hl & 1;
+        if (hl + 4 > total || nz == 0) return -1;
+        for (int i = 0; i < b; ++i)
+            if ((mask >> i & 1) && i != last) { c[i] = payload[o + pos++]; sum += c[i]; if (!c[i]) return -1; }
+        if (sum >= (uint32_t)t) return -1;
+        c[last] = (uint32_t)t - sum;
+        rans_len[s] = (int32_t)(total - hl);
+        memcpy(rans + r, payload + o + hl, (size_t)(total - hl));
+        r += total - hl;
+        o += total;
+    }
+    return o == n ? r : -1;
+}
+
 void oracle_cdf(const int8_t* sym, int NL, int t, int C, int16_t* cdf) {
 #pragma omp parallel for schedule(static)
     for (int64_t s = 0; s < (int64_t)NL * C; ++s) {

@@ -51,6 +51,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_counts.restype = None
         L.oracle_cdf_from_counts.argtypes = [vp, i64, i32, vp]
         L.oracle_cdf_from_counts.restype = None
+        L.oracle_v3_pack.argtypes = [vp, vp, i32, i32, vp, vp, vp, i64, vp]
+        L.oracle_v3_pack.restype = i64
+        L.oracle_v3_unpack.argtypes = [vp, i64, vp, vp, i32, i32, i32, vp, vp, vp]
+        L.oracle_v3_unpack.restype = i64
         L.oracle_encode_group.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i64, vp]
         L.oracle_encode_group.restype = i64
         L.oracle_decode_group.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
@@ -146,18 +150,43 @@ def cdf_from_counts(cnt: np.ndarray, t: int) -> np.ndarray:
 
 CODER_AC = 0     # B2KV container version 1: torchac-lineage arithmetic coder
 CODER_RANS = 1   # B2KV container version 2: rANS, 32-bit state / 16-bit renormalisation, same CDF section
-CODER_RANS_COMPACT = 2   # version 3: the same rANS streams; the CDF section is replaced by the histogram it is a function
-                         # of (u8 counts, nb = 2 * (bins // 2) per stream), stream lengths are stored as bytes / 2 in a u8
+CODER_RANS_COMPACT = 2   # version 3: the same rANS streams, each preceded by its own histogram (mask + count bytes, the
+                         # last count implied); no CDF section; stream lengths stored as bytes / 2 in a u8
 
 
 def nb_map(key_bins, value_bins, L: int) -> List[int]:
-    """counts a version-3 container stores per stream of every plane (keys, then values): 2 * (bins // 2)"""
+    """symbols a stream of every plane (keys, then values) can emit = a version-3 container's nb map: 2 * (bins // 2)"""
     return [2 * (int(b) // 2) for b in list(key_bins)[:L]] + [2 * (int(b) // 2) for b in list(value_bins)[:L]]
 
 
-def v3_counts_section(cnt: np.ndarray, nb: List[int]) -> bytes:
-    """uint32 [NL,C,33] -> the counts section of a version-3 container: per plane u8 [C][nb], 256 stored as 255"""
-    return b"".join(np.minimum(cnt[nl, :, :nb[nl]], 255).astype(np.uint8).tobytes() for nl in range(cnt.shape[0]))
+def v3_pack(cnt: np.ndarray, nb: List[int], rans_lengths: np.ndarray, rans: np.ndarray):
+    """version-3 payload of one <= 256-token chunk: (payload u8 [N], half_lengths u8 [NL,C]) from the histogram
+    uint32 [NL,C,33], the nb map and the group's rANS streams (lengths int32 [NL,C] + concatenated bytes)."""
+    cnt = np.ascontiguousarray(cnt, np.uint32)
+    NL, C, _ = cnt.shape
+    nb_a = np.ascontiguousarray(nb, np.int32)
+    ln = np.ascontiguousarray(rans_lengths, np.int32).reshape(NL, C)
+    rans = np.ascontiguousarray(rans, np.uint8)
+    cap = int(rans.size + NL * C * 40)
+    out = np.empty(cap, np.uint8)
+    half = np.empty((NL, C), np.uint8)
+    n = lib().oracle_v3_pack(_p(cnt), _p(nb_a), NL, C, _p(ln), _p(rans), _p(out), cap, _p(half))
+    assert n >= 0
+    return out[:n].copy(), half
+
+
+def v3_unpack(payload: np.ndarray, half: np.ndarray, nb: List[int], t: int):
+    """inverse of v3_pack: (counts uint32 [NL,C,33], rans_lengths int32 [NL,C], rans u8 [M])"""
+    payload = np.ascontiguousarray(payload, np.uint8)
+    half = np.ascontiguousarray(half, np.uint8)
+    NL, C = half.shape
+    nb_a = np.ascontiguousarray(nb, np.int32)
+    cnt = np.empty((NL, C, LP), np.uint32)
+    ln = np.empty((NL, C), np.int32)
+    rans = np.empty(max(payload.size, 1), np.uint8)
+    n = lib().oracle_v3_unpack(_p(payload), payload.size, _p(half), _p(nb_a), NL, C, int(t), _p(cnt), _p(ln), _p(rans))
+    assert n >= 0, "malformed version-3 stream header"
+    return cnt, ln, rans[:n].copy()
 
 
 def encode_group(cdf_i16: np.ndarray, sym: np.ndarray, tok0: int, g: int, coder: int = CODER_AC):
@@ -209,7 +238,8 @@ def dequantize(sym_u8: np.ndarray, maxes: np.ndarray, max_dtype: int, key_bins, 
 def encode_chunk(x_bits: np.ndarray, dtype: int, key_bins, value_bins, coder: int = CODER_AC):
     """Full encode_function (cachegen_encoder.py:266-325) on one chunk [L,2,t,C]:
     returns dict(cdf, maxes, groups=[(bytestream, lengths, ntokens)], sym, counts).  coder = CODER_RANS_COMPACT codes
-    the same streams as CODER_RANS; the dict's `counts` is what such a container stores in place of `cdf`."""
+    the same streams as CODER_RANS; the dict's `counts` is what such a container's stream headers carry in place of
+    `cdf` (v3_pack builds its payload)."""
     sym, maxes = quantize(x_bits, dtype, key_bins, value_bins)
     c = cdf(sym)
     t = sym.shape[1]

@@ -172,8 +172,12 @@ void sim_dequant_row(const uint8_t* sym, int C, uint16_t max_bits, int max_dtype
 void sim_half_to_float(const uint16_t* h, int n, int dtype, float* out) { for (int i = 0; i < n; ++i) out[i] = half_to_float(h[i], dtype); }
 void sim_float_to_half(const float* f, int n, int dtype, uint16_t* out) { for (int i = 0; i < n; ++i) out[i] = float_to_half(f[i], dtype); }
 
-void sim_layout(int L, int C, int t, int64_t* out) {
-    Layout lo = make_layout(L, C, t);
+void sim_layout(int L, int C, int t, int compact, int64_t* out) {
+    Layout lo = make_layout(L, C, t, compact);
     out[0] = lo.off_cdf; out[1] = lo.off_maxes; out[2] = lo.off_lengths; out[3] = lo.off_payload; out[4] = lo.ngroups;
 }
+
+// version-3 stream header as ac_core.cuh specifies it (hdr_write_host / hdr_len share the arithmetic with the kernels)
+int sim_hdr_write(const uint32_t* cnt, int nb, uint8_t* out) { return (int)hdr_write_host(out, cnt, nb); }
+int sim_hdr_len(uint32_t mask, int nb) { return (int)hdr_len(mask, nb); }
 }

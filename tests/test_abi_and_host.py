@@ -33,20 +33,18 @@ def test_layout_arithmetic():
     assert lo.off_payload == lo.off_lengths + 64 * 4096 * 4
     with pytest.raises(N.NativeError):
         N.container_layout(0, 1, 1, 1)
-    # compact container (version 3): nb map, u8 counts per plane (nb = 2 * (bins // 2)), maxes, u8 half-lengths
-    kb, vb = [32.0] * 10 + [16.0] * 22, [32.0] * 2 + [16.0] * 30
-    lo = N.container_layout(32, 32, 128, 256, N.CODER_RANS_COMPACT, kb, vb)
-    nbsum = 12 * 32 + 52 * 16
-    assert sum(N.nb_map(kb, vb, 32)) == nbsum
+    # compact container (version 3): nb map, maxes, u8 half-lengths; the histograms travel inside the streams
+    lo = N.container_layout(32, 32, 128, 256, N.CODER_RANS_COMPACT)
     assert lo.off_cdf == 64
-    assert lo.off_maxes == 64 + 64 + 4096 * nbsum
+    assert lo.off_maxes == 64 + 64
     assert lo.off_lengths == lo.off_maxes + 64 * 256 * 2
     assert lo.off_payload == lo.fixed_bytes == lo.off_lengths + 64 * 4096
-    assert lo.fixed_bytes < 0.32 * N.container_layout(32, 32, 128, 256).fixed_bytes
+    assert lo.fixed_bytes < 0.02 * N.container_layout(32, 32, 128, 256).fixed_bytes
+    assert N.container_layout(32, 32, 128, 256, N.CODER_AC).fixed_bytes == N.container_layout(32, 32, 128, 256).fixed_bytes
     with pytest.raises(N.NativeError):
-        N.container_layout(32, 32, 128, 257, N.CODER_RANS_COMPACT, kb, vb)       # one <= 256-token group only
+        N.container_layout(32, 32, 128, 257, N.CODER_RANS_COMPACT)       # one <= 256-token group only
     with pytest.raises(N.NativeError):
-        N.container_layout(2, 1, 8, 16, N.CODER_RANS_COMPACT, [2.0, 2.0], [32.0, 32.0])
+        N.container_layout(2, 1, 8, 16, 3)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -155,9 +153,9 @@ def test_container_view_roundtrip_from_oracle_stream(golden):
 
 @pytest.mark.parametrize("name", ["bf16_t1", "bf16_t40", "bf16_t236", "bf16_t256", "bf16_uniform_t16", "fp16_uniform_t128"])
 def test_compact_container_rebuilds_the_reference_cdf(golden, name):
-    """A version-3 container stores the symbol histogram instead of the CDF rows.  Assembled on the host from oracle
-    output, it parses back to the CDF tensor THE REFERENCE'S OWN calculate_cdf spec produced (goldens), to the same
-    lengths and bytestreams; a repeated symbol filling a whole 256-token stream (count 256 in a byte) survives."""
+    """A version-3 container has no CDF section: every stream carries its symbol histogram.  Assembled on the host from
+    oracle output, it parses back to the CDF tensor THE REFERENCE'S OWN calculate_cdf spec produced (goldens), to the
+    same lengths and bytestreams; the product's vectorised packer and the oracle's plain C one agree byte for byte."""
     import numpy as np
     from lmcache_b200.codec import parse_header
     from lmcache_b200.storage_backend.serde.cachegen_basics import (CacheGenGPUBytestream, CacheGenGPUEncoderOutput,
@@ -180,6 +178,13 @@ def test_compact_container_rebuilds_the_reference_cdf(golden, name):
     bs = obj.to_bytes()
     hd = parse_header(bs)
     assert hd.version == 3 and hd.nb == nb
+    lo = N.container_layout(L, H, D, t, N.CODER_RANS_COMPACT)
+    (b0, ln0, _), = enc["groups"]
+    pl, half = O.v3_pack(enc["counts"], nb, ln0, b0)                                       # oracle's packer
+    assert bs[lo.off_payload:] == pl.tobytes()
+    assert bs[lo.off_lengths:lo.off_lengths + half.size] == half.tobytes()
+    cnt2, ln2, r2 = O.v3_unpack(np.frombuffer(bs[lo.off_payload:], np.uint8), half, nb, t)  # ... and its parser
+    assert np.array_equal(cnt2, enc["counts"]) and np.array_equal(ln2, ln0) and np.array_equal(r2, b0)
     v2 = CacheGenGPUEncoderOutput(obj.data_chunks, obj.cdf, mk, mv, H, D, N.CODER_RANS).to_bytes()
     assert len(bs) < len(v2)
     back = CacheGenGPUEncoderOutput.from_bytes(bs)
@@ -189,17 +194,21 @@ def test_compact_container_rebuilds_the_reference_cdf(golden, name):
     for a, b in zip(back.data_chunks, obj.data_chunks):
         assert a.ntokens == b.ntokens and torch.equal(a.bytestream, b.bytestream)
         assert torch.equal(a.bytestream_lengths, b.bytestream_lengths.to(torch.int32))
-    # a damaged nb map or a truncated blob is a ValueError (a miss), never a wrong layout
+    # a damaged nb map, a truncated blob, a damaged stream header: ValueError (a miss), never a wrong layout
     bad = bytearray(bs)
     bad[64] = 33
     with pytest.raises(ValueError):
         parse_header(bytes(bad))
     with pytest.raises(ValueError):
         parse_header(bs[:-1])
+    bad = bytearray(bs)
+    bad[lo.off_payload:lo.off_payload + (nb[0] + 7) // 8] = bytes((nb[0] + 7) // 8)      # first stream: empty symbol mask
+    with pytest.raises(ValueError):
+        CacheGenGPUEncoderOutput.from_bytes(bytes(bad))
 
 
 def test_compact_container_count_of_256():
-    """all 256 tokens of a stream on one symbol: the count does not fit a byte, is stored as 255 and restored"""
+    """all 256 tokens of a stream on one symbol: the count (256) does not fit a byte -- it is the implied one"""
     import numpy as np
     from lmcache_b200.storage_backend.serde.cachegen_basics import (CacheGenGPUBytestream, CacheGenGPUEncoderOutput)
     from oracle import oracle as O

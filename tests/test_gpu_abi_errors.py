@@ -27,7 +27,7 @@ def test_encode_argument_validation():
     bins = N.float_array([32.0] * L)
     lo = N.container_layout(L, H, D, t)
     out = torch.empty(lo.max_total_bytes, dtype=torch.uint8, device="cuda")
-    ws = torch.empty(lib.b200kv_encode_workspace_bytes(L, H, D, t, 1, N.CODER_RANS), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(max(lib.b200kv_encode_workspace_bytes(L, H, D, t, 1, c) for c in range(3)), dtype=torch.uint8, device="cuda")
     sizes = torch.zeros(1, dtype=torch.int64, device="cuda")
     sp = torch.cuda.current_stream().cuda_stream
 
@@ -42,7 +42,7 @@ def test_encode_argument_validation():
     for coder in (N.CODER_AC, N.CODER_RANS, N.CODER_RANS_COMPACT):
         assert call(coder=coder) == 0
         torch.cuda.synchronize()
-        assert int(sizes[0]) > N.container_layout(L, H, D, t, coder, bins, bins).fixed_bytes
+        assert int(sizes[0]) > N.container_layout(L, H, D, t, coder).fixed_bytes
         assert N.Header.from_buffer_copy(out[:64].cpu().numpy().tobytes()).version == coder + 1
     for bad in (dict(n=0), dict(ct=0), dict(last=t + 1), dict(out=None), dict(out=out.data_ptr() + 1), dict(wsb=16),
                 dict(kb=None), dict(tok=-1), dict(stride=64), dict(coder=3), dict(coder=-1),
@@ -65,7 +65,7 @@ def test_slot_too_small_sets_status_not_corruption(coder):
     kv = torch.rand(L, 2, t, H, D, device="cuda").to(torch.bfloat16)       # ~5 bits/symbol: a real payload
     d = _desc(kv, L, H, D)
     bins = N.float_array([32.0] * L)
-    lo = N.container_layout(L, H, D, t, coder, bins, bins)
+    lo = N.container_layout(L, H, D, t, coder)
     stride = lo.fixed_bytes + 256                                           # far too small for the payload
     guard = 4096
     out = torch.full((stride + guard,), 0xAB, dtype=torch.uint8, device="cuda")
@@ -106,8 +106,8 @@ def test_decode_and_misc_validation():
     a = list(ok)
     a[4], a[8] = N.i32_array([257]), N.CODER_RANS_COMPACT
     assert lib.b200kv_decode_chunks(*a) < 0 and N.last_error()
-    with pytest.raises(ValueError):
-        N.container_layout(L, H, D, t, N.CODER_RANS_COMPACT)           # the compact layout needs the bins
+    with pytest.raises(N.NativeError):
+        N.container_layout(L, H, D, 257, N.CODER_RANS_COMPACT)
     assert lib.b200kv_sha256_chain(buf.data_ptr(), 3, N.i64_array([0, 4]), 1, 4, buf.data_ptr(), sp) < 0     # elem_size
     assert lib.b200kv_sha256_chain(buf.data_ptr(), 8, N.i64_array([4, 0]), 1, 4, buf.data_ptr(), sp) < 0     # decreasing offsets
     assert lib.b200kv_sha256_chain(buf.data_ptr(), 8, N.i64_array([0, 0]), 1, 4, buf.data_ptr(), sp) == 0    # empty: no-op

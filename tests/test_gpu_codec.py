@@ -52,29 +52,22 @@ def _sections(raw: bytes, L, H, D, t):
     C = H * D
     G = (t + 255) // 256
     a = np.frombuffer(raw, np.uint8)
+    payload = a[lo.off_payload: lo.off_payload + hd.payload_bytes]
     if hd.version == 3:
-        # compact container: the histogram stands in for the CDF (rebuilt here with the ORACLE's arithmetic and compared
-        # with the reference-made goldens by the callers); stream lengths are stored halved in one byte
+        # compact container: every stream carries its histogram in place of a CDF row.  Unpacked with the ORACLE's
+        # parser; the CDF is rebuilt with the oracle's arithmetic (callers compare it with the reference-made goldens)
         kb, vb = O.make_bins(MODEL)
         nb = O.nb_map(kb, vb, L)
         assert list(a[lo.off_cdf: lo.off_cdf + 2 * L]) == nb == hd.nb
-        cnt = np.zeros((2 * L, C, 33), np.uint32)
-        o = lo.off_cdf + ((2 * L + 15) & ~15)
-        for nl in range(2 * L):
-            rec = a[o:o + C * nb[nl]].reshape(C, nb[nl]).astype(np.uint32)
-            short = rec.sum(axis=1) == t - 1
-            rec[short] += (rec[short] == 255)
-            assert np.all(rec.sum(axis=1) == t)
-            cnt[nl, :, :nb[nl]] = rec
-            o += C * nb[nl]
-        assert o <= lo.off_maxes
+        half = a[lo.off_lengths: lo.off_lengths + 2 * L * C].reshape(2 * L, C)
+        cnt, ln, payload = O.v3_unpack(payload, half, nb, t)
+        assert np.all(cnt.sum(axis=2) == t)
         cdf = O.cdf_from_counts(cnt, t)
-        lengths = a[lo.off_lengths: lo.off_lengths + G * 2 * L * C].astype(np.int32).reshape(G, 2 * L, C) * 2
+        lengths = ln.reshape(1, 2 * L, C)
     else:
         cdf = a[lo.off_cdf: lo.off_cdf + 2 * L * C * 33 * 2].view(np.int16).reshape(2 * L, C, 33)
         lengths = a[lo.off_lengths: lo.off_lengths + G * 2 * L * C * 4].view(np.int32).reshape(G, 2 * L, C)
     maxes = a[lo.off_maxes: lo.off_maxes + 2 * L * t * 2].view(np.uint16).reshape(2, L, t)
-    payload = a[lo.off_payload: lo.off_payload + hd.payload_bytes]
     assert hd.total_bytes == lo.off_payload + hd.payload_bytes == len(raw)
     return cdf, maxes, lengths, payload
 
@@ -101,12 +94,13 @@ def test_encode_container_bit_exact_vs_oracle_and_goldens(codec, golden, name):
     enc = _oenc(codec, x.reshape(L, 2, t, H * D), dt, kb, vb)
     assert np.array_equal(np.stack([ln for _, ln, _ in enc["groups"]]), lengths)
     assert np.array_equal(np.concatenate([b for b, _, _ in enc["groups"]]), payload)
-    if raw[4] == 3:     # the stored histogram itself, byte for byte
+    if raw[4] == 3:     # the packed streams (histogram headers included) and their lengths, byte for byte
         from lmcache_b200.codec import container_layout_of, parse_header
         lo = container_layout_of(parse_header(raw))
-        want = O.v3_counts_section(enc["counts"], O.nb_map(kb, vb, L))
-        o = lo.off_cdf + ((2 * L + 15) & ~15)
-        assert bytes(raw[o:o + len(want)]) == want
+        (b0, ln0, _), = enc["groups"]
+        pl, half = O.v3_pack(enc["counts"], O.nb_map(kb, vb, L), ln0, b0)
+        assert bytes(raw[lo.off_payload:]) == pl.tobytes()
+        assert bytes(raw[lo.off_lengths:lo.off_lengths + half.size]) == half.tobytes()
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

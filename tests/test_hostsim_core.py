@@ -26,7 +26,9 @@ def sim():
     S.sim_dequant_row.argtypes = [vp, i32, ctypes.c_uint16, i32, ctypes.c_float, i32, vp]
     S.sim_half_to_float.argtypes = [vp, i32, i32, vp]
     S.sim_float_to_half.argtypes = [vp, i32, i32, vp]
-    S.sim_layout.argtypes = [i32, i32, i32, vp]
+    S.sim_layout.argtypes = [i32, i32, i32, i32, vp]
+    S.sim_hdr_write.argtypes = [vp, i32, vp]
+    S.sim_hdr_len.argtypes = [ctypes.c_uint32, i32]
     return S
 
 
@@ -245,8 +247,39 @@ def test_half_conversions_exhaustive(sim):
 def test_layout_matches_c_abi(sim):
     from lmcache_b200 import _native as N
     for (L, H, D, t) in [(32, 32, 128, 256), (12, 1, 16, 300), (40, 2, 128, 17), (1, 1, 1, 1)]:
-        lo = N.container_layout(L, H, D, t)
-        out = np.zeros(5, np.int64)
-        sim.sim_layout(L, H * D, t, P(out))
-        assert (lo.off_cdf, lo.off_maxes, lo.off_lengths, lo.off_payload) == tuple(out[:4])
-        assert lo.off_payload % 16 == 0 and lo.max_total_bytes >= lo.off_payload
+        for coder in (N.CODER_RANS, N.CODER_RANS_COMPACT):
+            if coder == N.CODER_RANS_COMPACT and t > 256:
+                continue
+            lo = N.container_layout(L, H, D, t, coder)
+            out = np.zeros(5, np.int64)
+            sim.sim_layout(L, H * D, t, 1 if coder == N.CODER_RANS_COMPACT else 0, P(out))
+            assert (lo.off_cdf, lo.off_maxes, lo.off_lengths, lo.off_payload) == tuple(out[:4])
+            assert lo.off_payload % 16 == 0 and lo.max_total_bytes >= lo.off_payload
+
+
+def test_stream_header_spec_matches_oracle(sim):
+    """version-3 stream header: the shared spec functions of ac_core.cuh (hdr_write_host, hdr_len -- the latter is what
+    the compaction and decode kernels evaluate) against the oracle's packer, on random histograms incl. a lone symbol
+    with 256 tokens, every nb, odd and even header lengths."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    for nb in (4, 6, 8, 10, 16, 30, 32):
+        for trial in range(40):
+            t = int(rng.integers(1, 257))
+            k = int(rng.integers(1, min(nb - 1, t) + 1))                   # symbols that occur (<= nb - 1 by construction)
+            syms = rng.choice(nb - 1, size=k, replace=False)
+            cnt = np.zeros(33, np.uint32)
+            cnt[syms] = 1
+            for _ in range(t - k):
+                cnt[rng.choice(syms)] += 1
+            if trial == 0:
+                cnt[:] = 0
+                cnt[nb - 2] = 256                                           # a lone symbol: count implied
+            out = np.zeros(48, np.uint8)
+            n = sim.sim_hdr_write(P(cnt), nb, P(out))
+            mask = int(sum(1 << i for i in range(nb) if cnt[i]))
+            assert n == sim.sim_hdr_len(mask, nb) and n % 2 == 0 and n <= 36
+            pl, half = O.v3_pack(cnt.reshape(1, 1, 33), [nb], np.array([[4]], np.int32), np.zeros(4, np.uint8))
+            assert bytes(out[:n]) == pl[:n].tobytes() and int(half[0, 0]) * 2 == n + 4
+            back, ln, _ = O.v3_unpack(pl, half, [nb], int(cnt.sum()))
+            assert np.array_equal(back[0, 0], cnt)
