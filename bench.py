@@ -363,7 +363,8 @@ def main():
         step_device(lambda ticket, c0, k: sizes.extend(ticket.wait().sizes))
         torch.cuda.synchronize()
         bps = 8.0 * (sum(sizes) - n_chunks * codec.layout(L, H, D, cs).fixed_bytes) / (raw_bytes / 2)
-        os.environ["B200KV_DECODE_TABLE"] = "transposed" if bps > 3.6 else "rows"
+        thr = 4.1 if codec.coder_for(cs) == N.CODER_RANS_COMPACT else 3.6     # the library's own rule (b200kv_decode_chunks)
+        os.environ["B200KV_DECODE_TABLE"] = "transposed" if bps > thr else "rows"
         return sizes
 
     def profile_kernels(steps):
@@ -396,6 +397,18 @@ def main():
         ev1.record(stream)
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / steps
+
+    codec_v2 = CacheGenCodec(MODEL, coder="rans") if codec.coder_for(cs) == N.CODER_RANS_COMPACT else None
+
+    def coder_bits():
+        """bits per symbol of the rANS streams alone, measured on the first wave with a version-2 container (a version-3
+        payload also holds the per-stream histograms, which version 2 keeps as CDF rows in its fixed sections); not timed"""
+        if codec_v2 is None:
+            return None
+        nt = min(W * cs, T)
+        k = (nt + cs - 1) // cs
+        sz = codec_v2.encode_async(view, 0, nt, cs).wait().sizes
+        return round(8.0 * (sum(sz) - k * codec_v2.layout(L, H, D, cs).fixed_bytes) / (L * 2 * nt * C), 4)
 
     # ---- warm-up + parity spot check (not timed)
     for _ in range(max(args.warmup, 3)):
@@ -472,7 +485,7 @@ def main():
     sweep = None
     if not args.no_sweep and world == 1:
         sweep = [{"data": args.data, "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
-                  "ms_per_step": round(ms_step, 4), "encode_ms": round(kern_ms.get("encode", 0), 4),
+                  "coder_bits_per_symbol": coder_bits(), "ms_per_step": round(ms_step, 4), "encode_ms": round(kern_ms.get("encode", 0), 4),
                   "decode_ms": round(kern_ms.get("decode", 0), 4), "container_bytes": container_bytes,
                   "GBps": round(value, 1), "parity_spot_check": parity}]
         for kind in [k for k in ("kv8d_nooutlier", "normal", "uniform", "uniform_signed") if k != args.data]:
@@ -483,7 +496,7 @@ def main():
             ms = timed(3)
             km = profile_kernels(2)
             sweep.append({"data": kind, "payload_bits_per_symbol": round(8.0 * (sum(sz) - n_chunks * fixed) / (raw_bytes / 2), 4),
-                          "ms_per_step": round(ms, 4), "encode_ms": round(km.get("encode", 0), 4),
+                          "coder_bits_per_symbol": coder_bits(), "ms_per_step": round(ms, 4), "encode_ms": round(km.get("encode", 0), 4),
                           "decode_ms": round(km.get("decode", 0), 4), "container_bytes": sum(sz),
                           "GBps": round(raw_bytes / (ms * 1e-3) / 1e9, 1), "parity_spot_check": par})
 
@@ -515,7 +528,11 @@ def main():
                        "data_kind": args.data, "coder": args.coder + f" (B2KV container v{codec.coder_for(cs) + 1})",
                        "raw_bytes_per_gpu": raw_bytes, "container_bytes": container_bytes,
                        "payload_bits_per_symbol": round(8.0 * payload_bytes / (raw_bytes / 2), 4),
-                       "wave_chunks": W, "device_scratch_bytes": {"staging": staging_bytes(stride, W, N), "encode_workspace": int(ws_enc),
+                       "payload_note": "container v3: the payload holds every stream's histogram header (mask + sparse counts) "
+                                       "in front of its rANS bytes; coder_bits_per_symbol in entropy_sweep = the rANS bytes alone"
+                       if codec_v2 is not None else "payload = the coder's bytes (histograms live in the CDF section)",
+                       "wave_chunks": W,
+                       "device_scratch_bytes": {"staging": staging_bytes(stride, W, N), "encode_workspace": int(ws_enc),
                                                                   "decode_workspace": int(ws_dec)},
                        "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity,
                        "decode_status_words_nonzero": sum(1 for w in status_words if w),

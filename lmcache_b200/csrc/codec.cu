@@ -137,6 +137,11 @@ __device__ __forceinline__ int64_t tok_row(const int64_t* slot_map, int64_t tok)
 // max1 = amax(|x|, channels) per (plane, token), kept in the input half dtype
 // (cachegen_encoder.py:54-55).  |x| ordering == integer ordering of (bits & 0x7fff); a NaN in the row
 // wins (pattern above inf), like torch.amax.  One warp per row, 128-bit loads when alignment allows.
+// Round 2 tried to hide this kernel -- the only HBM-bound one of the path -- under the instruction-bound coding kernels of
+// the previous wave (second stream, 128-thread blocks with <= 32 registers so that a block fits next to them): no gain
+// (8.31 -> 8.28 ms per step).  Both coder kernels fill the SM's shared memory with their own CTAs (7 x 32.5 KB, 12 x 18.6
+// KB incl. the 1 KB the system reserves per CTA), so not even a block without shared memory finds room; the kernels only
+// overlap at their tails.  Measured, rejected.
 template <bool VEC, bool PAGED>
 __global__ void __launch_bounds__(256) absmax_kernel(EncParams P, int64_t total_tokens) {
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -1380,12 +1385,12 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
             for (int n = tid; n <= kGroup; n += CT) pn[n] = fdiv((float)n, tf);
             __syncthreads();
             // the stream's header: mask of the symbols that occur, then their counts (the last one is implied).
-            // Two readers, chosen per warp: when every lane's header is short (<= 8 bytes: few symbols per stream, the
+            // Two readers, chosen per warp: when most lanes' headers are short (<= 8 bytes: few symbols per stream, the
             // streams themselves are short and neighbours share cache lines) each count is one byte load at a position
-            // that depends on the mask alone -- branch-free; otherwise the header is pulled into registers with aligned
-            // word loads, only as many as it is long, and consumed a byte at a time (scattered byte loads would cost a
-            // cache-line access each).  Measured: 3.29 / 4.64 ms (byte loads) vs 3.40 / 3.95 ms (registers) at 0.6 / 4.1
-            // payload bits per symbol.
+            // that depends on the mask alone -- branch-free; when a quarter of the lanes or more have long headers, the
+            // header is pulled into registers with aligned word loads, only as many as it is long, and consumed a byte
+            // at a time (scattered byte loads would cost a cache-line access each).  Measured, whole kernel: 3.29 / 4.64
+            // ms (byte loads only) vs 3.40 / 3.95 ms (registers only) at 0.6 / 4.1 payload bits per symbol.
             const int nb = 2 * ((int)cq + 1);
             const uint32_t mbytes = (uint32_t)hdr_mask_bytes(nb);
             const uint8_t* sp = dc.base + my_off;
@@ -1400,7 +1405,7 @@ __global__ void __launch_bounds__(CT, 12) decode_kernel(DecParams P) {
             if (nb < 32) mask &= (1u << nb) - 1u;
             hl = hdr_len(mask, nb);
             const uint32_t top = 0x80000000u >> __clz((int)mask);               // the last set bit: its count is implied
-            const bool all_short = __all_sync(0xffffffffu, hl <= 8u || !active);
+            const bool all_short = __popc(__ballot_sync(0xffffffffu, active && hl > 8u)) < 8;
             if (active) {
                 uint32_t sum = 0u;
                 uint32_t hb[9];
@@ -1860,7 +1865,8 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
             bits += 8.0 * (double)(total_bytes[j] - lj.off_payload);
             syms += 2.0 * P.L * (double)P.C * ntokens[j];
         }
-        transposed = bits > 3.6 * syms && bits < 6.0 * syms;       // a slot bound instead of a size says nothing: rows
+        // a version-3 payload also carries the stream histograms: ~0.5 bits per symbol at that entropy
+        transposed = bits > (P.compact ? 4.1 : 3.6) * syms && bits < 6.0 * syms;   // a slot bound instead of a size says nothing: rows
         if (const char* e = getenv("B200KV_DECODE_TABLE")) transposed = e[0] == 't';
     }
     P.tiles_max = (int32_t)tiles_max;
