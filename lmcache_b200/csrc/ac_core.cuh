@@ -261,6 +261,20 @@ struct CdfAccum {
     }
 };
 
+// The same arithmetic split into value() / absorb(): cdf[i] only changes when a count is absorbed, so a caller whose
+// lanes share a loop (one stream per lane) can skip the symbols none of its lanes uses -- absorbing p = 0 leaves cum, its
+// fp32 image and therefore rint(image * 65504) untouched.  value(i) == CdfAccum's i-th return value.
+struct CdfAccum2 {
+    double cum;
+    uint32_t R;     // rint(fl32(cum) * 65504)
+    B2_HD void init() { cum = 0.0; R = 0u; }
+    B2_HD uint32_t value(uint32_t i) const { return (R + i) & 0xffffu; }
+    B2_HD void absorb(float p_i) {
+        cum += (double)p_i;
+        R = (uint32_t)(int)frint(fmul((float)cum, 65504.0f));
+    }
+};
+
 // ---------------------------------------------------------------- arithmetic encoder (a8)
 struct EncState {
     uint32_t low, high, pending;

@@ -177,6 +177,15 @@ void sim_layout(int L, int C, int t, int compact, int64_t* out) {
     out[0] = lo.off_cdf; out[1] = lo.off_maxes; out[2] = lo.off_lengths; out[3] = lo.off_payload; out[4] = lo.ngroups;
 }
 
+// CdfAccum2 (value / absorb, symbols in `skip` are not absorbed -- legal when their count is 0) vs CdfAccum
+void sim_cdf_skip(const uint32_t* counts, int t, uint32_t skip, uint16_t* cdf) {
+    CdfAccum2 a; a.init();
+    for (uint32_t i = 0; i < (uint32_t)kLp; ++i) {
+        cdf[i] = (uint16_t)a.value(i);
+        if (i < 32 && !((skip >> i) & 1u)) a.absorb(fdiv((float)counts[i], (float)t));
+    }
+}
+
 // version-3 stream header as ac_core.cuh specifies it (hdr_write_host / hdr_len share the arithmetic with the kernels)
 int sim_hdr_write(const uint32_t* cnt, int nb, uint8_t* out) { return (int)hdr_write_host(out, cnt, nb); }
 int sim_hdr_len(uint32_t mask, int nb) { return (int)hdr_len(mask, nb); }

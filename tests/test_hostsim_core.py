@@ -22,6 +22,7 @@ def sim():
     S.sim_encode_stream2.argtypes = [vp, vp, i64, i32, vp, i64]
     S.sim_decode_stream2.argtypes = [vp, vp, i64, i32, vp, i64, i32, i32]
     S.sim_cdf.argtypes = [vp, i32, vp]
+    S.sim_cdf_skip.argtypes = [vp, i32, ctypes.c_uint32, vp]
     S.sim_quant_row.argtypes = [vp, i32, i32, ctypes.c_uint16, ctypes.c_float, vp]
     S.sim_dequant_row.argtypes = [vp, i32, ctypes.c_uint16, i32, ctypes.c_float, i32, vp]
     S.sim_half_to_float.argtypes = [vp, i32, i32, vp]
@@ -192,6 +193,12 @@ def test_cdf_bit_exact_vs_golden(sim, golden, golden_names):
                 out = np.zeros(33, np.uint16)
                 sim.sim_cdf(P(counts), t, P(out))
                 assert np.array_equal(out.view(np.int16), cdf[nl, c]), (n, nl, c)
+                # the value / absorb form the kernels use, skipping every symbol with a zero count (the kernels skip the
+                # ones no lane of a warp uses) and skipping none: both equal the reference-made CDF
+                for skip in (int(sum(1 << i for i in range(32) if counts[i] == 0)), 0):
+                    out2 = np.zeros(33, np.uint16)
+                    sim.sim_cdf_skip(P(counts), t, skip, P(out2))
+                    assert np.array_equal(out2.view(np.int16), cdf[nl, c]), (n, nl, c, skip)
 
 
 def test_quant_dequant_bit_exact_vs_golden(sim, golden, golden_names):
