@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(128) sha256_expand_kernel(ShaParams P) {
 // tokens = 1057 blocks in one chain): 1.225 ms with IADD3s (37 cycles per round), 1.345 ms with IMADs -- six two-input
 // IMADs form a longer dependency chain than two three-input IADD3s, and one warp is bound by that chain, not by pipe
 // throughput.  The same lesson as the attempt to move half of the ROTATIONS to the FMA pipe (x * 2^(32-n) as a 64-bit
-// product, halves summed): 1.74 ms.  B200KV_SHA_ADDS=alu|fma picks the variant (measurement knob, default alu).
+// product, halves summed): 1.74 ms.  A third variant moves only h + (W + K) -- known three rounds ahead, off every chain --
+// to the FMA pipe (13 ALU instructions per round instead of 14): 1.231 ms, no gain either.
+// B200KV_SHA_ADDS=alu|hwk|fma picks the variant (measurement knob, default alu).
 template <bool FMA_ADDS>
 __device__ __forceinline__ uint32_t sha_add(uint32_t x, uint32_t y, uint32_t one) {
     if constexpr (FMA_ADDS) {
@@ -140,13 +142,19 @@ __device__ __forceinline__ uint32_t sha_add(uint32_t x, uint32_t y, uint32_t one
         const uint32_t ch_ = ((e) & (f)) ^ (~(e) & (g));                                                   \
         const uint32_t s0_ = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);                                       \
         const uint32_t mj_ = ((a) & (b)) ^ ((a) & (c)) ^ ((b) & (c));                                      \
-        if constexpr (FMA_ADDS) {                                                                          \
+        if constexpr (FMA_ADDS == 1) {                                                                     \
             uint32_t t1_ = sha_add<true>(h, wk, one);          /* off the critical path */                 \
             t1_ = sha_add<true>(t1_, ch_, one);                                                            \
             t1_ = sha_add<true>(t1_, s1_, one);                                                            \
             const uint32_t t2_ = sha_add<true>(s0_, mj_, one);                                             \
             (d) = sha_add<true>(d, t1_, one);                                                              \
             (h) = sha_add<true>(t1_, t2_, one);                                                            \
+        } else if constexpr (FMA_ADDS == 2) {                                                              \
+            /* only h + (W + K) -- known three rounds ahead, off every dependency chain -- leaves the ALU pipe */ \
+            const uint32_t hwk_ = sha_add<true>(h, wk, one);                                               \
+            const uint32_t t1_ = hwk_ + s1_ + ch_;                                                         \
+            (d) += t1_;                                                                                    \
+            (h) = t1_ + s0_ + mj_;                                                                         \
         } else {                                                                                           \
             const uint32_t t1_ = (h) + s1_ + ch_ + (wk);                                                   \
             (d) += t1_;                                                                                    \
@@ -155,7 +163,7 @@ __device__ __forceinline__ uint32_t sha_add(uint32_t x, uint32_t y, uint32_t one
     }
 
 // 64 rounds over a block's (W + K) held in registers
-template <bool FMA_ADDS>
+template <int FMA_ADDS>
 __device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q)[16], uint32_t one) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
@@ -174,7 +182,7 @@ __device__ __forceinline__ void compress_regs(uint32_t (&st)[8], const uint4 (&q
 }
 
 // ... and over a block staged in shared memory: slot[i * 32] is this lane's i-th 16-byte group
-template <bool FMA_ADDS>
+template <int FMA_ADDS>
 __device__ __forceinline__ void compress_smem(uint32_t (&st)[8], const uint4* slot, uint32_t one) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
@@ -199,7 +207,7 @@ constexpr int kShaStages = 3;
 // waits for L2 / DRAM (round 1 kept the next block in registers; the compiler sank those loads to the point where the
 // registers became free, 70 % into the loop body, and a sixth of the cycles went to waiting for them -- ncu, round 2).
 // The ring is lane-interleaved at 16-byte granularity: a warp's LDS.128 of "its" i-th group is one conflict-free request.
-template <bool FMA_ADDS>
+template <int FMA_ADDS>
 __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
     __shared__ __align__(16) uint4 ring[kShaStages][16][32];
     const int lane = threadIdx.x;
@@ -368,9 +376,13 @@ extern "C" int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const 
     sha256_expand_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, stream>>>(P);
     e = cudaGetLastError();
     if (e == cudaSuccess) {
-        static const bool fma_adds = [] { const char* v = getenv("B200KV_SHA_ADDS"); return v != nullptr && v[0] == 'f'; }();
-        if (fma_adds) sha256_chain_kernel<true><<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
-        else sha256_chain_kernel<false><<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
+        static const int adds = [] {
+            const char* v = getenv("B200KV_SHA_ADDS");
+            return v == nullptr ? 0 : v[0] == 'f' ? 1 : v[0] == 'h' ? 2 : 0;
+        }();
+        if (adds == 1) sha256_chain_kernel<1><<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
+        else if (adds == 2) sha256_chain_kernel<2><<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
+        else sha256_chain_kernel<0><<<(unsigned)((n_seq + 31) / 32), 32, 0, stream>>>(P);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaEventRecord(g_ev[devi], stream);

@@ -22,7 +22,7 @@ def main():
             sha256_prefix_chain(t, 256)
         torch.cuda.synchronize()
         out[f"one_chain_{n}_tokens_ms"] = round((time.perf_counter() - t0) / 10 * 1e3, 3)
-    print(os.environ.get("B200KV_SHA_ADDS", "fma(default)"), out)
+    print(os.environ.get("B200KV_SHA_ADDS", "alu(default)"), out)
 
 
 if __name__ == "__main__":

@@ -27,7 +27,7 @@ ok = True
 for coder in ("rans_compact", "rans", "ac"):
     codec = CacheGenCodec(MODEL, coder=coder)
     for (L, H, D, T, cs, kind) in [(2, 2, 72, 300, 256, "peaked"), (2, 1, 128, 520, 512, "peaked"), (1, 3, 40, 77, 64, "peaked"),
-                                   (12, 2, 128, 300, 256, "uniform")]:
+                                   (4, 2, 128, 300, 256, "uniform")]:
         C = H * D
         if kind == "peaked":
             bits = O.synth_kv_bits(L, T, C, seed=T)
