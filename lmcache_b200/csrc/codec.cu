@@ -293,7 +293,7 @@ __device__ __forceinline__ void for_each_symbol_rev(const uint16_t* cbase, const
 //     row_end + 2 * nk - 2, so the row's tail holds the halfwords in decode order.  The address is one unpredicated
 //     IMAD.WIDE, only the 16-bit store and the count are predicated;
 //   * q = x / f by one reciprocal biased low (estimate is q or q - 1) and one fix-up;
-//   * x' = (q << 16) + (x - q f) + start  ==  x + start + q * (65536 - f): one IMAD.
+//   * x' = (q << 16) + (x - q f) + start  ==  x + start + q * (65536 - f).
 __device__ __forceinline__ void rans_put(uint32_t& x, int32_t& nk, const uint16_t* row_end, uint32_t start, uint32_t freq) {
     const uint32_t xh = x >> 16;
     asm volatile(
@@ -307,11 +307,15 @@ __device__ __forceinline__ void rans_put(uint32_t& x, int32_t& nk, const uint16_
         : "+r"(x), "+r"(nk) : "r"(xh), "r"(freq), "l"(row_end) : "memory");
     float rc;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rn(freq)));
-    uint32_t q = __float2uint_rz(__uint2float_rz(x) * (rc * 0.99999952316284179688f));
-    const uint32_t nf = 0u - freq;
-    const uint32_t r = q * nf + x;                       // x - q f
-    q += r >= freq ? 1u : 0u;
-    x = q * (nf + 65536u) + (x + start);
+    const uint32_t q = __float2uint_rz(__uint2float_rz(x) * (rc * 0.99999952316284179688f));   // floor(x / f) or one less
+    // With m = 65536 - f:  a = q m + x;  x - q f = a - (q << 16);  x' = a + start, plus m when the estimate was one short.
+    // Six integer instructions (m, a, r, compare, add, predicated add) where "negate f, r, compare, q + 1, select, x +
+    // start, m, multiply-add" took eight (ncu, round 2).
+    const uint32_t m = 65536u - freq;
+    const uint32_t a = q * m + x;
+    const uint32_t r = a - (q << 16);
+    x = a + start;
+    if (r >= freq) x += m;
 }
 
 // ------------------------------------------------------------------------------------------ encode
