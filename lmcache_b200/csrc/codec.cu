@@ -53,7 +53,7 @@ struct EncParams {
     uint64_t* sizes_out;
     uint32_t* temp;                  // [n_tiles][CT][tempw] coder output before compaction
     uint32_t* rstate;                // rANS: [n_tiles][CT] final coder states (the first 4 bytes of every stream); version 3:
-                                     //   [n_tiles][CT] records of 4 words {header word 0, header word 1, state, -}
+                                     //   [n_tiles][CT] records of 4 words {header word 0, header word 1, state, header bytes}
     uint32_t* tile_tot;              // [n_chunks][tiles_full] bytes per tile, then exclusive prefix (in place)
     unsigned long long* totals;      // [n_chunks] payload bytes
     unsigned int* err;               // [n_chunks]
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(CT, FUSED ? 7 : 4) encode_kernel(EncParams P) 
 #pragma unroll
                 for (int k = SPW - 1; k >= 0; --k) code(word, k);
             }
-            if (P.compact) P.rstate[((int64_t)blockIdx.x * CT + tid) * 4 + 2] = x;
+            if (P.compact) reinterpret_cast<uint2*>(P.rstate)[((int64_t)blockIdx.x * CT + tid) * 2 + 1] = make_uint2(x, hlen);
             else P.rstate[(int64_t)blockIdx.x * CT + tid] = x;
             len = hlen + 4u - 2u * (uint32_t)nk;
         } else if (active) {
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(CT, 7) encode_tma_kernel(EncParams P) {
         }
         consume_done(q);
     }
-    if (P.compact) P.rstate[((int64_t)blockIdx.x * CT + tid) * 4 + 2] = x_state;
+    if (P.compact) reinterpret_cast<uint2*>(P.rstate)[((int64_t)blockIdx.x * CT + tid) * 2 + 1] = make_uint2(x_state, hlen);
     else P.rstate[(int64_t)blockIdx.x * CT + tid] = x_state;
     const uint32_t len = hlen + 4u - 2u * (uint32_t)nk;
 
@@ -1022,12 +1022,11 @@ __global__ void __launch_bounds__(CT, 9) compact_kernel(EncParams P) {
         const uint32_t* tail = srcw;                               // the row's rANS part (halfwords right-aligned in it)
         uint32_t tailbytes = rowbytes;
         if (P.compact) {
-            // version 3: header words 0, 1 and the state come from the tile's side array (one coalesced 16-byte load),
-            // header words 2..8 -- long headers only -- from the front of the row; the length follows from the mask
-            const int nb = 2 * ((int)P.pt.maxq[id.nl] + 1);
+            // version 3: header words 0, 1, the state and the header length come from the tile's side array (one coalesced
+            // 16-byte load), header words 2..8 -- long headers only -- from the front of the row
             const uint4 rec = __ldg(reinterpret_cast<const uint4*>(P.rstate) + (int64_t)blockIdx.x * CT + tid);
             state = rec.z;
-            hl = min(hdr_len(rec.x & (nb >= 32 ? 0xffffffffu : (1u << nb) - 1u), nb), max(len, 4u) - 4u);
+            hl = min(min(rec.w, (uint32_t)kHdrMax), max(len, 4u) - 4u);
             uint32_t hw[9] = {rec.x, rec.y, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             if (hl > 8u) {
                 const uint4 a = __ldg(reinterpret_cast<const uint4*>(srcw)), b = __ldg(reinterpret_cast<const uint4*>(srcw) + 1);
