@@ -47,6 +47,20 @@ for coder in ("rans_compact", "rans", "ac"):
                 got = out.contiguous().cpu().view(torch.int16).numpy().view(np.uint16).reshape(L, 2, T, C)
                 ok &= bool(np.array_equal(got, want))
                 ok &= all(w == 0 for w in codec.decode_status())
+        # damaged containers (lengths, stream headers / CDF rows, payload): must stay inside the buffer under memcheck
+        from lmcache_b200.codec import container_layout_of, parse_header
+        rng = np.random.default_rng(T)
+        for raw in raws[:1]:
+            lo = container_layout_of(parse_header(raw))
+            for a, b in ((lo.off_lengths, lo.off_payload), (lo.off_payload, len(raw)), (lo.off_cdf, lo.off_maxes)):
+                bad = bytearray(raw)
+                for pos in rng.integers(a, b, size=256):
+                    bad[pos] = int(rng.integers(0, 256))
+                try:
+                    codec.decode([bytes(bad)], KvView.from_blob(torch.zeros_like(kv[:, :, :parse_header(raw).ntokens]), "vllm"), [0])
+                    torch.cuda.synchronize()
+                except ValueError:
+                    pass
         # paged
         slots = torch.randperm(T + 64)[:T].cuda()
         caches = []

@@ -544,3 +544,51 @@ def test_kernel_variants_agree(kind, coder, monkeypatch):
     want = np.concatenate([O.decode_chunk(O.encode_chunk(bits[:, :, j * cs:min(T, (j + 1) * cs)], 0, kb, vb, O.CODER_RANS), 0, kb, vb, 0)
                            for j in range(len(outs["tma"]))], axis=2)
     assert np.array_equal(_tensor_bits(decs["rows"]).reshape(L, 2, T, H * D), want)
+
+
+@pytest.mark.parametrize("kind", ["peaked", "uniform"])
+def test_damaged_containers_never_fault(codec, kind):
+    """A container whose bytes were damaged after its header was written (a remote tier, a disk) must decode to SOMETHING
+    without touching memory outside the caller's buffer: random byte flips in the lengths section, the stream headers /
+    CDF rows, the payload and the maxima of every container version.  The header itself stays intact (a damaged header is
+    rejected on the host, tests/test_abi_and_host.py).  rANS containers flag the damage in their status words; a clean
+    decode afterwards proves the context is alive."""
+    from lmcache_b200 import _native as N
+    from lmcache_b200.codec import KvView, container_layout_of, parse_header
+    L, H, D, T = 4, 2, 128, 256
+    g = torch.Generator(device="cuda").manual_seed(11)
+    if kind == "peaked":
+        kv = torch.randn((L, 2, T, H, D), device="cuda", generator=g) * 0.05
+        kv[:, :, :, :, 0] = 4.0
+    else:
+        kv = torch.rand((L, 2, T, H, D), device="cuda", generator=g) * 2 - 1
+    kv = kv.to(torch.bfloat16)
+    raw = bytes(codec.encode_to_host(KvView.from_blob(kv, "vllm"), 0, T, T)[0])
+    lo = container_layout_of(parse_header(raw))
+    rng = np.random.default_rng(3)
+    sections = {"lengths": (lo.off_lengths, lo.off_payload), "payload": (lo.off_payload, len(raw)),
+                "front": (lo.off_cdf, lo.off_maxes), "maxes": (lo.off_maxes, lo.off_lengths),
+                "payload_head": (lo.off_payload, min(len(raw), lo.off_payload + 4096))}
+    flagged = 0
+    for name, (a, b) in sections.items():
+        for n_flips in (1, 64, 4096):
+            bad = bytearray(raw)
+            for pos in rng.integers(a, b, size=n_flips):
+                bad[pos] = int(rng.integers(0, 256))
+            out = torch.zeros_like(kv)
+            try:
+                codec.decode([bytes(bad)], KvView.from_blob(out, "vllm"), [0])
+            except ValueError:
+                continue                                   # the host-side checks caught it (e.g. the nb map): a miss
+            torch.cuda.synchronize()                       # would raise on an illegal address
+            flagged += any(codec.decode_status())
+    if codec.coder != N.CODER_AC:
+        assert flagged > 0                                 # the rANS final-state check notices damaged streams
+    out = torch.zeros_like(kv)
+    codec.decode([raw], KvView.from_blob(out, "vllm"), [0])
+    torch.cuda.synchronize()
+    assert codec.decode_status() == [0]
+    bits = _tensor_bits(kv).reshape(L, 2, T, H * D)
+    kb, vb = O.make_bins(MODEL)
+    want = O.decode_chunk(O.encode_chunk(bits, 0, kb, vb, O.CODER_RANS), 0, kb, vb, 0)
+    assert np.array_equal(_tensor_bits(out).reshape(L, 2, T, H * D), want)
