@@ -17,6 +17,11 @@
  *       bits, MSB-first packing) and anchors it on the
  *       reference call sites cachegen_encoder.py:241-262,301-316 and
  *       cachegen_decoder.py:52-66.
+ *   rANS bitstream, version-3 stream framing    : this build's own wire format (container
+ *       versions 2 and 3, include/b200kv.h), restated here independently of the kernels:
+ *       same status as the arithmetic coder ("parity unpinned"), same anchors.  What a
+ *       version-3 reader evaluates -- the CDF as a function of the stored histogram,
+ *       oracle_cdf_from_counts -- IS pinned to the reference-made CDF goldens.
  *
  * Build: gcc -O2 -fopenmp -ffp-contract=off -fno-fast-math -shared -fPIC (oracle/Makefile).
  * -ffp-contract=off matters: the reference rounds the fp32 mul and add separately

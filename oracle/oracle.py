@@ -7,7 +7,11 @@ Every function cites the reference file:line it restates; see the C file for det
 Parity status: quantise / dequantise / CDF / hash are pinned against golden vectors made
 from the reference's own functions (tests/golden/make_golden.py); the arithmetic-coder
 bitstream is "parity unpinned" (torchac_cuda wheel absent) and is pinned only to the
-published torchac algorithm restated in SURVEY.md Appendix A.
+published torchac algorithm restated in SURVEY.md Appendix A.  The rANS coder and the
+version-3 stream framing (v3_pack / v3_unpack: every stream carries its symbol histogram,
+from which cdf_from_counts rebuilds the reference's CDF tensor -- that function IS pinned
+to the reference-made CDF goldens) are this build's own wire format, restated here
+independently of the kernels and of the product's host shim.
 """
 from __future__ import annotations
 
