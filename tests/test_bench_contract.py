@@ -33,10 +33,15 @@ def test_reference_arm_other_ranks_are_silent():
 
 
 def test_committed_gpu_line_has_the_contract_objects():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_final_bench.json")))
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r2_final_bench.json")).read().strip().splitlines()[-1])
     assert REQUIRED <= set(d) and {"roofline", "clocks", "gpu_launches"} <= set(d)
     rl = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rl) and rl["bound"] == "hbm"
     assert abs(rl["frac"] - rl["achieved"] / rl["peak"]) < 1e-3
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference")
+    # round 2: the end-to-end number goes through the engine, the sweep carries parity checks, the container is version 3
+    assert "LMCacheEngine.store" in d["e2e"]["path"] and d["e2e"]["value"] > 0
+    sweep = d["config"]["entropy_sweep"]
+    assert len(sweep) == 5 and all(x["parity_spot_check"] == "bit-exact" for x in sweep)
+    assert max(x["coder_bits_per_symbol"] for x in sweep) > 3.5 and "v3" in d["config"]["coder"]
