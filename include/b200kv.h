@@ -180,6 +180,13 @@ int b200kv_decode_chunks(const void* containers, int64_t containers_bytes, const
  */
 int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const int64_t* seq_offsets, int32_t n_seq,
                         int32_t chunk_size, void* digests, void* stream);
+/* Same, and digest k is announced as soon as it exists: ready[k] (DEVICE-visible uint32 array, one word per digest slot,
+ * normally mapped host memory like `digests`; or NULL) is set to `epoch` after digest k has been made visible system-wide.
+ * A chain is serial -- 38 us per 256-token chunk -- so a host thread that polls ready[] can look up and move the first
+ * chunks while the later ones are still being hashed (LMCacheEngine.store / retrieve do).  The digests must be 4-byte
+ * aligned. */
+int b200kv_sha256_chain_ready(const void* tokens, int32_t elem_size, const int64_t* seq_offsets, int32_t n_seq,
+                              int32_t chunk_size, void* digests, uint32_t* ready, uint32_t epoch, void* stream);
 
 /*
  * Blob pack / unpack between a kv_desc (tuple-of-tensors or strided blob) and contiguous chunk blobs

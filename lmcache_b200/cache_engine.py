@@ -28,23 +28,114 @@ from lmcache_b200.utils import CacheEngineKey, KVCache, _lmcache_nvtx_annotate
 logger = init_logger(__name__)
 
 
-_digest_lock = threading.Lock()
-_digest_buf: Optional[PinnedBuffer] = None
+class LazySeq:
+    """A read-only sequence whose items are computed on access: fn(base[i]).  Slices stay lazy.  The engine passes its
+    chunk keys around in this form: item i only exists once the hash chain has reached chunk i (38 us per chunk), and a
+    consumer that walks the sequence front to back -- look up / fetch / encode wave by wave -- overlaps with the chain
+    instead of waiting for its end."""
+
+    def __init__(self, fn, base, start: int = 0, stop: Optional[int] = None):
+        self._fn, self._base = fn, base
+        self._start = start
+        self._stop = len(base) if stop is None else stop
+
+    def __len__(self) -> int:
+        return self._stop - self._start
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            a, b, step = i.indices(len(self))
+            if step != 1:
+                return [self[k] for k in range(a, b, step)]
+            return LazySeq(self._fn, self._base, self._start + a, self._start + max(a, b))
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        v = self._base[self._start + i]
+        return v if self._fn is None else self._fn(v)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
 
 
-def _digest_buffer(nbytes: int) -> PinnedBuffer:
-    """Process-wide page-locked landing area for digests (cudaHostAlloc costs far more than a hash launch)."""
-    global _digest_buf
-    if _digest_buf is None or _digest_buf.nbytes < nbytes:
-        _digest_buf = PinnedBuffer(max(1 << 16, 2 * nbytes))
-    return _digest_buf
+class _HashRun:
+    """One hash-chain launch: digests and their ready words land in mapped page-locked memory; item i blocks (a short
+    spin on the ready word) until the kernel has produced digest i."""
+    _pool: List[PinnedBuffer] = []
+    _pool_lock = threading.Lock()
+    _epoch = 0
+    _streams: dict = {}
+
+    def __init__(self, dev_tokens: torch.Tensor, chunk_size: int, offs: List[int], nchunks: int):
+        self.n = nchunks
+        need = 36 * nchunks                                  # 32-byte digests, then one ready word each
+        with _HashRun._pool_lock:
+            _HashRun._epoch = (_HashRun._epoch % 0x7fffffff) + 1
+            self.epoch = _HashRun._epoch
+            fit = [b for b in _HashRun._pool if b.nbytes >= need]
+            if fit:
+                self.buf = min(fit, key=lambda b: b.nbytes)
+                _HashRun._pool.remove(self.buf)
+            else:
+                self.buf = PinnedBuffer(max(1 << 14, 2 * need))     # cudaHostAlloc zero-fills: no stale epoch inside
+        self.cap = self.buf.nbytes // 36
+        self._tokens = dev_tokens                            # alive until the kernel has run
+        self._hex: List[Optional[str]] = [None] * nchunks
+        self._flags = (ctypes.c_uint32 * self.cap).from_address(self.buf.host_ptr + 32 * self.cap)
+        dev = dev_tokens.device
+        with torch.cuda.device(dev):
+            # its own stream: the chain is one warp on one SM; the caller's encode / decode kernels must not queue behind it
+            side = _HashRun._streams.get(dev.index)
+            if side is None:
+                side = _HashRun._streams[dev.index] = torch.cuda.Stream(device=dev)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            side.wait_event(ready)
+            N.check(N.lib().b200kv_sha256_chain_ready(ctypes.c_void_p(dev_tokens.data_ptr()), dev_tokens.element_size(),
+                                                      N.i64_array(offs), len(offs) - 1, chunk_size,
+                                                      ctypes.c_void_p(self.buf.dev_ptr),
+                                                      ctypes.c_void_p(self.buf.dev_ptr + 32 * self.cap), self.epoch,
+                                                      side.cuda_stream), "sha256_chain")
+            self.done = torch.cuda.Event()
+            self.done.record(side)
+            dev_tokens.record_stream(side)
+
+    def __len__(self) -> int:
+        return self.n
+
+    def __getitem__(self, i: int) -> str:
+        h = self._hex[i]
+        if h is None:
+            spins = 0
+            while self._flags[i] != self.epoch:
+                spins += 1
+                if spins % 4096 == 0 and self.done.query():
+                    # the kernel is over: either the word is there now, or the launch failed
+                    if self._flags[i] != self.epoch:
+                        self.done.synchronize()
+                        raise N.NativeError("hash chain kernel finished without producing every digest")
+            h = self._hex[i] = bytes(self.buf.view(32 * i, 32)).hex()
+        return h
+
+    def __del__(self):
+        try:
+            if not self.done.query():
+                self.done.synchronize()                      # the kernel still writes into the buffer
+            with _HashRun._pool_lock:
+                if len(_HashRun._pool) < 8:
+                    _HashRun._pool.append(self.buf)
+                    self.buf = None
+            if self.buf is not None:
+                self.buf.close()
+        except Exception:       # noqa: BLE001 -- interpreter shutdown
+            pass
 
 
-def sha256_prefix_chain(tokens: torch.Tensor, chunk_size: int, seq_offsets: Optional[List[int]] = None) -> List[str]:
-    """Hex digests h_i = sha256(hex(h_{i-1}) || bytes(chunk_i)) for every chunk of every sequence
-    (cache_engine.py:58-96), computed on the GPU.  tokens: 1-D integer tensor on any device; the bytes hashed
-    are the tensor's native little-endian dtype, as in the reference.  seq_offsets: token boundaries of
-    independent sequences (default: one sequence)."""
+def sha256_prefix_chain_lazy(tokens: torch.Tensor, chunk_size: int, seq_offsets: Optional[List[int]] = None) -> LazySeq:
+    """sha256_prefix_chain without waiting for the end of the chain: returns at once with a lazy sequence of hex digests;
+    digest i becomes available ~38 us x (i + 1) after the launch (one 256-token chunk of int64 ids)."""
     N.require_cuda()
     if tokens.dim() != 1:
         raise ValueError(f"Invalid shape of tokens: {tokens.shape}")
@@ -53,19 +144,17 @@ def sha256_prefix_chain(tokens: torch.Tensor, chunk_size: int, seq_offsets: Opti
     n_seq = len(offs) - 1
     nchunks = sum((offs[i + 1] - offs[i] + chunk_size - 1) // chunk_size for i in range(n_seq))
     if nchunks == 0:
-        return []
+        return LazySeq(None, [])
     dev_tokens = tokens if tokens.is_cuda else tokens.to("cuda", non_blocking=False)
-    dev_tokens = dev_tokens.contiguous()
-    with _digest_lock:
-        out = _digest_buffer(32 * nchunks)   # the kernel writes digests straight into mapped host memory
-        with torch.cuda.device(dev_tokens.device):
-            sp = torch.cuda.current_stream().cuda_stream
-            N.check(N.lib().b200kv_sha256_chain(ctypes.c_void_p(dev_tokens.data_ptr()), dev_tokens.element_size(),
-                                                N.i64_array(offs), n_seq, chunk_size, ctypes.c_void_p(out.dev_ptr),
-                                                sp), "sha256_chain")
-            N.check(N.lib().b200kv_stream_sync(sp), "stream_sync")
-        raw = bytes(out.view(0, 32 * nchunks))
-    return [raw[32 * i: 32 * i + 32].hex() for i in range(nchunks)]
+    return LazySeq(None, _HashRun(dev_tokens.contiguous(), chunk_size, offs, nchunks))
+
+
+def sha256_prefix_chain(tokens: torch.Tensor, chunk_size: int, seq_offsets: Optional[List[int]] = None) -> List[str]:
+    """Hex digests h_i = sha256(hex(h_{i-1}) || bytes(chunk_i)) for every chunk of every sequence
+    (cache_engine.py:58-96), computed on the GPU.  tokens: 1-D integer tensor on any device; the bytes hashed
+    are the tensor's native little-endian dtype, as in the reference.  seq_offsets: token boundaries of
+    independent sequences (default: one sequence)."""
+    return list(sha256_prefix_chain_lazy(tokens, chunk_size, seq_offsets))
 
 
 class LMCacheEngine:
@@ -93,10 +182,13 @@ class LMCacheEngine:
     def _get_init_hash(self) -> str:
         return ""
 
-    def _prefix_hash(self, tokens: torch.Tensor, num_skip_chunk: Optional[int] = 0) -> List[str]:
+    def _prefix_hash(self, tokens: torch.Tensor, num_skip_chunk: Optional[int] = 0):
         """All chunk digests of `tokens` (the whole chain is hashed, then the first num_skip_chunk digests are
-        dropped, like cache_engine.py:86-96)."""
-        return sha256_prefix_chain(tokens, self.chunk_size)[num_skip_chunk:]
+        dropped, like cache_engine.py:86-96).  A lazy sequence: digest i is there once the chain has reached chunk i."""
+        return sha256_prefix_chain_lazy(tokens, self.chunk_size)[num_skip_chunk or 0:]
+
+    def _keys_of(self, chunk_hashes, fmt: str) -> LazySeq:
+        return LazySeq(lambda h: self._make_key(h, fmt), chunk_hashes)
 
     # ------------------------------------------------------------------ blob helpers
     def _chunk_shape(self, view: KvView, t: int, fmt: str) -> Tuple[int, ...]:
@@ -167,7 +259,7 @@ class LMCacheEngine:
                     break
         n_chunks = 0
         if start_chunk_idx < len(chunk_hashes):
-            keys = [self._make_key(h, fmt) for h in chunk_hashes[start_chunk_idx:]]
+            keys = self._keys_of(chunk_hashes[start_chunk_idx:], fmt)
             kv_cuda = self._as_cuda_kv(kv_tensors_raw)
             if kv_cuda[0][0].dtype not in (torch.bfloat16, torch.float16):
                 # the native pack / codec kernels move 16-bit KV; any other dtype (the reference's local and torch-serde
@@ -281,7 +373,7 @@ class LMCacheEngine:
         if start_chunk_idx < len(chunk_hashes):
             view = KvView.from_paged(kv_caches, slot_mapping.cuda())
             self._geom = (view.L, view.H, view.D, view.dtype)
-            keys = [self._make_key(h, fmt) for h in chunk_hashes[start_chunk_idx:]]
+            keys = self._keys_of(chunk_hashes[start_chunk_idx:], fmt)
             self.engine_.put_kv_chunks(keys, view, start_chunk_idx * self.chunk_size, self.chunk_size, blocking=blocking)
 
     @_lmcache_nvtx_annotate
@@ -311,7 +403,7 @@ class LMCacheEngine:
         extra = num_skip_tok - num_skip_chunk * cs
         ret_mask = torch.ones_like(tokens, dtype=torch.bool)
         ret_mask[:num_skip_tok] = False
-        keys = [self._make_key(h, "vllm") for h in self._prefix_hash(tokens, num_skip_chunk)]
+        keys = self._keys_of(self._prefix_hash(tokens, num_skip_chunk), "vllm")
         base = num_skip_chunk * cs
         view = KvView.from_paged(kv_caches, slots[base:])
         got_chunks, first = 0, 0
@@ -348,7 +440,7 @@ class LMCacheEngine:
     def _retrieve_into_blob(self, tokens, chunk_hashes, num_skip_tok, num_skip_chunk, ret_mask, fmt, st):
         """retrieve() without per-chunk tensors or torch.cat: the backend decodes / uploads every hit chunk straight
         into one preallocated blob; the suffix-mask trim of the first chunk is a view offset, not a copy."""
-        keys = [self._make_key(h, fmt) for h in chunk_hashes]
+        keys = self._keys_of(chunk_hashes, fmt)
         geom = self._kv_geometry()
         if geom is None:
             # shapes unknown (nothing stored through this engine yet -- the normal case for a retrieve-only replica):

@@ -44,6 +44,8 @@ struct ShaParams {
     const int64_t* seq_chunk0;    // device, n_seq + 1: first digest slot of each sequence
     uint32_t* scratch;            // [n_blocks][64]  (W + K)
     uint8_t* digests;
+    uint32_t* ready;              // or NULL: ready[slot] = epoch once digest `slot` is visible (system scope)
+    uint32_t epoch;
     int64_t n_blocks;
     int32_t n_seq, elem_size, chunk_size;
     int32_t blocks_per_full_chunk;   // ceil((chunk_size * elem_size + 9) / 64): tail blocks (tokens + padding) of a full chunk
@@ -279,12 +281,17 @@ __global__ void __launch_bounds__(32) sha256_chain_kernel(ShaParams P) {
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         gb += P.blocks_per_full_chunk;      // scratch blocks are laid out at a fixed stride per chunk
-        uint8_t* out = P.digests + slot * 32;
+        // big-endian words, eight 4-byte stores (the buffer is usually mapped host memory: every store is a PCIe write)
+        uint32_t* out = reinterpret_cast<uint32_t*>(P.digests + slot * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             dig[i] = st[i];
-            out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
-            out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+            out[i] = __byte_perm(st[i], 0u, 0x0123);
+        }
+        if (P.ready != nullptr) {
+            // a host thread polls this word and then reads the digest: make the digest visible system-wide first
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(P.ready + slot) = P.epoch;
         }
         first = false;
     }
@@ -296,6 +303,12 @@ using namespace b200kv;
 
 extern "C" int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const int64_t* seq_offsets, int32_t n_seq,
                                    int32_t chunk_size, void* digests, void* stream_) {
+    return b200kv_sha256_chain_ready(tokens, elem_size, seq_offsets, n_seq, chunk_size, digests, nullptr, 0u, stream_);
+}
+
+extern "C" int b200kv_sha256_chain_ready(const void* tokens, int32_t elem_size, const int64_t* seq_offsets, int32_t n_seq,
+                                         int32_t chunk_size, void* digests, uint32_t* ready, uint32_t epoch,
+                                         void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B2_REQUIRE(seq_offsets != nullptr && n_seq > 0, "bad sequence table");
     B2_REQUIRE(elem_size == 1 || elem_size == 2 || elem_size == 4 || elem_size == 8, "elem_size must be 1/2/4/8");
@@ -370,6 +383,8 @@ extern "C" int b200kv_sha256_chain(const void* tokens, int32_t elem_size, const 
     P.seq_chunk0 = P.seq_offsets + 2 * (n_seq + 1);
     P.scratch = reinterpret_cast<uint32_t*>(dmem + tab_pad);
     P.digests = static_cast<uint8_t*>(digests);
+    P.ready = ready;
+    P.epoch = epoch;
     P.n_blocks = n_blocks;
     P.n_seq = n_seq; P.elem_size = elem_size; P.chunk_size = chunk_size;
     P.blocks_per_full_chunk = (int32_t)bpc;

@@ -355,15 +355,17 @@ class LMCLocalCompressedBackend(LMCBackendInterface):
         self._retired = keep
 
     def put_kv_chunks(self, keys, view, tok_begin: int, chunk_size: int, blocking: bool = True) -> int:
-        entries = [_CEntry() for _ in keys]
+        # `keys` may be lazy (the engine's hash chain produces key i ~38 us x (i + 1) after its launch): the encode waves
+        # need no keys, so they are enqueued first; the entries are published as their keys arrive.  Readers wait on `ready`.
+        entries = [_CEntry() for _ in range(len(keys))]
+        job = self._pipe.submit(view, tok_begin, chunk_size, entries)
         old = []
-        with self.update_lock:                      # visible at once: contains() is true, readers wait on `ready`
-            for k, e in zip(keys, entries):
+        for k, e in zip(keys, entries):
+            with self.update_lock:
                 prev = self.dict.get(k)
                 if prev is not None:
                     old.append(prev)
                 self.dict[k] = e
-        job = self._pipe.submit(view, tok_begin, chunk_size, entries)
         for prev in old:                            # an overwritten container leaves once nobody reads it any more
             prev.ready.wait()
             self._retire(prev)
@@ -413,28 +415,17 @@ class LMCLocalCompressedBackend(LMCBackendInterface):
         """Upload + decode consecutive chunks (until the first miss) straight into `dst`; chunk i lands at token
         dst_tok0 + i * chunk_size.  Everything is enqueued: copies on the copy stream, decodes on the current stream."""
         from lmcache_b200.pipeline import UploadRing, wave_chunks_default
-        hits = []
-        for i, key in enumerate(keys):
-            e = self._ready_entry(key)
-            if e is None or (e.L, e.H, e.D) != (dst.L, dst.H, dst.D):
-                break
-            tok = dst_tok0 + i * chunk_size
-            if tok + e.ntokens > dst.ntokens:
-                break
-            if hits and (e.max_dtype, e.coder) != (hits[0].max_dtype, hits[0].coder):
-                break
-            hits.append(e)
-        if not hits:
-            return 0
         W = wave_chunks_default()
         lib = N.lib()
+        n_hits = 0
+        first = None
         with torch.cuda.device(dst.device):
             if self._upload is None or self._upload.device != dst.device:
                 self._upload = UploadRing(dst.device)
             up = self._upload
             cur = torch.cuda.current_stream()
-            for w0 in range(0, len(hits), W):
-                wave = hits[w0:w0 + W]
+
+            def flush(wave, w0):
                 offs, o = [], 0
                 for e in wave:
                     offs.append(o)
@@ -453,7 +444,27 @@ class LMCLocalCompressedBackend(LMCBackendInterface):
                                       [dst_tok0 + (w0 + j) * chunk_size for j in range(len(wave))],
                                       wave[0].max_dtype, wave[0].coder, cur)
                 up.mark_read(slot, cur)
-        return len(hits)
+
+            # keys may be lazy (the hash chain is still running): every full wave is uploaded and decoded as soon as its
+            # keys exist, while the chain works on the later chunks
+            wave = []
+            for i, key in enumerate(keys):
+                e = self._ready_entry(key)
+                if e is None or (e.L, e.H, e.D) != (dst.L, dst.H, dst.D):
+                    break
+                if dst_tok0 + i * chunk_size + e.ntokens > dst.ntokens:
+                    break
+                if first is not None and (e.max_dtype, e.coder) != (first.max_dtype, first.coder):
+                    break
+                first = first or e
+                wave.append(e)
+                n_hits += 1
+                if len(wave) == W:
+                    flush(wave, n_hits - W)
+                    wave = []
+            if wave:
+                flush(wave, n_hits - len(wave))
+        return n_hits
 
     @_lmcache_nvtx_annotate
     def get(self, key: CacheEngineKey) -> Optional[torch.Tensor]:
