@@ -240,7 +240,7 @@ class LMCRemoteBackend(LMCBackendInterface):
             if self._pipe is None:
                 from lmcache_b200.pipeline import EncodePipeline
                 self._pipe = EncodePipeline(self.serializer.codec, self._sink, name="b200kv-remote-store")
-            job = self._pipe.submit(view, tok_begin, chunk_size, list(keys))
+            job = self._pipe.submit(view, tok_begin, chunk_size, keys)      # keys may be lazy: a wave's are read when it is queued
             if blocking:
                 job.wait()
                 self.flush()
@@ -308,7 +308,7 @@ class LMCRemoteBackend(LMCBackendInterface):
         """Fetch consecutive chunks until the first miss and decode them straight into `dst` (chunk i lands at token
         dst_tok0 + i * chunk_size).  Returns the number of chunks."""
         if self._striped() and hasattr(self.deserializer, "codec"):
-            return self._get_striped(list(keys), dst, dst_tok0, chunk_size)
+            return self._get_striped(keys, dst, dst_tok0, chunk_size)        # keys may be lazy: read as the fetch window moves
         blobs = []
         for key in keys:
             if not self.contains(key):

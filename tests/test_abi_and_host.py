@@ -228,3 +228,34 @@ def test_compact_container_count_of_256():
     back = CacheGenGPUEncoderOutput.from_bytes(obj.to_bytes())
     assert np.array_equal(back.counts.numpy(), enc["counts"].astype(np.int32))
     assert np.array_equal(back.cdf.numpy(), enc["cdf"])
+
+
+def test_lazy_sequence_semantics():
+    """cache_engine.LazySeq: the engine's chunk keys as a read-only sequence whose items are computed on access; slices stay
+    lazy, iteration touches items front to back only as far as the consumer goes."""
+    from lmcache_b200.cache_engine import LazySeq
+    touched = []
+
+    class Base:
+        def __len__(self):
+            return 10
+
+        def __getitem__(self, i):
+            touched.append(i)
+            return i * i
+
+    s = LazySeq(lambda v: v + 1, Base())
+    assert len(s) == 10 and touched == []
+    assert s[3] == 10 and s[-1] == 82 and touched == [3, 9]
+    tail = s[4:]
+    assert isinstance(tail, LazySeq) and len(tail) == 6 and touched == [3, 9]
+    assert tail[0] == 17 and tail[1:3][1] == 37
+    touched.clear()
+    for i, v in enumerate(s):
+        if i == 2:
+            break
+    assert touched == [0, 1, 2]
+    assert list(s[8:]) == [65, 82] and list(s[5:5]) == [] and len(s[20:]) == 0
+    with pytest.raises(IndexError):
+        s[10]
+    assert list(LazySeq(None, [])) == []

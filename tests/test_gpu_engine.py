@@ -518,3 +518,26 @@ def test_fp32_kv_takes_the_generic_path(backend, autorelease):
     r, m = engine.retrieve(torch.cat([tokens, generate_tokens(50, "cuda")]))
     assert int(m.sum()) == 512 and r[0][0].dtype == torch.float32
     check_kv_cache_equal(r, kv, 512, "vllm")
+
+
+@pytest.mark.gpu
+def test_lazy_hash_chain_matches_oracle_in_any_order():
+    """sha256_prefix_chain_lazy: digests become readable while the chain is still running; whatever order they are asked
+    for in, they are the oracle's (and the reference's: the oracle is pinned to its goldens)."""
+    from lmcache_b200.cache_engine import LazySeq, sha256_prefix_chain, sha256_prefix_chain_lazy
+    toks = torch.randint(0, 32000, (8192 + 77,), dtype=torch.int64, device="cuda")
+    want = O.sha256_chain(toks.cpu().numpy(), 256)
+    lz = sha256_prefix_chain_lazy(toks, 256)
+    assert isinstance(lz, LazySeq) and len(lz) == 33
+    assert lz[32] == want[32] and lz[0] == want[0] and lz[-2] == want[31]        # the last one first: waits for the whole chain
+    assert list(lz[5:9]) == want[5:9] and list(lz) == want
+    # several runs in flight at once (each owns its landing buffer and epoch), consumed in reverse order of launch
+    runs = [(t, sha256_prefix_chain_lazy(t, 256)) for t in (torch.randint(0, 32000, (n,), dtype=torch.int64, device="cuda")
+                                                             for n in (300, 4096, 1, 2048))]
+    for t, r in reversed(runs):
+        assert list(r) == O.sha256_chain(t.cpu().numpy(), 256)
+    # several chains in one launch
+    offs = [0, 300, 300, 1000]
+    assert sha256_prefix_chain(toks[:1000], 256, offs) == O.sha256_chain(toks[:300].cpu().numpy(), 256) + \
+        O.sha256_chain(toks[300:1000].cpu().numpy(), 256)
+    assert list(sha256_prefix_chain_lazy(toks[:0], 256)) == []
