@@ -102,7 +102,7 @@ def main(args):
 
     c4 = args.config == "c4"
     T = 16384 if c4 else 4096
-    n_seq = (4 if c4 else 16)
+    n_seq = (8 if c4 else 16)                   # c4: enough prompts for a stable median (the wire's share of a retrieve varies)
     if args.tokens not in (8192, T):
         T = args.tokens                         # smaller shapes for smoke runs
     raw_seq = L * 2 * T * C * 2

@@ -45,6 +45,10 @@ class SlabBlock:
     def free(self) -> None:
         self.slab.free(self)
 
+    def shrink(self, nbytes: int) -> None:
+        """Give the tail back: a receive buffer is reserved for the largest possible payload and usually holds far less."""
+        self.slab.shrink(self, nbytes)
+
 
 class _FreeList:
     """Sorted, coalescing list of free extents of one segment."""
@@ -121,6 +125,15 @@ class PinnedSlab:
             off = self._free[s].take(cap)
             self.bytes_in_use += cap
             return SlabBlock(self, s, off, int(nbytes), cap)
+
+    def shrink(self, blk: SlabBlock, nbytes: int) -> None:
+        keep = max(ALIGN, (int(nbytes) + ALIGN - 1) // ALIGN * ALIGN)
+        with self._lock:
+            if blk.cap and keep < blk.cap:
+                self._free[blk.seg].give(blk.offset + keep, blk.cap - keep)
+                self.bytes_in_use -= blk.cap - keep
+                blk.cap = keep
+                blk.nbytes = min(blk.nbytes, keep)
 
     def free(self, blk: SlabBlock) -> None:
         with self._lock:

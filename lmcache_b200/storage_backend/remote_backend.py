@@ -282,6 +282,7 @@ class LMCRemoteBackend(LMCBackendInterface):
         if not n:
             blk.free()
             return None
+        blk.shrink(int(n))                      # the bound covers the largest container version; a v3 one is a tenth of it
         return blk, int(n)
 
     def peek_geometry(self, key: CacheEngineKey, fmt: str = "vllm"):
@@ -294,6 +295,8 @@ class LMCRemoteBackend(LMCBackendInterface):
         try:
             n = self.connection.get_into(self._combine_key(key), blk.host_ptr, blk.cap)
             hd = parse_header(blk.view()[:n]) if n else None
+            if n:
+                blk.shrink(int(n))
         except Exception:       # noqa: BLE001 -- broken connection / damaged container: a miss
             hd = None
         if hd is None:

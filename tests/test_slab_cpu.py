@@ -67,3 +67,18 @@ def test_slab_random_stress_no_overlap():
     assert slab.stats()[2] == 0
     for fl, seg in zip(slab._free, slab._segs):
         assert fl.offs == [0] and fl.lens == [seg.nbytes]
+
+
+def test_shrink_returns_the_tail():
+    """a receive block is reserved for the largest possible container and trimmed to what arrived"""
+    slab = PinnedSlab(segment_bytes=1 << 20, alloc_fn=_FakeSeg)
+    a = slab.alloc(600_000)
+    used = slab.bytes_in_use
+    a.shrink(10_000)
+    assert slab.bytes_in_use < used and 10_000 <= a.cap < 600_000 and a.nbytes <= a.cap
+    b = slab.alloc(500_000)                    # fits next to it in the same 1 MiB segment only after the shrink
+    assert b.seg == a.seg
+    a.shrink(1_000_000)                        # growing is not a thing: no-op
+    a.free()
+    b.free()
+    assert slab.bytes_in_use == 0
