@@ -988,7 +988,7 @@ __device__ __forceinline__ void copy_row_rans(uint8_t* d, const uint32_t* row, u
 // (collect_bytes, cachegen_encoder.py:225-238).  Each thread copies its own stream into a shared-memory image of the
 // tile's byte range (placed at the destination's 16-byte phase), then the CTA writes that range with 16-byte vector
 // stores: the payload is written as full sectors no matter how short the individual streams are.
-__global__ void __launch_bounds__(CT, 9) compact_kernel(EncParams P) {
+__global__ void __launch_bounds__(CT, 12) compact_kernel(EncParams P) {
     extern __shared__ __align__(16) uint8_t stage[];      // 16 + CT * tempw * 4 bytes
     __shared__ uint32_t s_warp[CT / 32];
     const int tid = threadIdx.x;
@@ -1840,6 +1840,14 @@ int b200kv_encode_chunks(const b200kv_kv_desc* kv, int64_t tok_begin, int32_t n_
         // reach 128 x 528 B, but sizing the stage for that would leave 3 CTAs per SM for streams that are typically
         // a few dozen bytes long -- oversized tiles take the direct path inside the kernel
         P.stage_bytes = coder == CODER_RANS ? CT * (TEMPW_FUSED_RANS * 4 + 4) + 32 : CT * TEMPW_FUSED * 4 + 32;
+        // The kernel waits on sparse row reads: more resident CTAs hide more of that latency.  Without the high-entropy
+        // hint a tile's streams total a few KB, so a 12 KB stage (12+ CTAs per SM instead of 9) covers them; the rare
+        // larger tile takes the kernel's direct path.  B200KV_COMPACT_STAGE=<bytes> overrides (measurement knob).
+        if (coder == CODER_RANS && !hint_tma) P.stage_bytes = 12 * 1024;
+        if (const char* e = getenv("B200KV_COMPACT_STAGE")) {
+            const int v = atoi(e);
+            if (v >= 1024 && v <= P.stage_bytes + 16 * 1024) P.stage_bytes = v & ~15;
+        }
         B2_CHECK_CUDA(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.stage_bytes));
         enc_scan_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(P);
         compact_kernel<<<(unsigned)n_tiles, CT, (size_t)P.stage_bytes, stream>>>(P);
