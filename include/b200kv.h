@@ -44,6 +44,8 @@ extern "C" {
                                                * payload bits per symbol (e.g. the previous call's sizes said so); selects the
                                                * TMA-staged encode kernel whose time does not grow with entropy.  Output bytes
                                                * are identical either way. */
+#define B200KV_ENCODE_HINT_MID_ENTROPY 0x200  /* likewise: more than ~1.2 payload bits per symbol expected -- the compaction
+                                               * kernel then keeps its full-size shared-memory stage (tiles of 10+ KB) */
 #define B200KV_LP 33            /* CDF entries per stream (cachegen_encoder.py:287-289: int(bins.max()) + 1) */
 #define B200KV_GROUP_TOKENS 256 /* CACHEGEN_GPU_MAX_TOKENS_PER_CHUNK (cachegen_basics.py:13) */
 #define B200KV_MAX_PLANES 128   /* 2 * nlayers upper bound */
