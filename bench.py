@@ -615,11 +615,12 @@ def run_e2e(args, kv, dev, world, rank, barrier):
            "host_tier_bytes": host_bytes, "slab_segments": backend.slab.stats()[0],
            "device_scratch_bytes": {"encode_ring": ring.scratch_bytes() if ring else None,
                                     "wave_chunks": ring.wave if ring else None},
-           "path": "LMCacheEngine.store(tokens, kv_tuple, blocking=True) [sha256 chain -> waves: b200kv_encode_chunks on the "
-                   "caller's stream || device->host of the previous wave's containers into the page-locked slab] then "
-                   "LMCacheEngine.retrieve(tokens) [sha256 chain -> waves: host->device of containers || "
-                   "b200kv_decode_chunks into one blob]; KV starts and ends on the GPU (retrieve returns CUDA tensors, "
-                   "4 KiB of the result is read back); wall clock incl. every copy and host-side step"}
+           "path": "LMCacheEngine.store(tokens, kv_tuple, blocking=True) [sha256 chain on its own stream, keys consumed as "
+                   "they appear || waves: b200kv_encode_chunks on the caller's stream || device->host of the previous wave's "
+                   "containers into the page-locked slab] then LMCacheEngine.retrieve(tokens) [sha256 chain || per wave of "
+                   "keys: host->device of containers || b200kv_decode_chunks into one blob]; KV starts and ends on the GPU "
+                   "(retrieve returns CUDA tensors, 4 KiB of the result is read back); wall clock incl. every copy and "
+                   "host-side step"}
     # the round-1 variant: the raw KV is first uploaded from page-locked host memory (not part of store(); PCIe-bound)
     if world == 1 and raw_bytes <= (8 << 30):
         host_raw = PinnedBuffer(raw_bytes)
