@@ -54,6 +54,9 @@ def parse_args():
                     help="c2 = BASELINE configs[1] (default, the BENCH/SCALE line); c4 / c5 = configs[3] / [4] (see c45_bench.py)")
     ap.add_argument("--wave", type=int, default=8, help="chunks per wave of the device-timed step")
     ap.add_argument("--no-sweep", action="store_true", help="skip config.entropy_sweep")
+    ap.add_argument("--pipelined", action="store_true",
+                    help="device step on TWO streams: the decode of wave k runs under the encode of wave k + 1 (measured: +1.4 %%; "
+                         "default: one stream, so that the per-kernel times add up to the step)")
     ap.add_argument("--data", default="kv8d", choices=list(DATA_KINDS), help="synthetic KV distribution (kv8d = SURVEY 8d, the headline)")
     ap.add_argument("--coder", default="rans_compact", choices=["rans_compact", "rans", "ac"],
                     help="container: rans_compact = v3 (default: rANS + symbol counts), rans = v2 (rANS + CDF rows), ac = v1")
@@ -333,8 +336,14 @@ def main():
     out_view = KvView.from_blob(out, "vllm")
     stride = codec.out_stride(L, H, D, cs)
     W = max(1, min(args.wave, n_chunks))
-    staging = torch.empty(stride * W + N.READ_SLACK, dtype=torch.uint8, device=dev)      # ONE wave, reused in stream order
+    # one wave of containers, reused in stream order.  --pipelined: two buffers, the decode of wave k (second stream) runs
+    # while wave k + 1 is being encoded (first stream), so the kernels' last, partly filled rounds of CTAs overlap
+    pipelined = args.pipelined
+    stagings = [torch.empty(stride * W + N.READ_SLACK, dtype=torch.uint8, device=dev) for _ in range(2 if pipelined else 1)]
+    staging = stagings[0]
     stream = torch.cuda.current_stream()
+    dstream = torch.cuda.Stream(device=dev) if pipelined else None
+    dec_done = [None, None]
     ws_enc = lib.b200kv_encode_workspace_bytes(L, H, D, cs, W, codec.coder_for(cs))
     ws_dec = lib.b200kv_decode_workspace_bytes(L, H, D, cs, W)
 
@@ -346,13 +355,25 @@ def main():
     def step_device(collect=None):
         """encode -> decode, wave by wave on one stream; the decoder takes the slot bound as each container's extent, so
         nothing in the step waits for the host"""
-        for c0, k, nt in waves():
-            ticket = codec.encode_async(view, c0 * cs, nt, cs, out=staging)
+        for w, (c0, k, nt) in enumerate(waves()):
+            buf = stagings[w % len(stagings)]
+            if pipelined and dec_done[w & 1] is not None:
+                stream.wait_event(dec_done[w & 1])                 # the decode that last read this buffer
+            ticket = codec.encode_async(view, c0 * cs, nt, cs, out=buf)
             if collect is not None:
                 collect(ticket, c0, k)
-            codec.decode_raw(staging.data_ptr(), staging.numel(), [j * stride for j in range(k)], [stride] * k,
+            if pipelined:
+                dstream.wait_event(ticket.event)
+            codec.decode_raw(buf.data_ptr(), buf.numel(), [j * stride for j in range(k)], [stride] * k,
                              [min(cs, T - (c0 + j) * cs) for j in range(k)], out_view, [(c0 + j) * cs for j in range(k)],
-                             N.DT_BF16, codec.coder_for(cs))
+                             N.DT_BF16, codec.coder_for(cs), dstream)
+            if pipelined:
+                dec_done[w & 1] = torch.cuda.Event()
+                dec_done[w & 1].record(dstream)
+        if pipelined:                                              # the step ends when its last decodes do
+            for ev in dec_done:
+                if ev is not None:
+                    stream.wait_event(ev)
 
     def measure_sizes():
         """container sizes of the resident block; also picks the decoder's table layout the way the product does from
@@ -503,7 +524,7 @@ def main():
     # ---- e2e through LMCacheEngine.store()/retrieve() with the compressed host tier
     e2e = None
     if not args.no_e2e:
-        del out, out_view, staging
+        del out, out_view, staging, stagings
         torch.cuda.empty_cache()
         if sweep is not None:
             kv = synth_kv_torch(T, dev, 1234 + 2 + rank, args.data)
@@ -532,7 +553,10 @@ def main():
                                        "in front of its rANS bytes; coder_bits_per_symbol in entropy_sweep = the rANS bytes alone"
                        if codec_v2 is not None else "payload = the coder's bytes (histograms live in the CDF section)",
                        "wave_chunks": W,
-                       "device_scratch_bytes": {"staging": staging_bytes(stride, W, N), "encode_workspace": int(ws_enc),
+                       "streams": ("2: encode waves on one, each wave's decode on the other (the decode of wave k runs under the "
+                                   "encode of wave k + 1); roofline.kernels are per-kernel times measured one kernel at a time, so "
+                                   "they may sum to slightly more than ms_per_step") if pipelined else "1",
+                       "device_scratch_bytes": {"staging": staging_bytes(stride, W, N) * len(stagings), "encode_workspace": int(ws_enc),
                                                                   "decode_workspace": int(ws_dec)},
                        "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity,
                        "decode_status_words_nonzero": sum(1 for w in status_words if w),
