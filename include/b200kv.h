@@ -32,7 +32,8 @@ extern "C" {
 #endif
 
 #define B200KV_VERSION 4           /* ABI version; 2: b200kv_kv_desc.slot_map; 3: coder selection, decode status, total_bytes;
-                                    * 4: compact container (B200KV_CODER_RANS_COMPACT), b200kv_container_layout_v */
+                                    * 4: compact container (B200KV_CODER_RANS_COMPACT), b200kv_container_layout_v,
+                                    *    b200kv_sha256_chain_ready */
 #define B200KV_CODER_AC 0          /* payload = torchac-lineage arithmetic coder; container version 1 */
 #define B200KV_CODER_RANS 1        /* payload = rANS, 32-bit state / 16-bit renormalisation; container version 2 */
 #define B200KV_CODER_RANS_COMPACT 2 /* rANS as in version 2, compact side information; container version 3 (chunks of
