@@ -5,7 +5,11 @@
 //           torchac_cuda calls, collect_bytes and the pickle container (cachegen_basics.py:131-136)
 //   decode: lmcache/storage_backend/serde/cachegen_decoder.py:52-106,143-202
 //
-// Thread mapping: one arithmetic-coder stream = one (plane nl, channel c) = one thread; a CTA owns a
+// Three container versions share these kernels (include/b200kv.h): 1 = arithmetic coder, 2 = rANS, both with the
+// reference's CDF tensor as a section; 3 (default) = rANS streams that carry their own symbol histogram, from which the
+// decoder rebuilds the CDF (ac_core.cuh: stream header).
+//
+// Thread mapping: one entropy-coder stream = one (plane nl, channel c) = one thread; a CTA owns a
 // tile of CT consecutive channels of one plane (and one <=256-token group).  Global KV reads/writes are
 // then naturally coalesced along the channel dimension (a warp touches 64 contiguous bytes per token)
 // and the tile's byte streams are contiguous in the container.  The coder writes each stream to a temp
