@@ -524,7 +524,8 @@ def main():
     # ---- e2e through LMCacheEngine.store()/retrieve() with the compressed host tier
     e2e = None
     if not args.no_e2e:
-        del out, out_view, staging, stagings
+        del out, out_view, staging
+        stagings.clear()                     # frees the buffers; the list itself is still asked for its former length below
         torch.cuda.empty_cache()
         if sweep is not None:
             kv = synth_kv_torch(T, dev, 1234 + 2 + rank, args.data)
@@ -556,7 +557,7 @@ def main():
                        "streams": ("2: encode waves on one, each wave's decode on the other (the decode of wave k runs under the "
                                    "encode of wave k + 1); roofline.kernels are per-kernel times measured one kernel at a time, so "
                                    "they may sum to slightly more than ms_per_step") if pipelined else "1",
-                       "device_scratch_bytes": {"staging": staging_bytes(stride, W, N) * len(stagings), "encode_workspace": int(ws_enc),
+                       "device_scratch_bytes": {"staging": staging_bytes(stride, W, N) * (2 if pipelined else 1), "encode_workspace": int(ws_enc),
                                                                   "decode_workspace": int(ws_dec)},
                        "l2": "inputs (4 GiB) exceed the 126 MB L2; no flush needed", "parity_spot_check": parity,
                        "decode_status_words_nonzero": sum(1 for w in status_words if w),
