@@ -107,6 +107,13 @@ def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321, coder=0):
     workload.  Threads are pinned (OMP_PROC_BIND=close, OMP_PLACES=cores, set before libgomp starts) and the sample's
     buffers are first touched by the timed thread team's own warm-up passes, so the figure does not depend on where the
     kernel happened to place threads and pages.  Returns (raw GB/s from the MEDIAN step, seconds [median, min], cores)."""
+    # the CPUs this process may use -- asked BEFORE any OpenMP runtime starts: with OMP_PROC_BIND the runtime binds the
+    # initial thread to its first place, after which sched_getaffinity() of that thread reports one core (round 2 found the
+    # reference arm running on 2 threads of a 128-thread host that way)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
     os.environ.setdefault("OMP_DYNAMIC", "false")
@@ -115,10 +122,6 @@ def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321, coder=0):
 
     from oracle import oracle as O
     O.build()
-    try:
-        ncpu = len(os.sched_getaffinity(0))
-    except AttributeError:
-        ncpu = os.cpu_count() or 1
     cores = O.set_threads(ncpu)          # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
     torch.set_num_threads(ncpu)
     kv = synth_kv_torch(n_chunks * chunk, "cpu", seed)
