@@ -123,6 +123,16 @@ def cpu_codec_sample(n_chunks, chunk, steps, warmup, seed=4321, coder=0):
     from oracle import oracle as O
     O.build()
     cores = O.set_threads(ncpu)          # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
+    # every chunk allocates ~400 MB of numpy temporaries; by default glibc mmaps and unmaps each of them, and at 128 threads
+    # the page faults -- not the coder -- bound the arm.  Keep freed blocks in the heap so that the timed passes reuse the
+    # pages their warm-up passes touched.
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 1 << 30)                     # M_MMAP_THRESHOLD
+        libc.mallopt(-1, ctypes.c_int(2 ** 31 - 1))   # M_TRIM_THRESHOLD
+    except OSError:
+        pass
     torch.set_num_threads(ncpu)
     kv = synth_kv_torch(n_chunks * chunk, "cpu", seed)
     bits = kv.view(torch.int16).numpy().view(np.uint16).reshape(L, 2, n_chunks * chunk, C)

@@ -252,7 +252,10 @@ def encode_chunk(x_bits: np.ndarray, dtype: int, key_bins, value_bins, coder: in
         g = min(GROUP, t - tok0)
         bs, ln = encode_group(c, sym, tok0, g, coder)
         groups.append((bs, ln, g))
-    return dict(cdf=c, maxes=maxes, groups=groups, sym=sym, coder=coder, counts=counts(sym))
+    out = dict(cdf=c, maxes=maxes, groups=groups, sym=sym, coder=coder)
+    if coder == CODER_RANS_COMPACT:          # only a version-3 container stores the histogram (keeps the timed CPU arm lean)
+        out["counts"] = counts(sym)
+    return out
 
 
 def decode_chunk(enc: dict, max_dtype: int, key_bins, value_bins, out_dtype: int) -> np.ndarray:

@@ -65,7 +65,7 @@ if role == "writer":
         mv = torch.from_numpy(enc["maxes"][1].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
         raw = CacheGenGPUEncoderOutput([CacheGenGPUBytestream(torch.from_numpy(b), torch.from_numpy(ln), g) for b, ln, g in enc["groups"]],
                                        torch.from_numpy(enc["cdf"]), mk, mv, H, D, coder,
-                                       torch.from_numpy(enc["counts"].astype(np.int32)), O.nb_map(kb, vb, L)).to_bytes()
+                                       torch.from_numpy(O.counts(enc["sym"]).astype(np.int32)), O.nb_map(kb, vb, L)).to_bytes()
         assert raw[4] == coder + 1
         conn.set(key, raw)
     assert conn.exists(keys[-1]) or True          # one round trip: the server has consumed the PUTs before it

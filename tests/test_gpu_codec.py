@@ -135,7 +135,7 @@ def test_oracle_made_container_decodes_on_gpu(codec, golden, name):
     mv = torch.from_numpy(enc["maxes"][1].view(np.int16)).view(torch.bfloat16).reshape(L, t, 1)
     raw = CacheGenGPUEncoderOutput(
         [CacheGenGPUBytestream(torch.from_numpy(b), torch.from_numpy(ln), g) for b, ln, g in enc["groups"]],
-        torch.from_numpy(enc["cdf"]), mk, mv, H, D, codec.coder_for(t), torch.from_numpy(enc["counts"].astype(np.int32)),
+        torch.from_numpy(enc["cdf"]), mk, mv, H, D, codec.coder_for(t), torch.from_numpy(O.counts(enc["sym"]).astype(np.int32)),
         O.nb_map(golden["key_bins"], golden["value_bins"], L)).to_bytes()
     assert raw[4] == codec.coder_for(t) + 1
     out = torch.zeros((L, 2, t, H, D), dtype=torch.bfloat16, device="cuda")
