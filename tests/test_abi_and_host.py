@@ -259,3 +259,36 @@ def test_lazy_sequence_semantics():
     with pytest.raises(IndexError):
         s[10]
     assert list(LazySeq(None, [])) == []
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_v3_stream_framing_product_vs_oracle_random(seed):
+    """The host shim's vectorised version-3 stream packer / parser against the oracle's plain C ones on random histograms
+    of every density (1 .. nb - 1 symbols in use, incl. lone symbols with 256 tokens), mixed plane widths, random rANS
+    bytes: both directions byte-identical."""
+    import numpy as np
+    from lmcache_b200.storage_backend.serde.cachegen_basics import _v3_build_streams, _v3_parse_streams
+    from oracle import oracle as O
+    rng = np.random.default_rng(seed)
+    nb = [32, 16, 8, 30, 16, 32]
+    C, t = 37, int(rng.integers(1, 257))
+    NL = len(nb)
+    cnt = np.zeros((NL, C, 33), np.uint32)
+    for nl in range(NL):
+        for c in range(C):
+            k = int(rng.integers(1, min(nb[nl] - 1, t) + 1))
+            syms = rng.choice(nb[nl] - 1, size=k, replace=False)
+            cnt[nl, c, syms] = 1
+            extra = rng.multinomial(t - k, np.ones(k) / k)
+            cnt[nl, c, syms] += extra.astype(np.uint32)
+    assert np.all(cnt.sum(axis=2) == t)
+    rlen = (4 + 2 * rng.integers(0, 40, size=(NL, C))).astype(np.int32)
+    rans = rng.integers(0, 256, size=int(rlen.sum()), dtype=np.uint8)
+    pl_o, half_o = O.v3_pack(cnt, nb, rlen, rans)
+    pl_p, half_p = _v3_build_streams(cnt.reshape(NL * C, 33).astype(np.int32), nb, C, rlen.reshape(-1), rans)
+    assert pl_p.tobytes() == pl_o.tobytes() and half_p.tobytes() == half_o.reshape(-1).tobytes()
+    c2, l2, r2 = _v3_parse_streams(pl_o, half_o.reshape(-1), nb, C, t)
+    c3, l3, r3 = O.v3_unpack(pl_o, half_o, nb, t)
+    assert np.array_equal(c2.reshape(NL, C, 33), cnt.astype(np.int32)) and np.array_equal(c3, cnt)
+    assert np.array_equal(l2.reshape(NL, C), rlen) and np.array_equal(l3, rlen)
+    assert r2.tobytes() == rans.tobytes() == r3.tobytes()
